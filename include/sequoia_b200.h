@@ -1,0 +1,80 @@
+/* sequoia_b200 — C ABI of the B200-native SEQUOIA hot paths.
+ *
+ * The reference (gevaertlab/sequoia-pub) has no native code and no FFI: its "plugin API" for these
+ * paths is the Python nn.Module surface.  This header is the boundary a replacement
+ * sits behind: plain C types, raw device pointers, explicit sizes, a CUDA stream handle.  Every entry
+ * point cites the reference interface it replaces.
+ *
+ * Conventions
+ *   - return 0 on success, negative on error; sq_last_error() returns a thread-local message;
+ *   - no C++ exception crosses the boundary, nothing here allocates memory the caller cannot see:
+ *     workspaces are sized by the *_workspace_bytes functions and passed in;
+ *   - every function ENQUEUES on `stream` (a cudaStream_t passed as void*) and never synchronises;
+ *   - all pointers are device pointers unless the name says `host`;
+ *   - "planes": an fp32 matrix split as hi = bf16(x), lo = bf16(x - hi); the tensor-core GEMMs use
+ *     hi*hi + hi*lo + lo*hi to keep fp32 parity.
+ */
+#ifndef SEQUOIA_B200_H
+#define SEQUOIA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define SQ_API __attribute__((visibility("default")))
+#else
+#define SQ_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ library */
+SQ_API int sq_version(void);
+SQ_API const char* sq_last_error(void);
+/* 0 when the current device is an sm_100 part; the product path refuses to run otherwise. */
+SQ_API int sq_device_ok(void);
+
+/* ------------------------------------------------------------------ building blocks (exposed for tests) */
+
+/* fp32 [rows, cols] (row stride ld_in) -> bf16 hi / lo planes (row stride ld_out); lo may be NULL. */
+SQ_API int sq_split_bf16(const float* x, void* hi, void* lo, long long rows, int cols, long long ld_in, long long ld_out,
+                  void* stream);
+
+enum { SQ_ACT_NONE = 0, SQ_ACT_RELU = 1, SQ_ACT_GELU = 2, SQ_ACT_LN64_GELU = 3, SQ_ACT_MUL_DGELU = 4 };
+
+/* One tcgen05 GEMM / implicit-GEMM convolution launch with its fused epilogue.
+ *   C[M,N] = alpha * sum_terms A[M,K] * B[N,K]^T, then bias / rowbias / residual / activation.
+ * Replaces every torch.nn.Linear / nn.Conv2d library call on the hot path
+ * (src/tformer_lin.py:14-16,37,55-58,93; src/resnet.py:60-68,101,124-128). */
+typedef struct sq_gemm_desc {
+    int M, N, K;
+    const void* a_hi; const void* a_lo; int a_mn_major; long long lda;
+    const void* b_hi; const void* b_lo; int b_mn_major; long long ldb;
+    int nterms;            /* 1 = plain bf16, 3 = split precision */
+    int split_k;           /* >1: partials go to workspace, a second kernel reduces + applies the epilogue */
+    int block_n;           /* 0 = auto, else 64 / 128 / 256 */
+    int a_koff_per_ntile;  /* block-diagonal mode (per-head 64x64 mixing weights) */
+    void* workspace; size_t workspace_bytes;
+    /* conv mode: A is an NHWC bf16 tensor, B is [Cout][R][S][Cin] */
+    int conv_enabled, conv_batch, conv_H, conv_W, conv_C, conv_Ho, conv_Wo, conv_R, conv_S, conv_stride, conv_pad;
+    /* epilogue */
+    float* out_f32; long long ld_f32;
+    void* out_hi; void* out_lo; long long ld_bf;
+    const float* bias;
+    const float* rowbias; int rowbias_div; long long ld_rowbias;
+    const float* res_f32; const void* res_bf; long long ld_res;
+    float* save_pre; long long ld_pre;
+    const float* aux; long long ld_aux;
+    const float* ln_gamma; const float* ln_beta;
+    int act;
+    float alpha;           /* 0 is read as 1 */
+} sq_gemm_desc;
+
+SQ_API int sq_gemm_bf16(const sq_gemm_desc* desc, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEQUOIA_B200_H */

@@ -1,0 +1,83 @@
+"""ctypes binding of libsequoia_b200.so (the C ABI declared in include/sequoia_b200.h).
+
+There is no fallback: if the shared library is missing the import of any product module fails,
+and every call that returns non-zero raises RuntimeError(sq_last_error()).
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsequoia_b200.so")
+
+c_void_p, c_int, c_ll, c_float, c_size_t = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_size_t
+
+
+class GemmDesc(C.Structure):
+    """Mirror of `sq_gemm_desc`."""
+    _fields_ = [
+        ("M", c_int), ("N", c_int), ("K", c_int),
+        ("a_hi", c_void_p), ("a_lo", c_void_p), ("a_mn_major", c_int), ("lda", c_ll),
+        ("b_hi", c_void_p), ("b_lo", c_void_p), ("b_mn_major", c_int), ("ldb", c_ll),
+        ("nterms", c_int), ("split_k", c_int), ("block_n", c_int), ("a_koff_per_ntile", c_int),
+        ("workspace", c_void_p), ("workspace_bytes", c_size_t),
+        ("conv_enabled", c_int), ("conv_batch", c_int), ("conv_H", c_int), ("conv_W", c_int), ("conv_C", c_int),
+        ("conv_Ho", c_int), ("conv_Wo", c_int), ("conv_R", c_int), ("conv_S", c_int), ("conv_stride", c_int),
+        ("conv_pad", c_int),
+        ("out_f32", c_void_p), ("ld_f32", c_ll),
+        ("out_hi", c_void_p), ("out_lo", c_void_p), ("ld_bf", c_ll),
+        ("bias", c_void_p),
+        ("rowbias", c_void_p), ("rowbias_div", c_int), ("ld_rowbias", c_ll),
+        ("res_f32", c_void_p), ("res_bf", c_void_p), ("ld_res", c_ll),
+        ("save_pre", c_void_p), ("ld_pre", c_ll),
+        ("aux", c_void_p), ("ld_aux", c_ll),
+        ("ln_gamma", c_void_p), ("ln_beta", c_void_p),
+        ("act", c_int), ("alpha", c_float),
+    ]
+
+
+# name -> (restype, argtypes); kept in one table so tests can check the export list against the header
+SIGNATURES = {
+    "sq_version": (c_int, []),
+    "sq_last_error": (C.c_char_p, []),
+    "sq_device_ok": (c_int, []),
+    "sq_split_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_ll, c_int, c_ll, c_ll, c_void_p]),
+    "sq_gemm_bf16": (c_int, [C.POINTER(GemmDesc), c_void_p]),
+}
+
+_lib = None
+
+
+def lib():
+    """Loads the shared library (once). Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(sequoia_b200 has no CPU / PyTorch fallback)")
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise RuntimeError("sequoia_b200: " + lib().sq_last_error().decode("utf-8", "replace"))
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None)."""
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_device():
+    check(lib().sq_device_ok())

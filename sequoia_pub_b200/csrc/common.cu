@@ -1,0 +1,110 @@
+// Library-wide plumbing: error string, SM count, driver entry point for tensor-map encoding,
+// and the generic GEMM / plane-split entry points of the C ABI (include/sequoia_b200.h).
+#include "gemm.cuh"
+#include "../../include/sequoia_b200.h"
+#include <stdarg.h>
+
+namespace sq {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
+PFN_encodeTiled get_encode_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    }
+    return fn;
+}
+
+// fp32 [rows, cols] (ld_in) -> bf16 hi / lo planes (ld_out); lo may be null
+__global__ void split_planes_kernel(const float* __restrict__ x, bf16* __restrict__ hi, bf16* __restrict__ lo, long long rows,
+                                    int cols, long long ld_in, long long ld_out) {
+    const long long n = rows * cols;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / cols; const int c = (int)(i - r * cols);
+        const float v = x[r * ld_in + c];
+        const bf16 h = __float2bfloat16_rn(v);
+        hi[r * ld_out + c] = h;
+        if (lo) lo[r * ld_out + c] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+}
+
+int split_planes(const float* x, bf16* hi, bf16* lo, long long rows, int cols, long long ld_in, long long ld_out, cudaStream_t st) {
+    const long long n = rows * cols;
+    if (n == 0) return 0;
+    long long blocks = (n + 255) / 256;
+    if (blocks > 148LL * 16) blocks = 148LL * 16;
+    split_planes_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, hi, lo, rows, cols, ld_in, ld_out);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) { set_error("split_planes: %s", cudaGetErrorString(err)); return -1; }
+    return 0;
+}
+
+}  // namespace sq
+
+using namespace sq;
+
+extern "C" {
+
+int sq_version(void) { return 100; }
+
+const char* sq_last_error(void) { return g_err; }
+
+int sq_device_ok(void) {
+    int dev = 0; cudaDeviceProp prop;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) { set_error("no CUDA device"); return -1; }
+    if (prop.major != 10) { set_error("sequoia_b200 needs an sm_100 device, found sm_%d%d", prop.major, prop.minor); return -2; }
+    return 0;
+}
+
+int sq_split_bf16(const float* x, void* hi, void* lo, long long rows, int cols, long long ld_in, long long ld_out, void* stream) {
+    return split_planes(x, (bf16*)hi, (bf16*)lo, rows, cols, ld_in, ld_out, (cudaStream_t)stream);
+}
+
+int sq_gemm_bf16(const sq_gemm_desc* d, void* stream) {
+    if (!d) { set_error("null desc"); return -1; }
+    GemmArgs g;
+    memset(&g, 0, sizeof(g));
+    g.M = d->M; g.N = d->N; g.K = d->K;
+    g.A.hi = (const bf16*)d->a_hi; g.A.lo = (const bf16*)d->a_lo; g.A.mn_major = d->a_mn_major; g.A.ld = d->lda;
+    g.B.hi = (const bf16*)d->b_hi; g.B.lo = (const bf16*)d->b_lo; g.B.mn_major = d->b_mn_major; g.B.ld = d->ldb;
+    g.nterms = d->nterms; g.split_k = d->split_k; g.block_n = d->block_n; g.a_koff_per_ntile = d->a_koff_per_ntile;
+    g.workspace = (float*)d->workspace; g.workspace_bytes = d->workspace_bytes;
+    if (d->conv_enabled) {
+        g.conv.enabled = 1; g.conv.batch = d->conv_batch; g.conv.H = d->conv_H; g.conv.W = d->conv_W; g.conv.C = d->conv_C;
+        g.conv.Ho = d->conv_Ho; g.conv.Wo = d->conv_Wo; g.conv.R = d->conv_R; g.conv.S = d->conv_S; g.conv.stride = d->conv_stride; g.conv.pad = d->conv_pad;
+    }
+    g.e.out_f32 = d->out_f32; g.e.ld_f32 = d->ld_f32;
+    g.e.out_hi = (bf16*)d->out_hi; g.e.out_lo = (bf16*)d->out_lo; g.e.ld_bf = d->ld_bf;
+    g.e.bias = d->bias;
+    g.e.rowbias = d->rowbias; g.e.rowbias_div = d->rowbias_div > 0 ? d->rowbias_div : 1; g.e.ld_rowbias = d->ld_rowbias;
+    g.e.res_f32 = d->res_f32; g.e.res_bf = (const bf16*)d->res_bf; g.e.ld_res = d->ld_res;
+    g.e.save_pre = d->save_pre; g.e.ld_pre = d->ld_pre;
+    g.e.aux = d->aux; g.e.ld_aux = d->ld_aux;
+    g.e.ln_gamma = d->ln_gamma; g.e.ln_beta = d->ln_beta;
+    g.e.act = d->act; g.e.alpha = d->alpha;
+    return gemm_launch(g, (cudaStream_t)stream);
+}
+
+}  // extern "C"

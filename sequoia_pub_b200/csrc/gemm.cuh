@@ -1,0 +1,589 @@
+// Persistent, warp-specialised tcgen05 GEMM / implicit-GEMM convolution for sm_100a.
+//
+//   C[M,N] = sum_terms A_t[M,K] * B_t[N,K]^T        (bf16 operands, fp32 accumulation in TMEM)
+//
+// * operands are staged by TMA into 128B-swizzled shared memory, either K-major ([MN][K] row-major)
+//   or MN-major ([K][MN] row-major) so dgrad/wgrad need no explicit transposes;
+// * nterms == 3 is the split-precision mode (A_hi*B_hi + A_hi*B_lo + A_lo*B_hi) that keeps fp32
+//   parity on bf16 tensor cores;
+// * conv mode loads A as a 4-D NHWC box per filter tap (TMA zero-fills the padding halo);
+// * the accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1;
+// * the epilogue is fused: bias, per-slide row bias, residual, ReLU / exact GELU / per-head LayerNorm(64)+GELU /
+//   GELU', and writes any of fp32, bf16-hi, bf16-lo planes.
+//
+// Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
+// warps 4..7 = epilogue (TMEM lane quadrant = warp % 4).
+#pragma once
+#include "ptx.cuh"
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+namespace sq {
+
+typedef __nv_bfloat16 bf16;
+
+enum { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_LN64_GELU = 3, ACT_MUL_DGELU = 4 };
+
+struct EpiParams {
+    float* out_f32;     long long ld_f32;
+    bf16* out_hi;       bf16* out_lo;  long long ld_bf;
+    const float* bias;                       // [N], may be null
+    const float* rowbias; int rowbias_div; long long ld_rowbias;   // rowbias[(row / div) * ld + col]
+    const float* res_f32; const bf16* res_bf; long long ld_res;    // added before the activation
+    float* save_pre;    long long ld_pre;    // value just before the activation
+    const float* aux;   long long ld_aux;    // ACT_MUL_DGELU: out = v * gelu'(aux)
+    const float* ln_gamma; const float* ln_beta;  // ACT_LN64_GELU: per-column affine, groups of 64 columns
+    int act;
+    float alpha;                             // scales the accumulator first
+};
+
+struct GemmKParams {
+    int M, N;
+    int num_m, num_n;
+    int nk;        // 64-wide k-blocks per term
+    int nterms;    // 1 or 3
+    int split_k;   // >= 1
+    int kb_per_split;
+    int a_mn, b_mn;
+    int a_koff_per_ntile;   // block-diagonal mode: extra A k-offset per n-tile
+    // conv mode
+    int conv, cblocks, S, stride, pad, tiles_per_img, BH, BIMG;
+    float* partial;         // split-K workspace [split][M][N]
+    EpiParams e;
+};
+
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float dgelu_f(float x) {
+    const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+    const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
+    return cdf + x * pdf;
+}
+
+// Applies the fused epilogue to NC consecutive columns of one row and stores them.
+template <int NC>
+__device__ __forceinline__ void epilogue_apply(float* v, long long row, int col0, int N, const EpiParams& e) {
+    const int nvalid = min(NC, N - col0);
+    if (e.alpha != 1.0f) {
+#pragma unroll
+        for (int i = 0; i < NC; ++i) v[i] *= e.alpha;
+    }
+    if (e.bias) {
+#pragma unroll
+        for (int i = 0; i < NC; ++i)
+            if (i < nvalid) v[i] += __ldg(e.bias + col0 + i);
+    }
+    if (e.rowbias) {
+        const float* rb = e.rowbias + (row / e.rowbias_div) * e.ld_rowbias + col0;
+#pragma unroll
+        for (int i = 0; i < NC; ++i)
+            if (i < nvalid) v[i] += __ldg(rb + i);
+    }
+    if (e.res_f32) {
+        const float* r = e.res_f32 + row * e.ld_res + col0;
+        if (nvalid == NC && (e.ld_res & 3) == 0) {
+#pragma unroll
+            for (int i = 0; i < NC; i += 4) {
+                const float4 t = *reinterpret_cast<const float4*>(r + i);
+                v[i] += t.x; v[i + 1] += t.y; v[i + 2] += t.z; v[i + 3] += t.w;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < NC; ++i)
+                if (i < nvalid) v[i] += r[i];
+        }
+    }
+    if (e.res_bf) {
+        const bf16* r = e.res_bf + row * e.ld_res + col0;
+        if (nvalid == NC && (e.ld_res & 7) == 0) {
+#pragma unroll
+            for (int i = 0; i < NC; i += 8) {
+                const uint4 t = *reinterpret_cast<const uint4*>(r + i);
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 f = __bfloat1622float2(h[j]);
+                    v[i + 2 * j] += f.x; v[i + 2 * j + 1] += f.y;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < NC; ++i)
+                if (i < nvalid) v[i] += __bfloat162float(r[i]);
+        }
+    }
+    if (e.save_pre) {
+        float* s = e.save_pre + row * e.ld_pre + col0;
+        if (nvalid == NC && (e.ld_pre & 3) == 0) {
+#pragma unroll
+            for (int i = 0; i < NC; i += 4) *reinterpret_cast<float4*>(s + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < NC; ++i)
+                if (i < nvalid) s[i] = v[i];
+        }
+    }
+    if (e.act == ACT_RELU) {
+#pragma unroll
+        for (int i = 0; i < NC; ++i) v[i] = fmaxf(v[i], 0.0f);
+    } else if (e.act == ACT_GELU) {
+#pragma unroll
+        for (int i = 0; i < NC; ++i) v[i] = gelu_f(v[i]);
+    } else if (e.act == ACT_MUL_DGELU) {
+        const float* a = e.aux + row * e.ld_aux + col0;
+#pragma unroll
+        for (int i = 0; i < NC; ++i)
+            if (i < nvalid) v[i] *= dgelu_f(a[i]);
+    } else if (e.act == ACT_LN64_GELU) {
+        // per-head LayerNorm over groups of 64 columns (eps 1e-5, biased variance), then exact GELU
+        if constexpr (NC % 64 == 0) {
+#pragma unroll
+            for (int g = 0; g < NC; g += 64) {
+                float mean = 0.f;
+#pragma unroll
+                for (int i = 0; i < 64; ++i) mean += v[g + i];
+                mean *= (1.0f / 64.0f);
+                float var = 0.f;
+#pragma unroll
+                for (int i = 0; i < 64; ++i) { const float d = v[g + i] - mean; var += d * d; }
+                const float rstd = rsqrtf(var * (1.0f / 64.0f) + 1e-5f);
+#pragma unroll
+                for (int i = 0; i < 64; ++i) {
+                    const float xh = (v[g + i] - mean) * rstd;
+                    v[g + i] = gelu_f(xh * __ldg(e.ln_gamma + col0 + g + i) + __ldg(e.ln_beta + col0 + g + i));
+                }
+            }
+        }
+    }
+    if (e.out_f32) {
+        float* o = e.out_f32 + row * e.ld_f32 + col0;
+        if (nvalid == NC && (e.ld_f32 & 3) == 0) {
+#pragma unroll
+            for (int i = 0; i < NC; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < NC; ++i)
+                if (i < nvalid) o[i] = v[i];
+        }
+    }
+    if (e.out_hi) {
+        bf16* oh = e.out_hi + row * e.ld_bf + col0;
+        bf16* ol = e.out_lo ? e.out_lo + row * e.ld_bf + col0 : nullptr;
+        if (nvalid == NC && (e.ld_bf & 7) == 0) {
+#pragma unroll
+            for (int i = 0; i < NC; i += 8) {
+                uint4 ph, pl;
+                __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&ph);
+                __nv_bfloat162* ll = reinterpret_cast<__nv_bfloat162*>(&pl);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float a = v[i + 2 * j], b = v[i + 2 * j + 1];
+                    const bf16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
+                    hh[j] = __halves2bfloat162(ha, hb);
+                    ll[j] = __halves2bfloat162(__float2bfloat16_rn(a - __bfloat162float(ha)),
+                                               __float2bfloat16_rn(b - __bfloat162float(hb)));
+                }
+                *reinterpret_cast<uint4*>(oh + i) = ph;
+                if (ol) *reinterpret_cast<uint4*>(ol + i) = pl;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < NC; ++i)
+                if (i < nvalid) {
+                    const bf16 h = __float2bfloat16_rn(v[i]);
+                    oh[i] = h;
+                    if (ol) ol[i] = __float2bfloat16_rn(v[i] - __bfloat162float(h));
+                }
+        }
+    }
+}
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_A_BYTES = GEMM_BM * GEMM_BK * 2;  // 16 KB
+
+template <int BN> struct GemmCfg {
+    static constexpr int B_BYTES = BN * GEMM_BK * 2;
+    static constexpr int STAGE_BYTES = GEMM_A_BYTES + B_BYTES;
+    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
+};
+
+template <int BN>
+__global__ void __launch_bounds__(256, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+               const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB1,
+               const GemmKParams p) {
+    using Cfg = GemmCfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smemA = smem;
+    uint8_t* smemB = smem + STAGES * GEMM_A_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + STAGES;
+    uint64_t* tmem_full = bars + 2 * STAGES;
+    uint64_t* tmem_empty = bars + 2 * STAGES + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&mapA0); tma_prefetch_desc(&mapA1);
+        tma_prefetch_desc(&mapB0); tma_prefetch_desc(&mapB1);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+        mbar_fence_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    const int tiles_mn = p.num_m * p.num_n;
+    const int total_tiles = tiles_mn * p.split_k;
+    const int total_kb = p.nk * p.nterms;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            // ===================== TMA producer =====================
+            int stage = 0; uint32_t phase = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const int split = t / tiles_mn;
+                const int mn = t - split * tiles_mn;
+                const int mt = mn / p.num_n, nt = mn - mt * p.num_n;
+                const int kb0 = split * p.kb_per_split;
+                const int kb1 = min(kb0 + p.kb_per_split, total_kb);
+                const int m0 = mt * GEMM_BM, n0 = nt * BN;
+                int img = 0, hin0 = 0;
+                if (p.conv) {
+                    if (p.BIMG == 1) { img = mt / p.tiles_per_img; hin0 = (mt - img * p.tiles_per_img) * p.BH * p.stride - p.pad; }
+                    else { img = mt * p.BIMG; hin0 = -p.pad; }
+                }
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+                    const int kk = kb / p.nterms, term = kb - kk * p.nterms;
+                    const CUtensorMap* ma = (term == 2) ? &mapA1 : &mapA0;
+                    const CUtensorMap* mb = (term == 1) ? &mapB1 : &mapB0;
+                    uint8_t* sa = smemA + stage * GEMM_A_BYTES;
+                    uint8_t* sb = smemB + stage * Cfg::B_BYTES;
+                    const int k0 = kk * GEMM_BK;
+                    if (p.conv) {
+                        const int tap = kk / p.cblocks, cb = kk - tap * p.cblocks;
+                        const int r = tap / p.S, s = tap - r * p.S;
+                        tma_load_4d(ma, &full[stage], sa, cb * GEMM_BK, s - p.pad, hin0 + r, img);
+                    } else if (p.a_mn) {
+                        tma_load_2d(ma, &full[stage], sa, m0, k0);
+                        tma_load_2d(ma, &full[stage], sa + 8192, m0 + 64, k0);
+                    } else {
+                        tma_load_2d(ma, &full[stage], sa, k0 + nt * p.a_koff_per_ntile, m0);
+                    }
+                    if (p.b_mn) {
+#pragma unroll
+                        for (int a = 0; a < BN / 64; ++a) tma_load_2d(mb, &full[stage], sb + a * 8192, n0 + a * 64, k0);
+                    } else {
+                        tma_load_2d(mb, &full[stage], sb, k0, n0);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        const uint32_t idesc = make_idesc_bf16(BN, p.a_mn, p.b_mn);
+        const uint32_t a_kstep = p.a_mn ? 2048u : 32u, b_kstep = p.b_mn ? 2048u : 32u;
+        const uint32_t a_lbo = p.a_mn ? 8192u : 0u, b_lbo = p.b_mn ? 8192u : 0u;
+        int stage = 0; uint32_t phase = 0; int iter = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++iter) {
+            const int split = t / tiles_mn;
+            const int kb0 = split * p.kb_per_split;
+            const int kb1 = min(kb0 + p.kb_per_split, total_kb);
+            const int as = iter & 1; const uint32_t aphase = (iter >> 1) & 1;
+            mbar_wait(&tmem_empty[as], aphase ^ 1);
+            tc_fence_after();
+            const uint32_t tacc = tmem_base + as * BN;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t a_base = smem_u32(smemA + stage * GEMM_A_BYTES);
+                    const uint32_t b_base = smem_u32(smemB + stage * Cfg::B_BYTES);
+#pragma unroll
+                    for (int k = 0; k < GEMM_BK / 16; ++k) {
+                        const uint64_t da = make_smem_desc(a_base + k * a_kstep, 1024, a_lbo);
+                        const uint64_t db = make_smem_desc(b_base + k * b_kstep, 1024, b_lbo);
+                        umma_bf16(tacc, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty[stage]);
+                    if (kb == kb1 - 1) umma_commit(&tmem_full[as]);
+                }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int q = warp - 4;
+        int iter = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++iter) {
+            const int split = t / tiles_mn;
+            const int mn = t - split * tiles_mn;
+            const int mt = mn / p.num_n, nt = mn - mt * p.num_n;
+            const int as = iter & 1; const uint32_t aphase = (iter >> 1) & 1;
+            mbar_wait(&tmem_full[as], aphase);
+            tc_fence_after();
+            const long long row = (long long)mt * GEMM_BM + q * 32 + lane;
+            const int n0 = nt * BN;
+            const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+            const bool row_ok = row < p.M;
+            if (p.split_k > 1) {
+                float* dst = p.partial + ((long long)split * p.M + row) * p.N;
+                for (int c = 0; c < BN && n0 + c < p.N; c += 32) {
+                    float v[32];
+                    tmem_ld32(tacc + c, v);
+                    tmem_ld_wait();
+                    if (row_ok) {
+                        const int nvalid = min(32, p.N - n0 - c);
+                        for (int i = 0; i < nvalid; ++i) dst[n0 + c + i] = v[i];
+                    }
+                }
+            } else if (p.e.act == ACT_LN64_GELU) {
+                for (int c = 0; c < BN && n0 + c < p.N; c += 64) {
+                    float v[64];
+                    tmem_ld32(tacc + c, v);
+                    tmem_ld32(tacc + c + 32, v + 32);
+                    tmem_ld_wait();
+                    if (row_ok) epilogue_apply<64>(v, row, n0 + c, p.N, p.e);
+                }
+            } else {
+                for (int c = 0; c < BN && n0 + c < p.N; c += 32) {
+                    float v[32];
+                    tmem_ld32(tacc + c, v);
+                    tmem_ld_wait();
+                    if (row_ok) epilogue_apply<32>(v, row, n0 + c, p.N, p.e);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[as]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// Sums split-K partials and applies the fused epilogue. One thread per (row, 32-column chunk).
+__global__ void splitk_reduce_kernel(const float* __restrict__ partial, int splits, int M, int N, EpiParams e) {
+    const int chunks = (N + 31) / 32;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)M * chunks) return;
+    const int chunk = (int)(idx % chunks);
+    const long long row = idx / chunks;
+    const int col0 = chunk * 32;
+    const int nvalid = min(32, N - col0);
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = 0.f;
+    for (int s = 0; s < splits; ++s) {
+        const float* src = partial + ((long long)s * M + row) * N + col0;
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+            if (i < nvalid) v[i] += src[i];
+    }
+    epilogue_apply<32>(v, row, col0, N, e);
+}
+
+// Same, for the per-head LayerNorm(64)+GELU epilogue (needs whole 64-column groups).
+__global__ void splitk_reduce_ln64_kernel(const float* __restrict__ partial, int splits, int M, int N, EpiParams e) {
+    const int chunks = N / 64;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)M * chunks) return;
+    const int chunk = (int)(idx % chunks);
+    const long long row = idx / chunks;
+    const int col0 = chunk * 64;
+    float v[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) v[i] = 0.f;
+    for (int s = 0; s < splits; ++s) {
+        const float* src = partial + ((long long)s * M + row) * N + col0;
+#pragma unroll
+        for (int i = 0; i < 64; ++i) v[i] += src[i];
+    }
+    epilogue_apply<64>(v, row, col0, N, e);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+struct Operand {
+    const bf16* hi; const bf16* lo;   // lo may be null when nterms == 1
+    int mn_major;                     // 0: [MN][K] row-major, 1: [K][MN] row-major
+    long long ld;                     // elements between consecutive rows of the stored matrix
+};
+
+struct ConvGeom {
+    int enabled;
+    int batch, H, W, C;      // NHWC input
+    int Ho, Wo, R, S, stride, pad;
+};
+
+struct GemmArgs {
+    int M, N, K;
+    Operand A, B;
+    int nterms;
+    int split_k;             // 0/1 = off
+    int a_koff_per_ntile;
+    int block_n;             // 0 = auto
+    ConvGeom conv;
+    float* workspace; size_t workspace_bytes;   // for split-K partials
+    EpiParams e;
+};
+
+void set_error(const char* fmt, ...);
+int num_sms();
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_encodeTiled get_encode_fn();
+
+inline int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+                      const cuuint32_t* box, const cuuint32_t* estr) {
+    PFN_encodeTiled fn = get_encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return -1; }
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu,%llu,%llu,%llu] stride0 %llu box [%u,%u,%u,%u] base %p",
+                  (int)r, rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+                  (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0),
+                  (unsigned long long)(rank > 1 ? strides[0] : 0), box[0], rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0,
+                  rank > 3 ? box[3] : 0, base);
+        return -1;
+    }
+    return 0;
+}
+
+// 2-D operand map. rows_mn = extent along M or N, K = reduction extent, box_mn = tile extent along MN.
+inline int make_operand_map(CUtensorMap* m, const bf16* base, int mn_major, long long ld, int rows_mn, int K, int box_mn) {
+    cuuint64_t dims[2], strides[1]; cuuint32_t box[2], estr[2] = {1, 1};
+    if (!mn_major) { dims[0] = K; dims[1] = rows_mn; box[0] = GEMM_BK; box[1] = box_mn; }
+    else { dims[0] = rows_mn; dims[1] = K; box[0] = 64; box[1] = GEMM_BK; }
+    strides[0] = (cuuint64_t)ld * 2;
+    return encode_map(m, base, 2, dims, strides, box, estr);
+}
+
+template <int BN>
+int launch_gemm_bn(const CUtensorMap* maps, const GemmKParams& kp, int grid, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t err = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::SMEM_BYTES);
+        if (err != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(err)); return -1; }
+        configured = true;
+    }
+    gemm_tc_kernel<BN><<<grid, 256, GemmCfg<BN>::SMEM_BYTES, st>>>(maps[0], maps[1], maps[2], maps[3], kp);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) { set_error("gemm launch: %s", cudaGetErrorString(err)); return -1; }
+    return 0;
+}
+
+inline int gemm_launch(const GemmArgs& g, cudaStream_t st) {
+    GemmKParams kp;
+    memset(&kp, 0, sizeof(kp));
+    int bn = g.block_n;
+    if (bn == 0) {
+        if (g.e.act == ACT_LN64_GELU) bn = 128;
+        else if (g.N <= 64) bn = 64;
+        else {
+            // prefer the widest tile that still gives every SM work
+            const int mt = (g.M + GEMM_BM - 1) / GEMM_BM;
+            const long long t256 = (long long)mt * ((g.N + 255) / 256);
+            bn = (g.N >= 256 && t256 >= 2LL * num_sms()) ? 256 : 128;
+        }
+    }
+    if (bn != 64 && bn != 128 && bn != 256) { set_error("gemm: bad block_n %d", bn); return -1; }
+    kp.M = g.M; kp.N = g.N;
+    kp.num_m = (g.M + GEMM_BM - 1) / GEMM_BM;
+    kp.num_n = (g.N + bn - 1) / bn;
+    kp.nterms = g.nterms;
+    kp.a_mn = g.A.mn_major; kp.b_mn = g.B.mn_major;
+    kp.a_koff_per_ntile = g.a_koff_per_ntile;
+    kp.e = g.e;
+    if (kp.e.alpha == 0.0f) kp.e.alpha = 1.0f;
+    if (g.nterms != 1 && g.nterms != 3) { set_error("gemm: nterms must be 1 or 3"); return -1; }
+    if (g.nterms == 3 && (!g.A.lo || !g.B.lo)) { set_error("gemm: split precision needs lo planes"); return -1; }
+
+    CUtensorMap maps[4];
+    if (g.conv.enabled) {
+        const ConvGeom& c = g.conv;
+        if (c.C % 64 != 0) { set_error("conv: C=%d must be a multiple of 64", c.C); return -1; }
+        if (g.A.mn_major || g.nterms != 1) { set_error("conv: A must be NHWC, single term"); return -1; }
+        int BW = c.Wo, BH, BIMG = 1;
+        if (BW > 128 || 128 % BW != 0) { set_error("conv: Wo=%d must divide 128", c.Wo); return -1; }
+        BH = 128 / BW;
+        if (BH > c.Ho) { BIMG = BH / c.Ho; BH = c.Ho; if (BIMG * BH * BW != 128) { set_error("conv: tile does not fit Ho=%d Wo=%d", c.Ho, c.Wo); return -1; } }
+        if (c.Ho % BH != 0) { set_error("conv: Ho=%d not a multiple of %d", c.Ho, BH); return -1; }
+        kp.conv = 1; kp.cblocks = c.C / 64; kp.S = c.S; kp.stride = c.stride; kp.pad = c.pad;
+        kp.tiles_per_img = c.Ho / BH; kp.BH = BH; kp.BIMG = BIMG;
+        kp.nk = c.R * c.S * kp.cblocks;
+        if (g.M != c.batch * c.Ho * c.Wo) { set_error("conv: M mismatch"); return -1; }
+        cuuint64_t dims[4] = {(cuuint64_t)c.C, (cuuint64_t)c.W, (cuuint64_t)c.H, (cuuint64_t)c.batch};
+        cuuint64_t strides[3] = {(cuuint64_t)c.C * 2, (cuuint64_t)c.W * c.C * 2, (cuuint64_t)c.H * c.W * c.C * 2};
+        cuuint32_t box[4] = {64, (cuuint32_t)(BW * c.stride), (cuuint32_t)(BH * c.stride), (cuuint32_t)BIMG};
+        cuuint32_t estr[4] = {1, (cuuint32_t)c.stride, (cuuint32_t)c.stride, 1};
+        if (encode_map(&maps[0], g.A.hi, 4, dims, strides, box, estr)) return -1;
+        maps[1] = maps[0];
+    } else {
+        kp.nk = (g.K + GEMM_BK - 1) / GEMM_BK;
+        if (make_operand_map(&maps[0], g.A.hi, g.A.mn_major, g.A.ld, g.M, g.a_koff_per_ntile ? (int)g.A.ld : g.K, GEMM_BM)) return -1;
+        if (g.nterms == 3) { if (make_operand_map(&maps[1], g.A.lo, g.A.mn_major, g.A.ld, g.M, g.a_koff_per_ntile ? (int)g.A.ld : g.K, GEMM_BM)) return -1; }
+        else maps[1] = maps[0];
+    }
+    if (make_operand_map(&maps[2], g.B.hi, g.B.mn_major, g.B.ld, g.N, g.conv.enabled ? kp.nk * 64 : g.K, bn)) return -1;
+    if (g.nterms == 3) { if (make_operand_map(&maps[3], g.B.lo, g.B.mn_major, g.B.ld, g.N, g.K, bn)) return -1; }
+    else maps[3] = maps[2];
+
+    const int total_kb = kp.nk * kp.nterms;
+    int split = g.split_k > 1 ? g.split_k : 1;
+    if (split > total_kb) split = total_kb;
+    kp.kb_per_split = (total_kb + split - 1) / split;
+    split = (total_kb + kp.kb_per_split - 1) / kp.kb_per_split;
+    kp.split_k = split;
+    if (split > 1) {
+        const size_t need = (size_t)split * g.M * g.N * sizeof(float);
+        if (!g.workspace || g.workspace_bytes < need) { set_error("gemm: split-K workspace too small (%zu < %zu)", g.workspace_bytes, need); return -1; }
+        kp.partial = g.workspace;
+    }
+    const long long total_tiles = (long long)kp.num_m * kp.num_n * split;
+    const int grid = (int)(total_tiles < num_sms() ? total_tiles : num_sms());
+    int rc;
+    if (bn == 64) rc = launch_gemm_bn<64>(maps, kp, grid, st);
+    else if (bn == 128) rc = launch_gemm_bn<128>(maps, kp, grid, st);
+    else rc = launch_gemm_bn<256>(maps, kp, grid, st);
+    if (rc) return rc;
+    if (split > 1) {
+        EpiParams e = kp.e;
+        e.alpha = kp.e.alpha;
+        if (e.act == ACT_LN64_GELU) {
+            const long long n = (long long)g.M * (g.N / 64);
+            splitk_reduce_ln64_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(kp.partial, split, g.M, g.N, e);
+        } else {
+            const long long n = (long long)g.M * ((g.N + 31) / 32);
+            splitk_reduce_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(kp.partial, split, g.M, g.N, e);
+        }
+        cudaError_t err = cudaGetLastError();
+        if (err != cudaSuccess) { set_error("splitk reduce launch: %s", cudaGetErrorString(err)); return -1; }
+    }
+    return 0;
+}
+
+}  // namespace sq
