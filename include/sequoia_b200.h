@@ -74,6 +74,31 @@ typedef struct sq_gemm_desc {
 
 SQ_API int sq_gemm_bf16(const sq_gemm_desc* desc, void* stream);
 
+/* ------------------------------------------------------------------ ResNet-50 feature extractor
+ * Replaces ResNet.forward_extract (src/resnet.py:155-170) and the CPU preprocessing in front of it
+ * (pre_processing/compute_features_hdf5.py:49-51,117-123). */
+
+/* Topology: 53 convolutions in module order: conv1, then per Bottleneck conv1, conv2, conv3[, downsample.0]
+ * (src/resnet.py:60-68,101-109,123-128). */
+SQ_API int sq_resnet50_num_convs(void);
+SQ_API int sq_resnet50_conv_info(int idx, int* cin, int* cout, int* k, int* stride, int* pad);
+SQ_API long long sq_resnet50_packed_weight_elems(void); /* bf16 elements */
+SQ_API long long sq_resnet50_shift_elems(void);         /* fp32 elements */
+
+/* Folds eval-mode BatchNorm (src/resnet.py:103, compute_features_hdf5.py:60) into the conv weights.
+ * `tensors` is a HOST array of 53*5 DEVICE pointers: {conv.weight (OIHW fp32), bn.weight, bn.bias,
+ * bn.running_mean, bn.running_var} per convolution.  Must be re-run whenever parameters change. */
+SQ_API int sq_resnet50_prepack(const void* const* tensors, void* packed_w, float* shifts, float bn_eps, void* stream);
+
+SQ_API size_t sq_resnet50_workspace_bytes(int batch, int H, int W);
+
+/* input_kind 0: uint8 [batch,H,W,3] raw RGB tiles; x/255 and Normalize(mean,std) are fused (R4).
+ * input_kind 1: fp32 [batch,3,H,W] already normalised — the tensor the reference passes to forward_extract.
+ * features: fp32 [batch, 2048] = AvgPool2d(7) of layer4, i.e. the top-left 7x7 of the 8x8 map at 256 px. */
+SQ_API int sq_resnet50_extract(const void* input, int input_kind, int batch, int H, int W, const void* packed_w,
+                               const float* shifts, float* features, void* workspace, size_t workspace_bytes,
+                               void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -42,6 +42,14 @@ SIGNATURES = {
     "sq_device_ok": (c_int, []),
     "sq_split_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_ll, c_int, c_ll, c_ll, c_void_p]),
     "sq_gemm_bf16": (c_int, [C.POINTER(GemmDesc), c_void_p]),
+    "sq_resnet50_num_convs": (c_int, []),
+    "sq_resnet50_conv_info": (c_int, [c_int] + [C.POINTER(c_int)] * 5),
+    "sq_resnet50_packed_weight_elems": (c_ll, []),
+    "sq_resnet50_shift_elems": (c_ll, []),
+    "sq_resnet50_prepack": (c_int, [C.POINTER(c_void_p), c_void_p, c_void_p, c_float, c_void_p]),
+    "sq_resnet50_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "sq_resnet50_extract": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_size_t, c_void_p]),
 }
 
 _lib = None

@@ -381,7 +381,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 }
 
 // Sums split-K partials and applies the fused epilogue. One thread per (row, 32-column chunk).
-__global__ void splitk_reduce_kernel(const float* __restrict__ partial, int splits, int M, int N, EpiParams e) {
+static __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int splits, int M, int N, EpiParams e) {
     const int chunks = (N + 31) / 32;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)M * chunks) return;
@@ -402,7 +402,7 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int spli
 }
 
 // Same, for the per-head LayerNorm(64)+GELU epilogue (needs whole 64-column groups).
-__global__ void splitk_reduce_ln64_kernel(const float* __restrict__ partial, int splits, int M, int N, EpiParams e) {
+static __global__ void splitk_reduce_ln64_kernel(const float* __restrict__ partial, int splits, int M, int N, EpiParams e) {
     const int chunks = N / 64;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)M * chunks) return;

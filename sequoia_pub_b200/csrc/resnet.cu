@@ -1,0 +1,294 @@
+// ResNet-50 feature extractor (reference: src/resnet.py:96-170 `ResNet`, `Bottleneck`, `forward_extract`;
+// caller pre_processing/compute_features_hdf5.py:49-51,116-123).
+//
+// Data layout in HBM: activations NHWC bf16, weights [Cout][R][S][Cin] bf16 with the eval-mode BatchNorm scale
+// folded in, one fp32 shift per output channel.  Every convolution is one launch of the tcgen05 implicit-GEMM
+// kernel (gemm.cuh) whose epilogue applies shift + residual + ReLU.  The 7x7/2 stem goes through an im2col
+// buffer (K = 147 padded to 192) so it also runs on the tensor cores; uint8 -> /255 -> normalise is fused
+// into that im2col kernel (R4), max-pool and the 7x7 top-left average pool (fact 4) are small bandwidth kernels.
+#include "gemm.cuh"
+#include "../../include/sequoia_b200.h"
+
+namespace sq {
+
+struct ConvSpec { int cin, cout, k, stride, pad; long long w_off, s_off; };
+
+struct ResNetPlan {
+    ConvSpec conv[53];
+    long long w_elems, s_elems;
+};
+
+static const int STEM_K = 192;   // 7*7*3 = 147 padded to 3 k-blocks
+
+static const ResNetPlan& plan() {
+    static ResNetPlan p;
+    static bool init = false;
+    if (!init) {
+        int n = 0; long long w = 0, s = 0;
+        auto add = [&](int cin, int cout, int k, int stride, int pad) {
+            ConvSpec c; c.cin = cin; c.cout = cout; c.k = k; c.stride = stride; c.pad = pad; c.w_off = w; c.s_off = s;
+            w += (n == 0) ? (long long)cout * STEM_K : (long long)cout * k * k * cin;
+            s += cout;
+            p.conv[n++] = c;
+        };
+        add(3, 64, 7, 2, 3);
+        const int planes[4] = {64, 128, 256, 512}, blocks[4] = {3, 4, 6, 3}, strides[4] = {1, 2, 2, 2};
+        int inpl = 64;
+        for (int st = 0; st < 4; ++st)
+            for (int b = 0; b < blocks[st]; ++b) {
+                const int stride = b == 0 ? strides[st] : 1;
+                add(inpl, planes[st], 1, 1, 0);
+                add(planes[st], planes[st], 3, stride, 1);
+                add(planes[st], planes[st] * 4, 1, 1, 0);
+                if (b == 0) add(inpl, planes[st] * 4, 1, stride, 0);
+                inpl = planes[st] * 4;
+            }
+        p.w_elems = w; p.s_elems = s;
+        init = true;
+    }
+    return p;
+}
+
+// OIHW fp32 + BN(gamma, beta, mean, var) -> [O][R][S][I] bf16 (scale folded) + fp32 shift
+__global__ void fold_bn_kernel(const float* __restrict__ w, const float* __restrict__ gamma, const float* __restrict__ beta,
+                               const float* __restrict__ mean, const float* __restrict__ var, float eps, int cout, int cin, int k,
+                               int kpad /*0 = dense*/, bf16* __restrict__ wp, float* __restrict__ shift) {
+    const int kk = k * k * cin;
+    const int row = kpad ? kpad : kk;
+    const long long n = (long long)cout * row;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int o = (int)(i / row); const int j = (int)(i - (long long)o * row);
+        const float sc = gamma[o] / sqrtf(var[o] + eps);
+        float v = 0.f;
+        if (j < kk) {
+            const int c = j % cin; const int rs = j / cin; const int s = rs % k; const int r = rs / k;
+            v = w[(((long long)o * cin + c) * k + r) * k + s] * sc;
+        }
+        wp[i] = __float2bfloat16_rn(v);
+        if (j == 0) shift[o] = beta[o] - mean[o] * sc;
+    }
+}
+
+// Stem im2col: one block = 32 consecutive output pixels of one output row.
+// kind 0: uint8 NHWC raw patch, applies x/255 then (x-mean)/std  (compute_features_hdf5.py:49-51)
+// kind 1: fp32 NCHW, already normalised (the tensor the reference hands to forward_extract)
+__global__ void __launch_bounds__(256) stem_im2col_kernel(const void* __restrict__ in, int kind, int H, int W, int Ho, int Wo,
+                                                          bf16* __restrict__ col) {
+    constexpr int TW = 32, IW = TW * 2 + 5;   // 69 input columns
+    __shared__ float tile[7][IW][3];
+    const int tiles_w = Wo / TW;
+    int b = blockIdx.x;
+    const int tw = b % tiles_w; b /= tiles_w;
+    const int oh = b % Ho; const int img = b / Ho;
+    const int ow0 = tw * TW;
+    const int ih0 = oh * 2 - 3, iw0 = ow0 * 2 - 3;
+    const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
+    for (int i = threadIdx.x; i < 7 * IW * 3; i += 256) {
+        const int c = i % 3; const int x = (i / 3) % IW; const int r = i / (3 * IW);
+        const int ih = ih0 + r, iw = iw0 + x;
+        float v = 0.f;
+        if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
+            if (kind == 0) {
+                const uint8_t u = reinterpret_cast<const uint8_t*>(in)[(((long long)img * H + ih) * W + iw) * 3 + c];
+                v = (static_cast<float>(u) / 255.0f - mean[c]) / stdv[c];
+            } else {
+                v = reinterpret_cast<const float*>(in)[(((long long)img * 3 + c) * H + ih) * W + iw];
+            }
+        }
+        tile[r][x][c] = v;
+    }
+    __syncthreads();
+    bf16* dst = col + (((long long)img * Ho + oh) * Wo + ow0) * STEM_K;
+    for (int i = threadIdx.x; i < TW * (STEM_K / 8); i += 256) {
+        const int p = i / (STEM_K / 8); const int k8 = (i - p * (STEM_K / 8)) * 8;
+        uint4 pack; bf16* h = reinterpret_cast<bf16*>(&pack);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = k8 + j;
+            float v = 0.f;
+            if (k < 147) { const int c = k % 3; const int rs = k / 3; const int s = rs % 7; const int r = rs / 7; v = tile[r][p * 2 + s][c]; }
+            h[j] = __float2bfloat16_rn(v);
+        }
+        *reinterpret_cast<uint4*>(dst + (long long)p * STEM_K + k8) = pack;
+    }
+}
+
+// 3x3 stride-2 pad-1 max pool, NHWC bf16, 8 channels per thread
+__global__ void maxpool3x3s2_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int batch, int H, int W, int C) {
+    const int Ho = H / 2, Wo = W / 2, C8 = C / 8;
+    const long long n = (long long)batch * Ho * Wo * C8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int c8 = (int)(i % C8); long long t = i / C8;
+        const int ow = (int)(t % Wo); t /= Wo; const int oh = (int)(t % Ho); const int img = (int)(t / Ho);
+        float m[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+        for (int r = 0; r < 3; ++r) {
+            const int ih = oh * 2 - 1 + r; if (ih < 0 || ih >= H) continue;
+            for (int s = 0; s < 3; ++s) {
+                const int iw = ow * 2 - 1 + s; if (iw < 0 || iw >= W) continue;
+                const uint4 v = *reinterpret_cast<const uint4*>(in + (((long long)img * H + ih) * W + iw) * C + c8 * 8);
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(h[j]); m[2 * j] = fmaxf(m[2 * j], f.x); m[2 * j + 1] = fmaxf(m[2 * j + 1], f.y); }
+            }
+        }
+        uint4 o; __nv_bfloat162* oh2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) oh2[j] = __floats2bfloat162_rn(m[2 * j], m[2 * j + 1]);
+        *reinterpret_cast<uint4*>(out + (((long long)img * Ho + oh) * Wo + ow) * C + c8 * 8) = o;
+    }
+}
+
+// AvgPool2d(7) on an HfxWf map with Hf,Wf in [7,13]: mean of the top-left 7x7 window (src/resnet.py:110,166; fact 4)
+__global__ void avgpool7_kernel(const float* __restrict__ in, float* __restrict__ out, int batch, int Hf, int Wf, int C) {
+    const long long n = (long long)batch * C;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C); const int img = (int)(i / C);
+        float acc = 0.f;
+        for (int h = 0; h < 7; ++h)
+            for (int w = 0; w < 7; ++w) acc += in[(((long long)img * Hf + h) * Wf + w) * C + c];
+        out[i] = acc * (1.0f / 49.0f);
+    }
+}
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct ResNetWs {
+    size_t col, stem, big[3], small[2], fmap, total;
+};
+
+static ResNetWs ws_layout(int batch, int H, int W) {
+    ResNetWs w; size_t off = 0;
+    const size_t Ho = H / 2, Wo = W / 2, Hp = H / 4, Wp = W / 4;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
+    w.col = take((size_t)batch * Ho * Wo * STEM_K * 2);
+    w.stem = take((size_t)batch * Ho * Wo * 64 * 2);
+    for (int i = 0; i < 3; ++i) w.big[i] = take((size_t)batch * Hp * Wp * 256 * 2);
+    for (int i = 0; i < 2; ++i) w.small[i] = take((size_t)batch * Hp * Wp * 128 * 2);
+    w.fmap = take((size_t)batch * (H / 32) * (W / 32) * 2048 * 4);
+    w.total = off;
+    return w;
+}
+
+static int run_conv(const ConvSpec& c, const bf16* wbase, const float* sbase, const bf16* in, int batch, int H, int W, bf16* out_bf,
+                    float* out_f32, const bf16* res, bool relu, cudaStream_t st, int* Ho_out, int* Wo_out) {
+    const int Ho = (H + 2 * c.pad - c.k) / c.stride + 1, Wo = (W + 2 * c.pad - c.k) / c.stride + 1;
+    GemmArgs g; memset(&g, 0, sizeof(g));
+    g.M = batch * Ho * Wo; g.N = c.cout; g.K = c.k * c.k * c.cin;
+    g.A.hi = in; g.A.ld = c.cin;
+    g.B.hi = wbase + c.w_off; g.B.ld = g.K;
+    g.nterms = 1;
+    g.conv.enabled = 1; g.conv.batch = batch; g.conv.H = H; g.conv.W = W; g.conv.C = c.cin; g.conv.Ho = Ho; g.conv.Wo = Wo;
+    g.conv.R = c.k; g.conv.S = c.k; g.conv.stride = c.stride; g.conv.pad = c.pad;
+    g.e.bias = sbase + c.s_off;
+    g.e.out_hi = out_bf; g.e.ld_bf = c.cout;
+    g.e.out_f32 = out_f32; g.e.ld_f32 = c.cout;
+    g.e.res_bf = res; g.e.ld_res = c.cout;
+    g.e.act = relu ? ACT_RELU : ACT_NONE;
+    g.e.alpha = 1.0f;
+    g.e.rowbias_div = 1;
+    *Ho_out = Ho; *Wo_out = Wo;
+    return gemm_launch(g, st);
+}
+
+}  // namespace sq
+
+using namespace sq;
+
+extern "C" {
+
+int sq_resnet50_num_convs(void) { return 53; }
+long long sq_resnet50_packed_weight_elems(void) { return plan().w_elems; }
+long long sq_resnet50_shift_elems(void) { return plan().s_elems; }
+
+int sq_resnet50_conv_info(int idx, int* cin, int* cout, int* k, int* stride, int* pad) {
+    if (idx < 0 || idx >= 53) { set_error("conv index out of range"); return -1; }
+    const ConvSpec& c = plan().conv[idx];
+    *cin = c.cin; *cout = c.cout; *k = c.k; *stride = c.stride; *pad = c.pad;
+    return 0;
+}
+
+int sq_resnet50_prepack(const void* const* tensors, void* packed_w, float* shifts, float bn_eps, void* stream) {
+    const ResNetPlan& p = plan();
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int i = 0; i < 53; ++i) {
+        const ConvSpec& c = p.conv[i];
+        const float* const* t = reinterpret_cast<const float* const*>(tensors + 5 * i);
+        for (int j = 0; j < 5; ++j) if (!t[j]) { set_error("prepack: null tensor %d of conv %d", j, i); return -1; }
+        const long long n = (long long)c.cout * (i == 0 ? STEM_K : c.k * c.k * c.cin);
+        int blocks = (int)((n + 255) / 256); if (blocks > 4096) blocks = 4096;
+        fold_bn_kernel<<<blocks, 256, 0, st>>>(t[0], t[1], t[2], t[3], t[4], bn_eps, c.cout, c.cin, c.k, i == 0 ? STEM_K : 0,
+                                               (bf16*)packed_w + c.w_off, shifts + c.s_off);
+    }
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) { set_error("prepack: %s", cudaGetErrorString(err)); return -1; }
+    return 0;
+}
+
+size_t sq_resnet50_workspace_bytes(int batch, int H, int W) { return ws_layout(batch, H, W).total; }
+
+int sq_resnet50_extract(const void* input, int input_kind, int batch, int H, int W, const void* packed_w, const float* shifts,
+                        float* features, void* workspace, size_t workspace_bytes, void* stream) {
+    if (batch <= 0) return 0;
+    // Tile geometry (full output rows per 128-pixel MMA tile, pooled map in [7,13]) is laid out for the
+    // 256 px tiles the reference pipeline produces (pre_processing/patch_gen_hdf5.py:119-120).
+    if (H != 256 || W != 256) { set_error("resnet50_extract: only 256x256 patches are supported (got %dx%d)", H, W); return -1; }
+    const ResNetWs L = ws_layout(batch, H, W);
+    if (!workspace || workspace_bytes < L.total) { set_error("resnet50_extract: workspace %zu < %zu", workspace_bytes, L.total); return -1; }
+    const ResNetPlan& p = plan();
+    cudaStream_t st = (cudaStream_t)stream;
+    uint8_t* ws = (uint8_t*)workspace;
+    const bf16* wp = (const bf16*)packed_w;
+    bf16* col = (bf16*)(ws + L.col);
+    bf16* stem = (bf16*)(ws + L.stem);
+    bf16* big[3] = {(bf16*)(ws + L.big[0]), (bf16*)(ws + L.big[1]), (bf16*)(ws + L.big[2])};
+    bf16* small_[2] = {(bf16*)(ws + L.small[0]), (bf16*)(ws + L.small[1])};
+    float* fmap = (float*)(ws + L.fmap);
+
+    // ---- stem: im2col (+ fused preprocessing) -> GEMM(+shift+ReLU) -> maxpool
+    const int Ho = H / 2, Wo = W / 2;
+    stem_im2col_kernel<<<batch * Ho * (Wo / 32), 256, 0, st>>>(input, input_kind, H, W, Ho, Wo, col);
+    {
+        GemmArgs g; memset(&g, 0, sizeof(g));
+        g.M = batch * Ho * Wo; g.N = 64; g.K = STEM_K;
+        g.A.hi = col; g.A.ld = STEM_K; g.B.hi = wp + p.conv[0].w_off; g.B.ld = STEM_K; g.nterms = 1;
+        g.e.bias = shifts + p.conv[0].s_off; g.e.out_hi = stem; g.e.ld_bf = 64; g.e.act = ACT_RELU; g.e.alpha = 1.0f; g.e.rowbias_div = 1;
+        if (gemm_launch(g, st)) return -1;
+    }
+    int h = Ho / 2, w = Wo / 2;
+    {
+        const long long n = (long long)batch * h * w * 8;
+        maxpool3x3s2_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(stem, big[0], batch, Ho, Wo, 64);
+    }
+    // ---- 16 bottlenecks
+    const int blocks[4] = {3, 4, 6, 3};
+    int ci = 1; int x = 0;   // big[x] holds the block input
+    for (int stg = 0; stg < 4; ++stg)
+        for (int b = 0; b < blocks[stg]; ++b) {
+            const bool last = (stg == 3 && b == blocks[3] - 1);
+            const bool down = (b == 0);
+            const ConvSpec& c1 = p.conv[ci]; const ConvSpec& c2 = p.conv[ci + 1]; const ConvSpec& c3 = p.conv[ci + 2];
+            int h1, w1, h2, w2, h3, w3, hd, wd;
+            if (run_conv(c1, wp, shifts, big[x], batch, h, w, small_[0], nullptr, nullptr, true, st, &h1, &w1)) return -1;
+            if (run_conv(c2, wp, shifts, small_[0], batch, h1, w1, small_[1], nullptr, nullptr, true, st, &h2, &w2)) return -1;
+            const bf16* res = big[x];
+            const int y = (x + 1) % 3, d = (x + 2) % 3;
+            if (down) {
+                if (run_conv(p.conv[ci + 3], wp, shifts, big[x], batch, h, w, big[d], nullptr, nullptr, false, st, &hd, &wd)) return -1;
+                res = big[d];
+            }
+            if (run_conv(c3, wp, shifts, small_[1], batch, h2, w2, last ? nullptr : big[y], last ? fmap : nullptr, res, true, st, &h3, &w3)) return -1;
+            x = y; h = h3; w = w3;
+            ci += down ? 4 : 3;
+        }
+    {
+        const long long n = (long long)batch * 2048;
+        avgpool7_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(fmap, features, batch, h, w, 2048);
+    }
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) { set_error("resnet50_extract: %s", cudaGetErrorString(err)); return -1; }
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,92 @@
+"""ResNet-50 extractor: CUDA path (through the C ABI) vs the oracle and the reference's golden vectors."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+# bf16 tensor-core operands with fp32 accumulation: SURVEY §8d expects ~1e-3 L2-relative vs fp32 (north_star sets no bar).
+FEATURE_TOL = 5e-3
+
+
+def _rel(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm()).item()
+
+
+def test_state_dict_keys_match_reference_names():
+    from oracle import resnet50_oracle as O
+    from sequoia_pub_b200.resnet import resnet50
+    m = resnet50()
+    sd = O.make_state_dict(0)
+    assert set(m.state_dict().keys()) == set(sd.keys())
+    for k, v in m.state_dict().items():
+        assert tuple(v.shape) == tuple(sd[k].shape), k
+    m.load_state_dict(sd, strict=True)
+
+
+@pytest.mark.gpu
+def test_extract_matches_golden_and_oracle():
+    from oracle import resnet50_oracle as O
+    from sequoia_pub_b200.resnet import resnet50
+    g = np.load(os.path.join(GOLD, "resnet50_golden.npz"))
+    sd = O.make_state_dict(int(g["weights_seed"]))
+    patches = O.make_patches(int(g["patches_seed"]), int(g["n"]))
+    m = resnet50().eval()
+    m.load_state_dict(sd)
+    m = m.cuda()
+    feat_u8 = m.extract_uint8(patches.cuda())
+    feat_f32 = m.forward_extract(O.preprocess(patches).cuda())
+    torch.cuda.synchronize()
+    gold = torch.from_numpy(g["features_fp64"])
+    e1, e2 = _rel(feat_u8.cpu(), gold), _rel(feat_f32.cpu(), gold)
+    print(f"\n[resnet parity] L2-rel vs reference fp64: uint8 path {e1:.3e}, fp32-NCHW path {e2:.3e}")
+    assert e1 < FEATURE_TOL and e2 < FEATURE_TOL
+    assert _rel(feat_u8, feat_f32) < 1e-3
+
+
+@pytest.mark.gpu
+def test_extract_batch_sizes_and_determinism():
+    from oracle import resnet50_oracle as O
+    from sequoia_pub_b200.resnet import resnet50
+    sd = O.make_state_dict(0)
+    m = resnet50().eval(); m.load_state_dict(sd); m = m.cuda()
+    patches = O.make_patches(3, 9).cuda()
+    full = m.extract_uint8(patches)
+    again = m.extract_uint8(patches)
+    assert torch.equal(full, again)                       # run-to-run deterministic
+    for bs in (1, 2, 5):                                  # ragged batches (odd counts hit the 2-image 8x8 tiles)
+        parts = torch.cat([m.extract_uint8(patches[i:i + bs]) for i in range(0, 9, bs)])
+        assert torch.equal(parts, full)
+    with torch.no_grad():
+        ref = O.forward_extract(sd, O.preprocess(patches.cpu()))
+    assert _rel(full.cpu(), ref) < FEATURE_TOL
+
+
+@pytest.mark.gpu
+def test_train_mode_and_bad_shapes_fail_loudly():
+    from sequoia_pub_b200.resnet import resnet50
+    m = resnet50().cuda()
+    with pytest.raises(RuntimeError):
+        m.train(); m.forward_extract(torch.zeros(1, 3, 256, 256, device="cuda"))
+    m.eval()
+    with pytest.raises(RuntimeError):
+        m.forward_extract(torch.zeros(1, 3, 224, 224, device="cuda"))
+
+
+@pytest.mark.gpu
+def test_throughput_report(capsys):
+    from oracle import resnet50_oracle as O
+    from sequoia_pub_b200.resnet import resnet50
+    m = resnet50().eval(); m.load_state_dict(O.make_state_dict(0)); m = m.cuda()
+    patches = torch.randint(0, 256, (64, 256, 256, 3), dtype=torch.uint8, device="cuda")
+    for _ in range(3):
+        m.extract_uint8(patches)
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(10):
+        m.extract_uint8(patches)
+    e.record(); torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / 10
+    with capsys.disabled():
+        print(f"\n[resnet timing] batch 64: {ms:.3f} ms -> {64 / ms * 1e3:.0f} patches/s")
