@@ -36,6 +36,12 @@ SQ_API const char* sq_last_error(void);
 /* 0 when the current device is an sm_100 part; the product path refuses to run otherwise. */
 SQ_API int sq_device_ok(void);
 
+/* Measurement aid for bench.py: when enabled, every launch of the tcgen05 GEMM/conv kernel is bracketed by CUDA
+ * events on its stream.  _read (after a stream synchronise) returns the summed kernel time, the launch count and
+ * the tensor-core FLOPs those launches issued, then resets the counters. */
+SQ_API int sq_gemm_timing_enable(int on);
+SQ_API int sq_gemm_timing_read(double* total_ms, long long* launches, double* mma_flops);
+
 /* ------------------------------------------------------------------ building blocks (exposed for tests) */
 
 /* fp32 [rows, cols] (row stride ld_in) -> bf16 hi / lo planes (row stride ld_out); lo may be NULL. */

@@ -3,6 +3,7 @@
 #include "gemm.cuh"
 #include "../../include/sequoia_b200.h"
 #include <stdarg.h>
+#include <vector>
 
 namespace sq {
 
@@ -35,6 +36,26 @@ PFN_encodeTiled get_encode_fn() {
             fn = reinterpret_cast<PFN_encodeTiled>(p);
     }
     return fn;
+}
+
+// ---- per-launch timing of the tensor-core kernel (used by bench.py to report the roofline of the dominant kernel)
+static bool g_timing = false;
+static std::vector<cudaEvent_t> g_ev;       // pairs: begin, end
+static size_t g_ev_used = 0;
+static double g_flops = 0.0;
+
+void gemm_timing_begin(cudaStream_t st, double flops) {
+    if (!g_timing) return;
+    if (g_ev_used + 2 > g_ev.size()) {
+        for (int i = 0; i < 2; ++i) { cudaEvent_t e; cudaEventCreate(&e); g_ev.push_back(e); }
+    }
+    g_flops += flops;
+    cudaEventRecord(g_ev[g_ev_used], st);
+}
+void gemm_timing_end(cudaStream_t st) {
+    if (!g_timing) return;
+    cudaEventRecord(g_ev[g_ev_used + 1], st);
+    g_ev_used += 2;
 }
 
 // fp32 [rows, cols] (ld_in) -> bf16 hi / lo planes (ld_out); lo may be null
@@ -75,6 +96,26 @@ int sq_device_ok(void) {
     int dev = 0; cudaDeviceProp prop;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) { set_error("no CUDA device"); return -1; }
     if (prop.major != 10) { set_error("sequoia_b200 needs an sm_100 device, found sm_%d%d", prop.major, prop.minor); return -2; }
+    return 0;
+}
+
+int sq_gemm_timing_enable(int on) {
+    g_timing = on != 0; g_ev_used = 0; g_flops = 0.0;
+    return 0;
+}
+
+int sq_gemm_timing_read(double* total_ms, long long* launches, double* mma_flops) {
+    double ms = 0.0;
+    for (size_t i = 0; i + 1 < g_ev_used; i += 2) {
+        float t = 0.f;
+        cudaError_t err = cudaEventElapsedTime(&t, g_ev[i], g_ev[i + 1]);
+        if (err != cudaSuccess) { set_error("gemm timing: %s (synchronise the stream first)", cudaGetErrorString(err)); return -1; }
+        ms += t;
+    }
+    if (total_ms) *total_ms = ms;
+    if (launches) *launches = (long long)(g_ev_used / 2);
+    if (mma_flops) *mma_flops = g_flops;
+    g_ev_used = 0; g_flops = 0.0;
     return 0;
 }
 

@@ -449,6 +449,9 @@ struct GemmArgs {
 
 void set_error(const char* fmt, ...);
 int num_sms();
+// optional per-launch CUDA-event timing of the GEMM kernel (bench.py's roofline leg); no-ops unless enabled
+void gemm_timing_begin(cudaStream_t st, double flops);
+void gemm_timing_end(cudaStream_t st);
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -566,9 +569,11 @@ inline int gemm_launch(const GemmArgs& g, cudaStream_t st) {
     const long long total_tiles = (long long)kp.num_m * kp.num_n * split;
     const int grid = (int)(total_tiles < num_sms() ? total_tiles : num_sms());
     int rc;
+    gemm_timing_begin(st, 2.0 * g.M * g.N * (g.conv.enabled ? (double)kp.nk * 64 : (double)g.K) * g.nterms);
     if (bn == 64) rc = launch_gemm_bn<64>(maps, kp, grid, st);
     else if (bn == 128) rc = launch_gemm_bn<128>(maps, kp, grid, st);
     else rc = launch_gemm_bn<256>(maps, kp, grid, st);
+    gemm_timing_end(st);
     if (rc) return rc;
     if (split > 1) {
         EpiParams e = kp.e;

@@ -109,7 +109,7 @@ class ResNet(nn.Module):
         self._packed = (key, packed_w, shifts)
         return packed_w, shifts
 
-    def _run(self, inp, kind, batch, H, W):
+    def _run(self, inp, kind, batch, H, W, out=None):
         if self.training:
             raise RuntimeError("sequoia_b200 ResNet implements eval-mode BatchNorm only; call .eval() "
                                "(the reference does: pre_processing/compute_features_hdf5.py:60)")
@@ -119,7 +119,10 @@ class ResNet(nn.Module):
         need = L.sq_resnet50_workspace_bytes(batch, H, W)
         if self._workspace is None or self._workspace.numel() < need or self._workspace.device != inp.device:
             self._workspace = torch.empty(need, dtype=torch.uint8, device=inp.device)
-        out = torch.empty(batch, 2048, dtype=torch.float32, device=inp.device)
+        if out is None:
+            out = torch.empty(batch, 2048, dtype=torch.float32, device=inp.device)
+        elif out.shape != (batch, 2048) or out.dtype != torch.float32 or not out.is_contiguous() or out.device != inp.device:
+            raise ValueError("out must be a contiguous float32 [B,2048] tensor on the input's device")
         _lib.check(L.sq_resnet50_extract(_lib.ptr(inp), kind, batch, H, W, _lib.ptr(packed_w), _lib.ptr(shifts),
                                          _lib.ptr(out), _lib.ptr(self._workspace), self._workspace.numel(),
                                          _lib.stream_ptr()))
@@ -135,12 +138,12 @@ class ResNet(nn.Module):
         return self._run(x, 1, x.shape[0], x.shape[2], x.shape[3])
 
     @torch.no_grad()
-    def extract_uint8(self, patches):
+    def extract_uint8(self, patches, out=None):
         """patches: uint8 [B,H,W,3] raw RGB tiles as stored in the patch HDF5 -> float32 [B,2048]."""
         if patches.dim() != 4 or patches.shape[3] != 3 or patches.dtype != torch.uint8:
             raise ValueError("extract_uint8 expects uint8 [B,H,W,3]")
         patches = patches.contiguous()
-        return self._run(patches, 0, patches.shape[0], patches.shape[1], patches.shape[2])
+        return self._run(patches, 0, patches.shape[0], patches.shape[1], patches.shape[2], out)
 
     @torch.no_grad()
     def forward(self, x):
