@@ -40,6 +40,60 @@ def gen_resnet():
     print("resnet golden:", feat.shape, float(feat.abs().mean()))
 
 
+def gen_vis():
+    """Reference ViS (src/tformer_lin.py) on the oracle's seeded weights:
+    cfg1 = BASELINE configs[0] (1 slide, 100x2048 -> 1000 genes, depth 6, 16 heads): forward only;
+    small = depth 2, 257 genes, batch 3: forward, MSE loss, autograd gradients, 3 AdamW steps (src/vit.py:163-180)."""
+    from oracle import vis_oracle as V
+    from src.tformer_lin import ViS  # the reference
+    out = {}
+    # ---- config 1: forward
+    sd = V.make_state_dict(0, 1000)
+    ref = ViS(num_outputs=1000, input_dim=2048, depth=6, nheads=16, dimensions_f=64, dimensions_s=64, dimensions_c=64,
+              device="cpu")
+    assert list(ref.state_dict().keys()) == list(sd.keys())
+    ref.load_state_dict(sd, strict=True)
+    x, _ = V.make_inputs(0, 1, 1000)
+    with torch.no_grad():
+        out["cfg1_pred"] = ref(x).numpy()
+        out["cfg1_pred_fp64"] = ref.double()(x.double()).numpy()
+    # ---- small training case (D = 1024 exercises the UNI feature width, 257 genes an unaligned head)
+    for tag, D, G, B, depth in (("small", 1024, 257, 3, 2), ("wide", 2048, 1000, 4, 1)):
+        sd = V.make_state_dict(1, G, input_dim=D, depth=depth)
+        ref = ViS(num_outputs=G, input_dim=D, depth=depth, nheads=16, dimensions_f=64, dimensions_s=64, dimensions_c=64,
+                  device="cpu")
+        ref.load_state_dict(sd, strict=True)
+        opt = torch.optim.AdamW(list(ref.parameters()), lr=1e-3, amsgrad=False, weight_decay=0.)
+        loss_fn = torch.nn.MSELoss()
+        losses = []
+        for step in range(3):
+            x, y = V.make_inputs(10 + step, B, G, input_dim=D)
+            pred = ref(x)
+            loss = loss_fn(pred, y)
+            opt.zero_grad()
+            loss.backward()
+            if step == 0:
+                out[f"{tag}_pred0"] = pred.detach().numpy()
+                names = [n for n, _ in ref.named_parameters()]
+                out[f"{tag}_grad_norms"] = np.array([float(p.grad.double().norm()) for p in ref.parameters()])
+                keep = ["pos_emb1D", "transformer.layers.0.0.mixers.3.f.weight", "transformer.layers.0.0.mixers.3.s.weight",
+                        "transformer.layers.0.0.mixers.5.c.weight", "transformer.layers.0.0.mixers.5.c.bias",
+                        "transformer.layers.0.0.mixers.7.local_norm.weight", "transformer.layers.0.0.mixers.7.summary_norm.bias",
+                        "transformer.layers.0.0.projection.bias", "transformer.layers.0.1.net.0.weight",
+                        "transformer.layers.0.1.net.1.bias", "linear_head.0.weight", "linear_head.1.bias"]
+                for k in keep:
+                    out[f"{tag}_grad::{k}"] = dict(ref.named_parameters())[k].grad.numpy().copy()
+                assert names == list(sd.keys())
+            opt.step()
+            losses.append(float(loss))
+        out[f"{tag}_losses"] = np.array(losses)
+        x, _ = V.make_inputs(99, B, G, input_dim=D)
+        with torch.no_grad():
+            out[f"{tag}_pred_after3"] = ref(x).numpy()
+    np.savez_compressed(os.path.join(HERE, "vis_golden.npz"), **out)
+    print("vis golden:", {k: v.shape for k, v in out.items() if "grad::" not in k})
+
+
 if __name__ == "__main__":
     what = sys.argv[1:] or ["resnet", "vis", "kmeans"]
     for w in what:
