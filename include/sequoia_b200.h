@@ -76,6 +76,11 @@ typedef struct sq_gemm_desc {
     const float* ln_gamma; const float* ln_beta;
     int act;
     float alpha;           /* 0 is read as 1 */
+    /* block-diagonal backward modes (per-head 64x64 weights of SummaryMixing.c, src/tformer_lin.py:16,24) */
+    int b_koff_per_ntile;  /* dgrad: B k-offset per n-tile */
+    int b_nadj_per_ntile;  /* dgrad: B n-coordinate adjustment per n-tile */
+    int b_map_mn, b_map_k; /* explicit extents of B's tensor map (0 = N, K) */
+    int diag64;            /* wgrad: only the diagonal 64x64 blocks of C[M,M] are produced, stored at columns 0..63 */
 } sq_gemm_desc;
 
 SQ_API int sq_gemm_bf16(const sq_gemm_desc* desc, void* stream);
@@ -104,6 +109,49 @@ SQ_API size_t sq_resnet50_workspace_bytes(int batch, int H, int W);
 SQ_API int sq_resnet50_extract(const void* input, int input_kind, int batch, int H, int W, const void* packed_w,
                                const float* shifts, float* features, void* workspace, size_t workspace_bytes,
                                void* stream);
+
+/* ------------------------------------------------------------------ ViS aggregator (SummaryMixing transformer)
+ * Replaces ViS.forward (src/tformer_lin.py:97-106 and everything it calls, :18-26,39-48,60-61,73-77), the autograd
+ * backward behind loss.backward() (src/vit.py:179), nn.MSELoss (src/vit.py:129,166) and the AdamW step
+ * (src/main.py:180-183, src/vit.py:180).  dimensions_f = dimensions_s = dimensions_c = 64 (hard-coded at
+ * src/main.py:147,167). */
+typedef struct sq_vis_config {
+    int input_dim;     /* D: 2048 (ResNet features) or 1024 (UNI); multiple of 64 */
+    int depth;         /* L */
+    int nheads;        /* H */
+    int num_clusters;  /* N tokens per slide (100) */
+    int num_outputs;   /* G genes */
+} sq_vis_config;
+
+/* Flat fp32 parameter buffer.  The table lists element offsets of, in order: pos_emb1D [N,D]; per layer 18 entries
+ * {local_norm.weight [H*64], local_norm.bias, summary_norm.weight, summary_norm.bias, s.weight [H*64,D], s.bias,
+ *  f.weight [H*64,D], f.bias, c.weight [H*64,128], c.bias, projection.weight [D,H*64], projection.bias,
+ *  net.0.weight [D], net.0.bias, net.1.weight [D,D], net.1.bias, net.3.weight [D,D], net.3.bias}
+ * (the per-mixer tensors of head h are rows h*64..h*64+63 of these); linear_head.0.weight, .0.bias, .1.weight [G,D], .1.bias.
+ * Gradients, Adam moments and the bf16 hi/lo planes of the parameters use the same offsets. */
+SQ_API int sq_vis_param_table_len(const sq_vis_config* cfg);
+SQ_API int sq_vis_param_layout(const sq_vis_config* cfg, long long* offsets, int n, long long* total_elems);
+SQ_API size_t sq_vis_act_bytes(const sq_vis_config* cfg, int batch);   /* activations kept for the backward pass */
+SQ_API size_t sq_vis_bwd_bytes(const sq_vis_config* cfg, int batch);   /* scratch of the backward pass */
+
+/* x: fp32 [batch, N, D] -> pred fp32 [batch, G].  w_hi / w_lo: bf16 planes of `params` (sq_split_bf16 or sq_adamw_flat). */
+SQ_API int sq_vis_forward(const sq_vis_config* cfg, const float* params, const void* w_hi, const void* w_lo, const float* x,
+                          int batch, float* pred, void* act, size_t act_bytes, void* stream);
+/* Backward stages stage_hi .. stage_lo (inclusive, descending): stage `depth` = regression head (needs dpred fp32
+ * [batch,G]), stage l < depth = transformer layer l (stage 0 also produces pos_emb1D's gradient and, if dx != NULL,
+ * dL/dx [batch,N,D]).  Every gradient of a stage is OVERWRITTEN in `grads` (flat, same offsets as params); stages are
+ * contiguous ranges of that buffer so a data-parallel caller can all-reduce a stage while the next one runs. */
+SQ_API int sq_vis_backward(const sq_vis_config* cfg, const float* params, const void* w_hi, const void* w_lo, const float* dpred,
+                           int batch, void* act, size_t act_bytes, float* grads, float* dx, void* scratch, size_t scratch_bytes,
+                           int stage_hi, int stage_lo, void* stream);
+/* loss = mean((pred - target)^2) over batch*G elements; dpred = 2 (pred - target) / (batch*G) (may be NULL).
+ * scratch: >= 512 floats. */
+SQ_API int sq_mse_fwd_bwd(const float* pred, const float* target, int batch, int num_outputs, float* loss, float* dpred,
+                          float* scratch, void* stream);
+/* torch.optim.AdamW(amsgrad=False) update of a flat buffer (n multiple of 4); gradients are multiplied by grad_scale
+ * first (1/world_size after a sum all-reduce).  p_hi / p_lo (may be NULL) receive the refreshed bf16 planes. */
+SQ_API int sq_adamw_flat(float* p, const float* g, float* m, float* v, void* p_hi, void* p_lo, long long n, float lr, float beta1,
+                         float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

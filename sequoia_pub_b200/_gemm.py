@@ -24,7 +24,7 @@ def split_planes(x, ld_out=None, want_lo=True):
 def gemm(M, N, K, a_hi, b_hi, a_lo=None, b_lo=None, a_mn=False, b_mn=False, lda=None, ldb=None, nterms=1, split_k=0,
          block_n=0, a_koff_per_ntile=0, conv=None, out_f32=None, out_hi=None, out_lo=None, bias=None, rowbias=None,
          rowbias_div=1, res_f32=None, res_bf=None, save_pre=None, aux=None, ln_gamma=None, ln_beta=None, act="none",
-         alpha=1.0, workspace=None):
+         alpha=1.0, workspace=None, b_koff_per_ntile=0, b_nadj_per_ntile=0, b_map_mn=0, b_map_k=0, diag64=0):
     d = _lib.GemmDesc()
     d.M, d.N, d.K = M, N, K
     d.a_hi, d.a_lo, d.a_mn_major = a_hi.data_ptr(), (a_lo.data_ptr() if a_lo is not None else None), int(a_mn)
@@ -60,5 +60,7 @@ def gemm(M, N, K, a_hi, b_hi, a_lo=None, b_lo=None, a_mn=False, b_mn=False, lda=
     if aux is not None:
         d.ld_aux = aux.stride(0)
     d.act, d.alpha = ACT[act], alpha
+    d.b_koff_per_ntile, d.b_nadj_per_ntile, d.b_map_mn, d.b_map_k, d.diag64 = (b_koff_per_ntile, b_nadj_per_ntile,
+                                                                               b_map_mn, b_map_k, diag64)
     _lib.check(_lib.lib().sq_gemm_bf16(C.byref(d), _lib.stream_ptr()))
     return workspace

@@ -32,7 +32,14 @@ class GemmDesc(C.Structure):
         ("aux", c_void_p), ("ld_aux", c_ll),
         ("ln_gamma", c_void_p), ("ln_beta", c_void_p),
         ("act", c_int), ("alpha", c_float),
+        ("b_koff_per_ntile", c_int), ("b_nadj_per_ntile", c_int), ("b_map_mn", c_int), ("b_map_k", c_int),
+        ("diag64", c_int),
     ]
+
+
+class VisConfig(C.Structure):
+    """Mirror of `sq_vis_config`."""
+    _fields_ = [("input_dim", c_int), ("depth", c_int), ("nheads", c_int), ("num_clusters", c_int), ("num_outputs", c_int)]
 
 
 # name -> (restype, argtypes); kept in one table so tests can check the export list against the header
@@ -52,6 +59,17 @@ SIGNATURES = {
     "sq_resnet50_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "sq_resnet50_extract": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                     c_size_t, c_void_p]),
+    "sq_vis_param_table_len": (c_int, [C.POINTER(VisConfig)]),
+    "sq_vis_param_layout": (c_int, [C.POINTER(VisConfig), C.POINTER(c_ll), c_int, C.POINTER(c_ll)]),
+    "sq_vis_act_bytes": (c_size_t, [C.POINTER(VisConfig), c_int]),
+    "sq_vis_bwd_bytes": (c_size_t, [C.POINTER(VisConfig), c_int]),
+    "sq_vis_forward": (c_int, [C.POINTER(VisConfig), c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                               c_size_t, c_void_p]),
+    "sq_vis_backward": (c_int, [C.POINTER(VisConfig), c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_size_t,
+                                c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p]),
+    "sq_mse_fwd_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "sq_adamw_flat": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_float, c_float, c_float,
+                              c_float, c_float, c_int, c_float, c_void_p]),
 }
 
 _lib = None

@@ -145,6 +145,8 @@ int sq_gemm_bf16(const sq_gemm_desc* d, void* stream) {
     g.e.aux = d->aux; g.e.ld_aux = d->ld_aux;
     g.e.ln_gamma = d->ln_gamma; g.e.ln_beta = d->ln_beta;
     g.e.act = d->act; g.e.alpha = d->alpha;
+    g.b_koff_per_ntile = d->b_koff_per_ntile; g.b_nadj_per_ntile = d->b_nadj_per_ntile;
+    g.b_map_mn = d->b_map_mn; g.b_map_k = d->b_map_k; g.diag64 = d->diag64;
     return gemm_launch(g, (cudaStream_t)stream);
 }
 

@@ -47,6 +47,9 @@ struct GemmKParams {
     int kb_per_split;
     int a_mn, b_mn;
     int a_koff_per_ntile;   // block-diagonal mode: extra A k-offset per n-tile
+    int b_koff_per_ntile;   // block-diagonal dgrad: extra B k-offset per n-tile ...
+    int b_nadj_per_ntile;   // ... and an adjustment of B's n coordinate per n-tile
+    int diag64;             // block-diagonal wgrad: only the 64x64 diagonal blocks of C are produced (BN = 64)
     // conv mode
     int conv, cblocks, S, stride, pad, tiles_per_img, BH, BIMG;
     float* partial;         // split-K workspace [split][M][N]
@@ -260,7 +263,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 const int mt = mn / p.num_n, nt = mn - mt * p.num_n;
                 const int kb0 = split * p.kb_per_split;
                 const int kb1 = min(kb0 + p.kb_per_split, total_kb);
-                const int m0 = mt * GEMM_BM, n0 = nt * BN;
+                const int m0 = mt * GEMM_BM, n0 = p.diag64 ? (2 * mt + nt) * 64 : nt * BN;
+                const int bn0 = n0 + nt * p.b_nadj_per_ntile, bkoff = nt * p.b_koff_per_ntile;
                 int img = 0, hin0 = 0;
                 if (p.conv) {
                     if (p.BIMG == 1) { img = mt / p.tiles_per_img; hin0 = (mt - img * p.tiles_per_img) * p.BH * p.stride - p.pad; }
@@ -287,9 +291,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     }
                     if (p.b_mn) {
 #pragma unroll
-                        for (int a = 0; a < BN / 64; ++a) tma_load_2d(mb, &full[stage], sb + a * 8192, n0 + a * 64, k0);
+                        for (int a = 0; a < BN / 64; ++a) tma_load_2d(mb, &full[stage], sb + a * 8192, bn0 + a * 64, k0 + bkoff);
                     } else {
-                        tma_load_2d(mb, &full[stage], sb, k0, n0);
+                        tma_load_2d(mb, &full[stage], sb, k0 + bkoff, bn0);
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -340,9 +344,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             mbar_wait(&tmem_full[as], aphase);
             tc_fence_after();
             const long long row = (long long)mt * GEMM_BM + q * 32 + lane;
-            const int n0 = nt * BN;
+            const int n0 = p.diag64 ? (2 * mt + nt) * 64 : nt * BN;
             const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
-            const bool row_ok = row < p.M;
+            // diag64: a row belongs to head row/64 and only that head's 64 columns are kept, stored at columns 0..63
+            const bool row_ok = row < p.M && (!p.diag64 || (row >> 6) == (long long)(n0 >> 6));
+            const int ncols = p.diag64 ? 64 : p.N;
+            const int c0 = p.diag64 ? 0 : n0;
             if (p.split_k > 1) {
                 float* dst = p.partial + ((long long)split * p.M + row) * p.N;
                 for (int c = 0; c < BN && n0 + c < p.N; c += 32) {
@@ -367,7 +374,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     float v[32];
                     tmem_ld32(tacc + c, v);
                     tmem_ld_wait();
-                    if (row_ok) epilogue_apply<32>(v, row, n0 + c, p.N, p.e);
+                    if (row_ok) epilogue_apply<32>(v, row, c0 + c, ncols, p.e);
                 }
             }
             tc_fence_before();
@@ -441,6 +448,9 @@ struct GemmArgs {
     int nterms;
     int split_k;             // 0/1 = off
     int a_koff_per_ntile;
+    int b_koff_per_ntile, b_nadj_per_ntile;   // block-diagonal dgrad (see GemmKParams)
+    int b_map_mn, b_map_k;   // explicit extents of B's tensor map (0 = N / K)
+    int diag64;              // block-diagonal wgrad
     int block_n;             // 0 = auto
     ConvGeom conv;
     float* workspace; size_t workspace_bytes;   // for split-K partials
@@ -449,6 +459,7 @@ struct GemmArgs {
 
 void set_error(const char* fmt, ...);
 int num_sms();
+int split_planes(const float* x, bf16* hi, bf16* lo, long long rows, int cols, long long ld_in, long long ld_out, cudaStream_t st);
 // optional per-launch CUDA-event timing of the GEMM kernel (bench.py's roofline leg); no-ops unless enabled
 void gemm_timing_begin(cudaStream_t st, double flops);
 void gemm_timing_end(cudaStream_t st);
@@ -520,6 +531,12 @@ inline int gemm_launch(const GemmArgs& g, cudaStream_t st) {
     kp.nterms = g.nterms;
     kp.a_mn = g.A.mn_major; kp.b_mn = g.B.mn_major;
     kp.a_koff_per_ntile = g.a_koff_per_ntile;
+    kp.b_koff_per_ntile = g.b_koff_per_ntile; kp.b_nadj_per_ntile = g.b_nadj_per_ntile;
+    kp.diag64 = g.diag64;
+    if (g.diag64) {
+        if (bn != 64 || g.split_k > 1 || g.M != g.N || g.M % 128 != 0 || g.conv.enabled) { set_error("gemm: diag64 needs block_n 64, no split-K, M == N, M %% 128 == 0"); return -1; }
+        kp.num_n = 2;
+    }
     kp.e = g.e;
     if (kp.e.alpha == 0.0f) kp.e.alpha = 1.0f;
     if (g.nterms != 1 && g.nterms != 3) { set_error("gemm: nterms must be 1 or 3"); return -1; }
@@ -551,8 +568,10 @@ inline int gemm_launch(const GemmArgs& g, cudaStream_t st) {
         if (g.nterms == 3) { if (make_operand_map(&maps[1], g.A.lo, g.A.mn_major, g.A.ld, g.M, g.a_koff_per_ntile ? (int)g.A.ld : g.K, GEMM_BM)) return -1; }
         else maps[1] = maps[0];
     }
-    if (make_operand_map(&maps[2], g.B.hi, g.B.mn_major, g.B.ld, g.N, g.conv.enabled ? kp.nk * 64 : g.K, bn)) return -1;
-    if (g.nterms == 3) { if (make_operand_map(&maps[3], g.B.lo, g.B.mn_major, g.B.ld, g.N, g.K, bn)) return -1; }
+    const int bmn = g.b_map_mn ? g.b_map_mn : g.N;
+    const int bk = g.b_map_k ? g.b_map_k : (g.conv.enabled ? kp.nk * 64 : g.K);
+    if (make_operand_map(&maps[2], g.B.hi, g.B.mn_major, g.B.ld, bmn, bk, bn)) return -1;
+    if (g.nterms == 3) { if (make_operand_map(&maps[3], g.B.lo, g.B.mn_major, g.B.ld, bmn, bk, bn)) return -1; }
     else maps[3] = maps[2];
 
     const int total_kb = kp.nk * kp.nterms;

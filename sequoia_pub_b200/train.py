@@ -1,0 +1,83 @@
+"""Fused ViS optimisation step: the body of the reference's training loop (src/vit.py:163-166,175-180 —
+`pred = model(x); loss = MSELoss(pred, y); optimizer.zero_grad(); loss.backward(); optimizer.step()` with
+`AdamW(lr, weight_decay=0, amsgrad=False)`, src/main.py:180-183) enqueued as one chain of CUDA kernels with no autograd
+graph: sq_vis_forward -> sq_mse_fwd_bwd -> sq_vis_backward (stage by stage) -> [NCCL all-reduce] -> sq_adamw_flat.
+
+Data parallel: one process per GPU, the batch of slides is split evenly across ranks, every backward stage's
+contiguous slice of the flat gradient buffer is all-reduced (sum) as soon as the stage is enqueued so the exchange of
+the head / upper layers overlaps the backward of the lower layers; AdamW then applies grad * 1/world_size, which
+equals the gradient of the global-batch mean loss because MSELoss is a mean over equal shards (src/vit.py:129).
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .tformer_lin import ViS
+
+
+class FusedTrainer:
+    def __init__(self, model: ViS, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, process_group=None, overlap=True):
+        self.model = model
+        self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
+        self.step_count = 0
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+        self.overlap = overlap
+        self._token = None
+        self.launch_count = 0     # sq_* calls of the last step (bench.py reports kernels separately)
+
+    def _bind(self):
+        m = self.model
+        m._ensure_flat()
+        if self._token != m._flat_token:
+            dev = m._flat.device
+            self.m = torch.zeros_like(m._flat)
+            self.v = torch.zeros_like(m._flat)
+            self.g = torch.zeros_like(m._flat)
+            self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
+            self.mse_scratch = torch.empty(1024, dtype=torch.float32, device=dev)
+            self._token = m._flat_token
+            # contiguous [begin, end) element ranges of the flat buffer per backward stage (head = stage depth)
+            n = _lib.lib().sq_vis_param_table_len(C.byref(m._cfg))
+            table = (C.c_longlong * n)()
+            total = C.c_longlong()
+            _lib.check(_lib.lib().sq_vis_param_layout(C.byref(m._cfg), table, n, C.byref(total)))
+            depth = m._cfg.depth
+            starts = [table[1 + 18 * l] for l in range(depth)] + [table[n - 4], total.value]
+            self.stage_range = [(0 if l == 0 else starts[l], starts[l + 1]) for l in range(depth)] + [(starts[depth], total.value)]
+        return m
+
+    def step(self, x, y):
+        """x: float32 [B, N, D], y: float32 [B, G] on the model's device -> loss (1-element device tensor, this rank's shard)."""
+        m = self._bind()
+        cfg = m._cfg
+        L = _lib.lib()
+        B = x.shape[0]
+        if y.shape != (B, cfg.num_outputs) or y.dtype != torch.float32 or not y.is_contiguous():
+            raise ValueError("y must be a contiguous float32 [B, num_outputs] tensor")
+        pred, act = m._forward_impl(x, keep=False)
+        self.pred = pred
+        dpred = torch.empty_like(pred)
+        _lib.check(L.sq_mse_fwd_bwd(_lib.ptr(pred), _lib.ptr(y), B, cfg.num_outputs, _lib.ptr(self.loss), _lib.ptr(dpred),
+                                    _lib.ptr(self.mse_scratch), _lib.stream_ptr()))
+        works = []
+        if self.world > 1 and self.overlap:
+            for s in range(cfg.depth, -1, -1):
+                m._backward_impl(act, dpred if s == cfg.depth else None, B, False, gbuf=self.g, stage_hi=s, stage_lo=s)
+                b, e = self.stage_range[s]
+                works.append(torch.distributed.all_reduce(self.g[b:e], group=self.pg, async_op=True))
+            for w in works:
+                w.wait()
+        else:
+            m._backward_impl(act, dpred, B, False, gbuf=self.g)
+            if self.world > 1:
+                torch.distributed.all_reduce(self.g, group=self.pg)
+        self.step_count += 1
+        _lib.check(L.sq_adamw_flat(_lib.ptr(m._flat), _lib.ptr(self.g), _lib.ptr(self.m), _lib.ptr(self.v), _lib.ptr(m._w_hi),
+                                   _lib.ptr(m._w_lo), m._total, self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
+                                   self.step_count, 1.0 / self.world, _lib.stream_ptr()))
+        m._planes_are_fresh()
+        return self.loss

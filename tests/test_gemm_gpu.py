@@ -202,3 +202,27 @@ def test_timing_report(capsys):
             with capsys.disabled():
                 print(f"\n[gemm timing] M={M} N={N} K={K} terms={nt} BN={bn}: {ms*1e3:.1f} us, "
                       f"{2.0*M*N*K*nt/ms/1e9:.1f} TFLOP/s (bf16 MMA work)")
+
+
+def test_block_diagonal_backward_modes():
+    """Per-head dgrad (B read transposed from the [H*64, 128] c.weight layout) and diagonal-block wgrad."""
+    gm = _mods()
+    M, H, d = 300, 16, 64
+    dC = _mk(M, H * d, 21)                                   # dL/dCpre [tokens, H*64]
+    Wc = _mk(H * d, 2 * d, 22) * 0.2                         # c.weight of all heads, [H*64, 128]
+    local = _mk(M, H * d, 23)
+    a_hi, a_lo = gm.split_planes(dC); w_hi, w_lo = gm.split_planes(Wc); l_hi, l_lo = gm.split_planes(local)
+    for half in (0, 1):                                      # Wc[:, :64] and Wc[:, 64:]
+        out = torch.full((M, H * d), float("nan"), device="cuda")
+        gm.gemm(M, H * d, d, a_hi, w_hi[:, half * 64:], a_lo, w_lo[:, half * 64:], b_mn=True, ldb=128, nterms=3, out_f32=out,
+                block_n=64, a_koff_per_ntile=64, b_koff_per_ntile=64, b_nadj_per_ntile=-64, b_map_mn=64, b_map_k=H * d)
+        torch.cuda.synchronize()
+        W = Wc.double().view(H, d, 2 * d)[:, :, half * 64:(half + 1) * 64]          # [h, j, i]
+        ref = torch.einsum("mhj,hji->mhi", dC.double().view(M, H, d), W).reshape(M, H * d)
+        assert _rel(out, ref) < 2e-5
+    dW = torch.full((H * d, 2 * d), float("nan"), device="cuda")
+    gm.gemm(H * d, H * d, M, a_hi, l_hi, a_lo, l_lo, a_mn=True, b_mn=True, nterms=3, out_f32=dW, diag64=1, block_n=64)
+    torch.cuda.synchronize()
+    ref = torch.einsum("mhj,mhi->hji", dC.double().view(M, H, d), local.double().view(M, H, d)).reshape(H * d, d)
+    assert _rel(dW[:, :64], ref) < 2e-5
+    assert torch.isnan(dW[:, 64:]).all()                      # the other half of c.weight's gradient is untouched
