@@ -18,6 +18,7 @@
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 
 namespace sq {
 
@@ -351,14 +352,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             const int ncols = p.diag64 ? 64 : p.N;
             const int c0 = p.diag64 ? 0 : n0;
             if (p.split_k > 1) {
-                float* dst = p.partial + ((long long)split * p.M + row) * p.N;
+                float* dst = p.partial + ((long long)split * p.M + row) * ncols + c0;
                 for (int c = 0; c < BN && n0 + c < p.N; c += 32) {
                     float v[32];
                     tmem_ld32(tacc + c, v);
                     tmem_ld_wait();
                     if (row_ok) {
                         const int nvalid = min(32, p.N - n0 - c);
-                        for (int i = 0; i < nvalid; ++i) dst[n0 + c + i] = v[i];
+                        if (nvalid == 32 && (ncols & 3) == 0) {
+#pragma unroll
+                            for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + c + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                        } else {
+                            for (int i = 0; i < nvalid; ++i) dst[c + i] = v[i];
+                        }
                     }
                 }
             } else if (p.e.act == ACT_LN64_GELU) {
@@ -387,25 +393,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
-// Sums split-K partials and applies the fused epilogue. One thread per (row, 32-column chunk).
+// Sums split-K partials and applies the fused epilogue. One thread per (row, 8-column chunk): a warp reads 1 KB
+// of consecutive columns per split, in a fixed order (deterministic).
 static __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int splits, int M, int N, EpiParams e) {
-    const int chunks = (N + 31) / 32;
+    const int chunks = (N + 7) / 8;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)M * chunks) return;
     const int chunk = (int)(idx % chunks);
     const long long row = idx / chunks;
-    const int col0 = chunk * 32;
-    const int nvalid = min(32, N - col0);
-    float v[32];
+    const int col0 = chunk * 8;
+    const int nvalid = min(8, N - col0);
+    float v[8];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = 0.f;
+    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+    const bool vec = (nvalid == 8) && ((N & 3) == 0);
     for (int s = 0; s < splits; ++s) {
         const float* src = partial + ((long long)s * M + row) * N + col0;
+        if (vec) {
+            const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
+            v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+        } else {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-            if (i < nvalid) v[i] += src[i];
+            for (int i = 0; i < 8; ++i)
+                if (i < nvalid) v[i] += src[i];
+        }
     }
-    epilogue_apply<32>(v, row, col0, N, e);
+    epilogue_apply<8>(v, row, col0, N, e);
 }
 
 // Same, for the per-head LayerNorm(64)+GELU epilogue (needs whole 64-column groups).
@@ -514,6 +527,8 @@ inline int gemm_launch(const GemmArgs& g, cudaStream_t st) {
     GemmKParams kp;
     memset(&kp, 0, sizeof(kp));
     int bn = g.block_n;
+    static const int env_bn = getenv("SQ_GEMM_BN") ? atoi(getenv("SQ_GEMM_BN")) : 0;     // tuning knob (experiments only)
+    if (bn == 0 && env_bn && g.e.act != ACT_LN64_GELU && g.N >= env_bn) bn = env_bn;
     if (bn == 0) {
         if (g.e.act == ACT_LN64_GELU) bn = 128;
         else if (g.N <= 64) bn = 64;
@@ -534,7 +549,7 @@ inline int gemm_launch(const GemmArgs& g, cudaStream_t st) {
     kp.b_koff_per_ntile = g.b_koff_per_ntile; kp.b_nadj_per_ntile = g.b_nadj_per_ntile;
     kp.diag64 = g.diag64;
     if (g.diag64) {
-        if (bn != 64 || g.split_k > 1 || g.M != g.N || g.M % 128 != 0 || g.conv.enabled) { set_error("gemm: diag64 needs block_n 64, no split-K, M == N, M %% 128 == 0"); return -1; }
+        if (bn != 64 || g.M != g.N || g.M % 64 != 0 || g.conv.enabled || g.e.act == ACT_LN64_GELU) { set_error("gemm: diag64 needs block_n 64, M == N, M %% 64 == 0"); return -1; }
         kp.num_n = 2;
     }
     kp.e = g.e;
@@ -581,7 +596,7 @@ inline int gemm_launch(const GemmArgs& g, cudaStream_t st) {
     split = (total_kb + kp.kb_per_split - 1) / kp.kb_per_split;
     kp.split_k = split;
     if (split > 1) {
-        const size_t need = (size_t)split * g.M * g.N * sizeof(float);
+        const size_t need = (size_t)split * g.M * (g.diag64 ? 64 : g.N) * sizeof(float);
         if (!g.workspace || g.workspace_bytes < need) { set_error("gemm: split-K workspace too small (%zu < %zu)", g.workspace_bytes, need); return -1; }
         kp.partial = g.workspace;
     }
@@ -601,8 +616,9 @@ inline int gemm_launch(const GemmArgs& g, cudaStream_t st) {
             const long long n = (long long)g.M * (g.N / 64);
             splitk_reduce_ln64_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(kp.partial, split, g.M, g.N, e);
         } else {
-            const long long n = (long long)g.M * ((g.N + 31) / 32);
-            splitk_reduce_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(kp.partial, split, g.M, g.N, e);
+            const int rn = g.diag64 ? 64 : g.N;      // diag64 partials are a dense [M, 64] matrix
+            const long long n = (long long)g.M * ((rn + 7) / 8);
+            splitk_reduce_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(kp.partial, split, g.M, rn, e);
         }
         cudaError_t err = cudaGetLastError();
         if (err != cudaSuccess) { set_error("splitk reduce launch: %s", cudaGetErrorString(err)); return -1; }

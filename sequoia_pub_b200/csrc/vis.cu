@@ -87,7 +87,7 @@ static void vis_act_layout(const VisDims& d, int B, VisAct* A) {
 struct VisBwd { size_t dp_hi, dp_lo, splitk, splitk_bytes, dz, dpooled, g2_f32, g2_hi, g2_lo, g1_f32, g1_hi, g1_lo, du_hi, du_lo, dh,
                 dc_hi, dc_lo, dlocal, df_hi, df_lo, drb, drb_hi, drb_lo, dt, ds_hi, ds_lo, dxm, part, part_bytes, gsum, total; };
 
-constexpr int LN_RPB = 8;     // rows per block in the row-LayerNorm backward
+constexpr int LN_RPB = 16;    // rows per block in the row-LayerNorm backward
 
 static void vis_bwd_layout(const VisDims& d, int B, VisBwd* S) {
     size_t off = 0;
@@ -104,7 +104,7 @@ static void vis_bwd_layout(const VisDims& d, int B, VisBwd* S) {
     S->drb = take((size_t)B * HD * 4); S->drb_hi = take((size_t)B * HD * 2); S->drb_lo = take((size_t)B * HD * 2);
     S->dt = take((size_t)B * HD * 4); S->ds_hi = take((size_t)B * HD * 2); S->ds_lo = take((size_t)B * HD * 2);
     S->dxm = take((size_t)B * D * 4);
-    const size_t nblk = (M + LN_RPB - 1) / LN_RPB > (M + 127) / 128 ? (M + LN_RPB - 1) / LN_RPB : (M + 127) / 128;
+    const size_t nblk = (M + 7) / 8 + 128;
     S->part_bytes = nblk * 2 * W * 4; S->part = take(S->part_bytes);
     S->gsum = take((size_t)B * W * 4);
     S->total = off;
@@ -127,72 +127,109 @@ __device__ __forceinline__ void store_planes4(bf16* hi, bf16* lo, size_t off, fl
     }
 }
 
-// x_in [B,N,D] + pos [N,D] -> x (fp32 + planes) and the token mean of every slide (planes).  tformer_lin.py:100
+// x_in [B,N,D] + pos [N,D] -> x (fp32 + planes).  tformer_lin.py:100
 __global__ void prep_input_kernel(const float* __restrict__ x_in, const float* __restrict__ pos, float* __restrict__ x,
-                                  bf16* __restrict__ xh, bf16* __restrict__ xl, bf16* __restrict__ mh, bf16* __restrict__ ml, int N, int D) {
-    const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (c >= D) return;
-    const int b = blockIdx.y;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int n = 0; n < N; ++n) {
-        const size_t off = ((size_t)b * N + n) * D + c;
-        const float4 a = *reinterpret_cast<const float4*>(x_in + off);
-        const float4 p = *reinterpret_cast<const float4*>(pos + (size_t)n * D + c);
+                                  bf16* __restrict__ xh, bf16* __restrict__ xl, int N, int D, long long total4) {
+    const int D4 = D / 4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+        const long long row = i / D4; const int c = (int)(i - row * D4) * 4;
+        const float4 a = *reinterpret_cast<const float4*>(x_in + i * 4);
+        const float4 p = *reinterpret_cast<const float4*>(pos + (size_t)(row % N) * D + c);
         const float4 v = make_float4(a.x + p.x, a.y + p.y, a.z + p.z, a.w + p.w);
-        *reinterpret_cast<float4*>(x + off) = v;
-        store_planes4(xh, xl, off, v);
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        *reinterpret_cast<float4*>(x + i * 4) = v;
+        store_planes4(xh, xl, (size_t)i * 4, v);
     }
-    const float s = 1.0f / (float)N;
-    store_planes4(mh, ml, (size_t)b * D + c, make_float4(acc.x * s, acc.y * s, acc.z * s, acc.w * s));
 }
 
 // mean over the N tokens of every slide: x [B*N, D] fp32 -> [B, D] (fp32 and/or planes).  tformer_lin.py:22,103
-__global__ void group_mean_kernel(const float* __restrict__ x, int N, int D, float scale, float* __restrict__ out,
-                                  bf16* __restrict__ oh, bf16* __restrict__ ol) {
-    const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (c >= D) return;
+// block = (slide, 128-column slab); the 8 warps stride over the tokens, partial sums are combined in warp order.
+__global__ void __launch_bounds__(256) group_mean_kernel(const float* __restrict__ x, int N, int D, float scale, float* __restrict__ out,
+                                                         bf16* __restrict__ oh, bf16* __restrict__ ol) {
+    __shared__ float4 red[8][32];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = blockIdx.x * 128 + lane * 4;
     const int b = blockIdx.y;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int n = 0; n < N; ++n) {
-        const float4 v = *reinterpret_cast<const float4*>(x + ((size_t)b * N + n) * D + c);
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    if (c < D) {
+#pragma unroll 4
+        for (int n = w; n < N; n += 8) {
+            const float4 v = *reinterpret_cast<const float4*>(x + ((size_t)b * N + n) * D + c);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
     }
-    acc.x *= scale; acc.y *= scale; acc.z *= scale; acc.w *= scale;
-    if (out) *reinterpret_cast<float4*>(out + (size_t)b * D + c) = acc;
-    if (oh) store_planes4(oh, ol, (size_t)b * D + c, acc);
+    red[w][lane] = acc;
+    __syncthreads();
+    if (w == 0 && c < D) {
+        float4 t = red[0][lane];
+#pragma unroll
+        for (int i = 1; i < 8; ++i) { const float4 u = red[i][lane]; t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w; }
+        t.x *= scale; t.y *= scale; t.z *= scale; t.w *= scale;
+        if (out) *reinterpret_cast<float4*>(out + (size_t)b * D + c) = t;
+        if (oh) store_planes4(oh, ol, (size_t)b * D + c, t);
+    }
 }
 
-// sum of hi+lo over groups of gs consecutive rows: planes [groups*gs, C] -> [groups, C] (fp32 and/or planes)
-__global__ void group_sum_planes_kernel(const bf16* __restrict__ hi, const bf16* __restrict__ lo, long long ld, int gs, int C,
-                                        float* __restrict__ out, bf16* __restrict__ oh, bf16* __restrict__ ol) {
-    const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
-    if (c >= C) return;
+// sum of hi+lo over groups of gs consecutive rows: planes [groups*gs, C] -> [groups, C] (fp32 and/or planes).
+// block = (group, 256-column slab); 8 warps stride over the rows, 8 columns per lane.
+__global__ void __launch_bounds__(256) group_sum_planes_kernel(const bf16* __restrict__ hi, const bf16* __restrict__ lo, long long ld, int gs, int C,
+                                                               float* __restrict__ out, bf16* __restrict__ oh, bf16* __restrict__ ol) {
+    __shared__ float red[8][256];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = blockIdx.x * 256 + lane * 8;
     const int g = blockIdx.y;
-    float a0 = 0.f, a1 = 0.f;
-    for (int r = 0; r < gs; ++r) {
-        const size_t off = ((size_t)g * gs + r) * ld + c;
-        const float2 h = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(hi + off));
-        const float2 l = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(lo + off));
-        a0 += h.x + l.x; a1 += h.y + l.y;
+    float a[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = 0.f;
+    if (c < C) {
+#pragma unroll 2
+        for (int r = w; r < gs; r += 8) {
+            const size_t off = ((size_t)g * gs + r) * ld + c;
+            const uint4 h = *reinterpret_cast<const uint4*>(hi + off);
+            const uint4 l = *reinterpret_cast<const uint4*>(lo + off);
+            const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&h);
+            const __nv_bfloat162* lp = reinterpret_cast<const __nv_bfloat162*>(&l);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 hf = __bfloat1622float2(hp[j]), lf = __bfloat1622float2(lp[j]);
+                a[2 * j] += hf.x + lf.x; a[2 * j + 1] += hf.y + lf.y;
+            }
+        }
     }
-    const size_t o = (size_t)g * C + c;
-    if (out) { out[o] = a0; out[o + 1] = a1; }
-    if (oh) {
-        const bf16 h0 = __float2bfloat16_rn(a0), h1 = __float2bfloat16_rn(a1);
-        *reinterpret_cast<__nv_bfloat162*>(oh + o) = __halves2bfloat162(h0, h1);
-        *reinterpret_cast<__nv_bfloat162*>(ol + o) = __halves2bfloat162(__float2bfloat16_rn(a0 - __bfloat162float(h0)),
-                                                                         __float2bfloat16_rn(a1 - __bfloat162float(h1)));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[w][lane * 8 + j] = a[j];
+    __syncthreads();
+    const int col = blockIdx.x * 256 + threadIdx.x;
+    if (col < C) {
+        float t = red[0][threadIdx.x];
+#pragma unroll
+        for (int i = 1; i < 8; ++i) t += red[i][threadIdx.x];
+        const size_t o = (size_t)g * C + col;
+        if (out) out[o] = t;
+        if (oh) {
+            const bf16 h0 = __float2bfloat16_rn(t);
+            oh[o] = h0; ol[o] = __float2bfloat16_rn(t - __bfloat162float(h0));
+        }
     }
 }
 
-// out[c] = scale * sum_p in[p*ld + c]   (fixed order)
-__global__ void colsum_kernel(const float* __restrict__ in, int P, int C, long long ld, float scale, float* __restrict__ out) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
+// out[c] = scale * sum_p in[p*ld + c]   (fixed order); block = 32 columns x 8 row lanes
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ in, int P, int C, long long ld, float scale, float* __restrict__ out) {
+    __shared__ float red[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + tx;
     float a = 0.f;
-    for (int p = 0; p < P; ++p) a += in[(size_t)p * ld + c];
-    out[c] = a * scale;
+    if (c < C) {
+#pragma unroll 4
+        for (int p = ty; p < P; p += 8) a += in[(size_t)p * ld + c];
+    }
+    red[ty][tx] = a;
+    __syncthreads();
+    if (ty == 0 && c < C) {
+        float t = red[0][tx];
+#pragma unroll
+        for (int i = 1; i < 8; ++i) t += red[i][tx];
+        out[c] = t * scale;
+    }
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -308,7 +345,7 @@ __device__ __forceinline__ float half_sum(float v) {     // sum over the 16 lane
 // Backward of GELU(LayerNorm64(pre)) per head group of 64 columns (tformer_lin.py:20,22): din = dL/d(GELU output).
 // A half-warp owns one (row, head) group, 4 columns per lane; block = 8 warps x 16 rows x 128 columns.
 __global__ void __launch_bounds__(256) ln64_bwd_kernel(const float* __restrict__ din, const float* __restrict__ pre,
-                                                       const float* __restrict__ gamma, const float* __restrict__ beta, int rows, int HD,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta, int rows, int HD, int rpw,
                                                        bf16* __restrict__ oh, bf16* __restrict__ ol, float* __restrict__ part) {
     __shared__ float red[8][2][128];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -317,8 +354,8 @@ __global__ void __launch_bounds__(256) ln64_bwd_kernel(const float* __restrict__
     const bool col_ok = col < HD;
     float4 g = make_float4(0.f, 0.f, 0.f, 0.f), bt = g, dg = g, db = g;
     if (col_ok) { g = *reinterpret_cast<const float4*>(gamma + col); bt = *reinterpret_cast<const float4*>(beta + col); }
-    for (int i = 0; i < 16; ++i) {
-        const size_t row = (size_t)blockIdx.y * 128 + w * 16 + i;
+    for (int i = 0; i < rpw; ++i) {
+        const size_t row = ((size_t)blockIdx.y * 8 + w) * rpw + i;
         const bool ok = col_ok && row < (size_t)rows;
         float4 p = make_float4(0.f, 0.f, 0.f, 0.f), d = p;
         if (ok) { p = *reinterpret_cast<const float4*>(pre + row * HD + col); d = *reinterpret_cast<const float4*>(din + row * HD + col); }
@@ -349,6 +386,23 @@ __global__ void __launch_bounds__(256) ln64_bwd_kernel(const float* __restrict__
         for (int i = 0; i < 8; ++i) s += red[i][which][c];
         part[((size_t)blockIdx.y * 2 + which) * HD + blockIdx.x * 128 + c] = s;
     }
+}
+
+// GELU(LayerNorm64(pre)) per head group, rows = slides (the summary branch after its split-K GEMM; tformer_lin.py:22).
+// One warp per row and 128-column slab (two head groups).
+__global__ void __launch_bounds__(256) ln64_fwd_kernel(const float* __restrict__ pre, const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, int rows, int HD, bf16* __restrict__ oh, bf16* __restrict__ ol) {
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int col = blockIdx.x * 128 + (lane >> 4) * 64 + (lane & 15) * 4;
+    const size_t row = (size_t)blockIdx.y * 8 + w;
+    const bool ok = col < HD && row < (size_t)rows;
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f), g = p, bt = p;
+    if (ok) { p = *reinterpret_cast<const float4*>(pre + row * HD + col); g = *reinterpret_cast<const float4*>(gamma + col); bt = *reinterpret_cast<const float4*>(beta + col); }
+    const float mean = half_sum(p.x + p.y + p.z + p.w) * (1.0f / 64.0f);
+    const float4 e = make_float4(p.x - mean, p.y - mean, p.z - mean, p.w - mean);
+    const float rstd = rsqrtf(half_sum(e.x * e.x + e.y * e.y + e.z * e.z + e.w * e.w) * (1.0f / 64.0f) + 1e-5f);
+    if (ok) store_planes4(oh, ol, row * HD + col, make_float4(gelu_f(e.x * rstd * g.x + bt.x), gelu_f(e.y * rstd * g.y + bt.y),
+                                                               gelu_f(e.z * rstd * g.z + bt.z), gelu_f(e.w * rstd * g.w + bt.w)));
 }
 
 // g[b*N + n, :] = scale * src[b, :]   (backward of the token mean, tformer_lin.py:103)
@@ -469,7 +523,6 @@ static int check_launch(const char* what) {
     return 0;
 }
 
-static inline dim3 grid_cols4(int D, int rows, int bd) { return dim3((D / 4 + bd - 1) / bd, rows); }
 
 static int launch_ln_rows_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma, const float* res,
                               int rows, int D, float* dx, bf16* dxh, bf16* dxl, float* part, float* dgamma_dbeta, cudaStream_t st) {
@@ -479,22 +532,23 @@ static int launch_ln_rows_bwd(const float* dy, const float* x, const float* mean
     else if (v <= 2) ln_rows_bwd_kernel<2><<<nblk, 256, 0, st>>>(dy, x, mean, rstd, gamma, res, rows, D, dx, dxh, dxl, part);
     else if (v <= 4) ln_rows_bwd_kernel<4><<<nblk, 256, 0, st>>>(dy, x, mean, rstd, gamma, res, rows, D, dx, dxh, dxl, part);
     else ln_rows_bwd_kernel<8><<<nblk, 256, 0, st>>>(dy, x, mean, rstd, gamma, res, rows, D, dx, dxh, dxl, part);
-    colsum_kernel<<<(2 * D + 255) / 256, 256, 0, st>>>(part, nblk, 2 * D, 2LL * D, 1.0f, dgamma_dbeta);   // gamma and beta are adjacent
+    colsum_kernel<<<(2 * D + 31) / 32, 256, 0, st>>>(part, nblk, 2 * D, 2LL * D, 1.0f, dgamma_dbeta);   // gamma and beta are adjacent
     return check_launch("ln_rows_bwd");
 }
 
 static int launch_ln64_bwd(const float* din, const float* pre, const float* gamma, const float* beta, int rows, int HD, bf16* oh, bf16* ol,
                            float* part, float* dgamma_dbeta, cudaStream_t st) {
-    const int nrb = (rows + 127) / 128;
-    ln64_bwd_kernel<<<dim3((HD + 127) / 128, nrb), 256, 0, st>>>(din, pre, gamma, beta, rows, HD, oh, ol, part);
-    colsum_kernel<<<(2 * HD + 255) / 256, 256, 0, st>>>(part, nrb, 2 * HD, 2LL * HD, 1.0f, dgamma_dbeta);
+    const int rpw = rows >= 1024 ? 16 : 1;
+    const int nrb = (rows + 8 * rpw - 1) / (8 * rpw);
+    ln64_bwd_kernel<<<dim3((HD + 127) / 128, nrb), 256, 0, st>>>(din, pre, gamma, beta, rows, HD, rpw, oh, ol, part);
+    colsum_kernel<<<(2 * HD + 31) / 32, 256, 0, st>>>(part, nrb, 2 * HD, 2LL * HD, 1.0f, dgamma_dbeta);
     return check_launch("ln64_bwd");
 }
 
 // bias gradient: column sums of a [rows, C] planes matrix, rows = groups * gs; via per-slide sums (fixed order)
 static int launch_bias_grad(const bf16* hi, const bf16* lo, int groups, int gs, int C, float* gsum, float* out, cudaStream_t st) {
-    group_sum_planes_kernel<<<dim3((C / 2 + 127) / 128, groups), 128, 0, st>>>(hi, lo, C, gs, C, gsum, nullptr, nullptr);
-    colsum_kernel<<<(C + 255) / 256, 256, 0, st>>>(gsum, groups, C, C, 1.0f, out);
+    group_sum_planes_kernel<<<dim3((C + 255) / 256, groups), 256, 0, st>>>(hi, lo, C, gs, C, gsum, nullptr, nullptr);
+    colsum_kernel<<<(C + 31) / 32, 256, 0, st>>>(gsum, groups, C, C, 1.0f, out);
     return check_launch("bias_grad");
 }
 
@@ -508,18 +562,19 @@ static int vis_forward(const VisDims& d, const VisLayout& P, const float* prm, c
         const LayerOff& o = P.lay[l];
         float* x = (float*)(act + a.x_f32);
         if (l == 0) {
-            prep_input_kernel<<<grid_cols4(D, B, 64), 64, 0, st>>>(x_in, prm + P.pos, x, (bf16*)(act + a.x_hi), (bf16*)(act + a.x_lo),
-                                                                   (bf16*)(act + a.xm_hi), (bf16*)(act + a.xm_lo), N, D);
-        } else {
-            group_mean_kernel<<<grid_cols4(D, B, 64), 64, 0, st>>>(x, N, D, 1.0f / (float)N, nullptr, (bf16*)(act + a.xm_hi), (bf16*)(act + a.xm_lo));
+            prep_input_kernel<<<148 * 8, 256, 0, st>>>(x_in, prm + P.pos, x, (bf16*)(act + a.x_hi), (bf16*)(act + a.x_lo), N, D, (long long)M * D / 4);
         }
+        group_mean_kernel<<<dim3((D + 127) / 128, B), 256, 0, st>>>(x, N, D, 1.0f / (float)N, nullptr, (bf16*)(act + a.xm_hi), (bf16*)(act + a.xm_lo));
         SQ_TRY(check_launch("vis prep"));
         // local branch, all heads: GELU(LN64(x Wf^T + bf))                       tformer_lin.py:20
         SQ_TRY(GB(M, HD, D).A(act + a.x_hi, act + a.x_lo, D).B(wh + o.wf, wl + o.wf, D).bias(prm + o.bf).ln64(prm + o.lnl_g, prm + o.lnl_b)
                    .save_pre((float*)(act + a.fpre), HD).out_planes(act + a.loc_hi, act + a.loc_lo, HD).run(st));
         // summary branch on the token mean: GELU(LN64(mean(x) Ws^T + bs))           tformer_lin.py:21-22
-        SQ_TRY(GB(B, HD, D).A(act + a.xm_hi, act + a.xm_lo, D).B(wh + o.ws, wl + o.ws, D).bias(prm + o.bs).ln64(prm + o.lns_g, prm + o.lns_b)
-                   .save_pre((float*)(act + a.spre), HD).out_planes(act + a.t_hi, act + a.t_lo, HD).bn(128).auto_split(sk, A.splitk_bytes).run(st));
+        SQ_TRY(GB(B, HD, D).A(act + a.xm_hi, act + a.xm_lo, D).B(wh + o.ws, wl + o.ws, D).bias(prm + o.bs).out_f32((float*)(act + a.spre), HD)
+                   .bn(128).auto_split(sk, A.splitk_bytes).run(st));
+        ln64_fwd_kernel<<<dim3((HD + 127) / 128, (B + 7) / 8), 256, 0, st>>>((const float*)(act + a.spre), prm + o.lns_g, prm + o.lns_b, B, HD,
+                                                                            (bf16*)(act + a.t_hi), (bf16*)(act + a.t_lo));
+        SQ_TRY(check_launch("vis ln64 fwd"));
         // per-slide row bias: Wc[:, 64:] t + bc (per head)                          tformer_lin.py:23-24
         SQ_TRY(GB(B, HD, 64).A(act + a.t_hi, act + a.t_lo, HD).akoff(64).B(wh + o.wc + 64, wl + o.wc + 64, 128).bn(64).bias(prm + o.bc)
                    .out_f32((float*)(act + a.rb), HD).run(st));
@@ -544,7 +599,7 @@ static int vis_forward(const VisDims& d, const VisLayout& P, const float* prm, c
         SQ_TRY(g2.run(st));
     }
     // token mean, head LayerNorm, gene regression head                              tformer_lin.py:103-106
-    group_mean_kernel<<<grid_cols4(D, B, 64), 64, 0, st>>>((const float*)(act + A.xL), N, D, 1.0f / (float)N, (float*)(act + A.pooled), nullptr, nullptr);
+    group_mean_kernel<<<dim3((D + 127) / 128, B), 256, 0, st>>>((const float*)(act + A.xL), N, D, 1.0f / (float)N, (float*)(act + A.pooled), nullptr, nullptr);
     ln_rows_fwd_kernel<<<B, 256, 0, st>>>((const float*)(act + A.pooled), prm + P.hg, prm + P.hb, D, 1e-5f, (float*)(act + A.hmean),
                                           (float*)(act + A.hrstd), (bf16*)(act + A.z_hi), (bf16*)(act + A.z_lo));
     SQ_TRY(check_launch("vis head ln"));
@@ -559,7 +614,7 @@ static int vis_backward_head(const VisDims& d, const VisLayout& P, const float* 
     SQ_TRY(split_planes(dpred, (bf16*)(sc + S.dp_hi), (bf16*)(sc + S.dp_lo), B, G, G, d.Gpad, st));
     // dWh = dpred^T z ; dbh = colsum(dpred)
     SQ_TRY(GB(G, D, B).A(sc + S.dp_hi, sc + S.dp_lo, d.Gpad, 1).B(act + A.z_hi, act + A.z_lo, D, 1).out_f32(grads + P.wh, D).run(st));
-    colsum_kernel<<<(G + 255) / 256, 256, 0, st>>>(dpred, B, G, G, 1.0f, grads + P.bh);
+    colsum_kernel<<<(G + 31) / 32, 256, 0, st>>>(dpred, B, G, G, 1.0f, grads + P.bh);
     // dz = dpred Wh
     SQ_TRY(GB(B, D, G).A(sc + S.dp_hi, sc + S.dp_lo, d.Gpad).B(wh + P.wh, wl + P.wh, D, 1).out_f32((float*)(sc + S.dz), D)
                .auto_split(sc + S.splitk, S.splitk_bytes).run(st));
@@ -597,11 +652,12 @@ static int vis_backward_layer(const VisDims& d, const VisLayout& P, int l, const
     // dlocal = dCpre Wc[:, :64] per head ; dWc[:, :64] = dCpre^T local per head
     SQ_TRY(GB(M, HD, 64).A(sc + S.dc_hi, sc + S.dc_lo, HD).akoff(64).B(wh + o.wc, wl + o.wc, 128, 1).bdiag_dgrad(64, HD).bn(64)
                .out_f32((float*)(sc + S.dlocal), HD).run(st));
-    SQ_TRY(GB(HD, HD, M).A(sc + S.dc_hi, sc + S.dc_lo, HD, 1).B(act + a.loc_hi, act + a.loc_lo, HD, 1).diag64().out_f32(grads + o.wc, 128).run(st));
+    SQ_TRY(GB(HD, HD, M).A(sc + S.dc_hi, sc + S.dc_lo, HD, 1).B(act + a.loc_hi, act + a.loc_lo, HD, 1).diag64().out_f32(grads + o.wc, 128)
+               .auto_split(sc + S.splitk, S.splitk_bytes).run(st));
     // per-slide sums of dCpre: gradient of the row bias (and of bc)
-    group_sum_planes_kernel<<<dim3((HD / 2 + 127) / 128, B), 128, 0, st>>>((bf16*)(sc + S.dc_hi), (bf16*)(sc + S.dc_lo), HD, N, HD, (float*)(sc + S.drb),
+    group_sum_planes_kernel<<<dim3((HD + 255) / 256, B), 256, 0, st>>>((bf16*)(sc + S.dc_hi), (bf16*)(sc + S.dc_lo), HD, N, HD, (float*)(sc + S.drb),
                                                                            (bf16*)(sc + S.drb_hi), (bf16*)(sc + S.drb_lo));
-    colsum_kernel<<<(HD + 255) / 256, 256, 0, st>>>((const float*)(sc + S.drb), B, HD, HD, 1.0f, grads + o.bc);
+    colsum_kernel<<<(HD + 31) / 32, 256, 0, st>>>((const float*)(sc + S.drb), B, HD, HD, 1.0f, grads + o.bc);
     SQ_TRY(check_launch("vis drb"));
     SQ_TRY(launch_ln64_bwd((const float*)(sc + S.dlocal), (const float*)(act + a.fpre), prm + o.lnl_g, prm + o.lnl_b, M, HD, (bf16*)(sc + S.df_hi),
                            (bf16*)(sc + S.df_lo), part, grads + o.lnl_g, st));
@@ -612,7 +668,7 @@ static int vis_backward_layer(const VisDims& d, const VisLayout& P, int l, const
     SQ_TRY(launch_ln64_bwd((const float*)(sc + S.dt), (const float*)(act + a.spre), prm + o.lns_g, prm + o.lns_b, B, HD, (bf16*)(sc + S.ds_hi),
                            (bf16*)(sc + S.ds_lo), part, grads + o.lns_g, st));
     SQ_TRY(GB(HD, D, B).A(sc + S.ds_hi, sc + S.ds_lo, HD, 1).B(act + a.xm_hi, act + a.xm_lo, D, 1).out_f32(grads + o.ws, D).run(st));
-    group_sum_planes_kernel<<<dim3((HD / 2 + 127) / 128, 1), 128, 0, st>>>((bf16*)(sc + S.ds_hi), (bf16*)(sc + S.ds_lo), HD, B, HD, grads + o.bs, nullptr, nullptr);
+    group_sum_planes_kernel<<<dim3((HD + 255) / 256, 1), 256, 0, st>>>((bf16*)(sc + S.ds_hi), (bf16*)(sc + S.ds_lo), HD, B, HD, grads + o.bs, nullptr, nullptr);
     SQ_TRY(check_launch("vis dbs"));
     SQ_TRY(GB(B, D, HD).A(sc + S.ds_hi, sc + S.ds_lo, HD).B(wh + o.ws, wl + o.ws, D, 1).alpha(1.0f / (float)N).out_f32((float*)(sc + S.dxm), D)
                .auto_split(sc + S.splitk, S.splitk_bytes).run(st));

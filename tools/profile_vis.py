@@ -30,7 +30,7 @@ e.record()
 t_cpu = time.perf_counter() - t0
 torch.cuda.synchronize()
 ms = s.elapsed_time(e) / max(steps, 1)
-print(f"[vis train] {ms:.3f} ms/step (host enqueue {t_cpu / max(steps,1) * 1e3:.3f} ms/step) -> {B / ms * 1e3:.1f} slides/s, loss {loss.item():.5f}")
+if steps: print(f"[vis train] {ms:.3f} ms/step (host enqueue {t_cpu / max(steps,1) * 1e3:.3f} ms/step) -> {B / ms * 1e3:.1f} slides/s, loss {loss.item():.5f}")
 if steps:
     m.eval()
     with torch.no_grad():
