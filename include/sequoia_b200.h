@@ -153,6 +153,23 @@ SQ_API int sq_mse_fwd_bwd(const float* pred, const float* target, int batch, int
 SQ_API int sq_adamw_flat(float* p, const float* g, float* m, float* v, void* p_hi, void* p_lo, long long n, float lr, float beta1,
                          float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream);
 
+/* ------------------------------------------------------------------ per-slide k-means reduction
+ * Replaces `KMeans(n_clusters=100, random_state=0).fit(features)` and the per-label mean loop of
+ * pre_processing/kmean_features.py:96-105 (the arithmetic is scikit-learn's: init='k-means++', n_init=1,
+ * max_iter=300, tol=1e-4, algorithm='lloyd').  features: fp32 [n, d] (d % 4 == 0), device.
+ * The MT19937 draws are data independent and come from the caller:
+ *   first_center = RandomState(seed).choice(n, p=uniform);  uniforms = the next (k-1)*trials .uniform() doubles (device),
+ *   trials = 2 + int(ln k).
+ * Outputs (device): labels int32 [n]; cluster_means fp32 [k, d] = mean of the RAW rows of every label, ascending row
+ * order (a row of NaN for an empty label, like np.mean); chosen (may be NULL) int32 [k] = k-means++ seed rows.
+ * n_iter_host (may be NULL) receives sklearn's n_iter_.  UNLIKE the other entry points this one synchronises the stream
+ * once per Lloyd iteration (the convergence test decides on the host whether another iteration is enqueued).
+ * Returns -2 if an iteration produces an empty cluster (sklearn's relocation step is not implemented). */
+SQ_API size_t sq_kmeans_workspace_bytes(int n, int d, int k);
+SQ_API int sq_kmeans_fit(const float* features, int n, int d, int k, int trials, int first_center, const double* uniforms,
+                         int max_iter, float tol_scale, int* labels, float* cluster_means, int* chosen, int* n_iter_host,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

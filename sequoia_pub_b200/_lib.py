@@ -70,6 +70,9 @@ SIGNATURES = {
     "sq_mse_fwd_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "sq_adamw_flat": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_float, c_float, c_float,
                               c_float, c_float, c_int, c_float, c_void_p]),
+    "sq_kmeans_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "sq_kmeans_fit": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p,
+                              C.POINTER(c_int), c_void_p, c_size_t, c_void_p]),
 }
 
 _lib = None

@@ -1,0 +1,533 @@
+// Per-slide k-means reduction (reference: pre_processing/kmean_features.py:96-105 —
+// `KMeans(n_clusters=100, random_state=0).fit(features)` followed by the per-label mean of the raw features).
+// The algorithm is scikit-learn's (sklearn/cluster/_kmeans.py: fit, _kmeans_plusplus, _kmeans_single_lloyd;
+// _k_means_lloyd.pyx); this file re-expresses it for one B200 with every order-dependent float operation that can
+// change a LABEL kept in sklearn's order:
+//   * column mean / centring: sequential float32 over rows (numpy add.reduce over axis 0);
+//   * k-means++ distances: float64 (sklearn upcasts float32 chunks), rounded to float32, clamped at 0;
+//   * the potential sums `closest @ w`, `dist @ w`: the summation orders of the OpenBLAS 0.3.30 x86-64 sdot / sgemv_t
+//     kernels numpy dispatches to (restated and pinned against numpy in oracle/kmeans_oracle.py);
+//   * cumsum for the candidate draw: sequential float32; searchsorted(left) against float64 rand_vals;
+//   * Lloyd: D = ||c||^2 - 2 x.c in float32 FMA, first-minimum argmin, centres = ascending-row sums * (1/count);
+//   * cluster features: ascending-row float32 sums of the RAW features divided by the count (np.mean(axis=0)).
+// The MT19937 draws (RandomState(0).choice / .uniform) are data independent and are produced on the host by the caller.
+// Everything is deterministic (integer atomics only).
+#include "gemm.cuh"
+#include "../../include/sequoia_b200.h"
+
+namespace sq {
+
+constexpr int KM_NB = 4096;          // OpenBLAS sgemv_t block length
+constexpr int KM_MAXT = 8;           // max local trials
+
+struct KmFlags { int n_changed; int tol_ok; int n_empty; int pad; float shift_tot; float tol; };
+
+// ---------------------------------------------------------------- preparation
+// One thread per column: sequential float32 sum over rows (numpy's order), mean = sum / n; second pass: variance.
+__global__ void km_colstats_kernel(const float* __restrict__ X, int n, int d, float* __restrict__ mean, float* __restrict__ var) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= d) return;
+    float s = 0.f;
+    int i = 0;
+    for (; i + 8 <= n; i += 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = X[(size_t)(i + u) * d + j];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s = __fadd_rn(s, v[u]);
+    }
+    for (; i < n; ++i) s = __fadd_rn(s, X[(size_t)i * d + j]);
+    const float m = __fdiv_rn(s, (float)n);
+    mean[j] = m;
+    float q = 0.f;
+    for (i = 0; i + 8 <= n; i += 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const float e = __fsub_rn(X[(size_t)(i + u) * d + j], m); v[u] = __fmul_rn(e, e); }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) q = __fadd_rn(q, v[u]);
+    }
+    for (; i < n; ++i) { const float e = __fsub_rn(X[(size_t)i * d + j], m); q = __fadd_rn(q, __fmul_rn(e, e)); }
+    var[j] = __fdiv_rn(q, (float)n);
+}
+
+// tol = mean(var) * tol_scale (sklearn _tolerance); single block
+__global__ void km_tol_kernel(const float* __restrict__ var, int d, float tol_scale, KmFlags* flags) {
+    __shared__ double red[256];
+    double s = 0.0;
+    for (int j = threadIdx.x; j < d; j += 256) s += (double)var[j];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o]; __syncthreads(); }
+    if (threadIdx.x == 0) flags->tol = (float)(red[0] / d) * tol_scale;
+}
+
+// Xc = X - mean (float32), xx64[i] = sum_k (double)Xc[i,k]^2 ; one warp per row
+__global__ void km_center_kernel(const float* __restrict__ X, const float* __restrict__ mean, int n, int d, float* __restrict__ Xc,
+                                 double* __restrict__ xx64) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= n) return;
+    double acc = 0.0;
+    for (int c = lane * 4; c < d; c += 128) {
+        const float4 v = *reinterpret_cast<const float4*>(X + (size_t)row * d + c);
+        const float4 m = *reinterpret_cast<const float4*>(mean + c);
+        const float4 e = make_float4(__fsub_rn(v.x, m.x), __fsub_rn(v.y, m.y), __fsub_rn(v.z, m.z), __fsub_rn(v.w, m.w));
+        *reinterpret_cast<float4*>(Xc + (size_t)row * d + c) = e;
+        acc += (double)e.x * e.x + (double)e.y * e.y + (double)e.z * e.z + (double)e.w * e.w;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) xx64[row] = acc;
+}
+
+// ---------------------------------------------------------------- k-means++ seeding
+// out[t][i] = min(closest[i], float32(max(0, (-2 <x_cand_t, x_i> + ||x_cand_t||^2) + ||x_i||^2))) in float64.
+// One warp per pair of rows; candidate rows are read through L1.
+template <int T>
+__global__ void __launch_bounds__(256) km_dist_kernel(const float* __restrict__ Xc, const double* __restrict__ xx64, const int* __restrict__ cand,
+                                                      const float* __restrict__ closest, int n, int d, float* __restrict__ out) {
+    const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    const int r0 = warp * 2;
+    if (r0 >= n) return;
+    const int r1 = min(r0 + 1, n - 1);
+    int ci[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) ci[t] = cand[t];
+    double acc0[T], acc1[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) { acc0[t] = 0.0; acc1[t] = 0.0; }
+    for (int c = lane * 4; c < d; c += 128) {
+        const float4 a = *reinterpret_cast<const float4*>(Xc + (size_t)r0 * d + c);
+        const float4 b = *reinterpret_cast<const float4*>(Xc + (size_t)r1 * d + c);
+        const double a0 = a.x, a1 = a.y, a2 = a.z, a3 = a.w, b0 = b.x, b1 = b.y, b2 = b.z, b3 = b.w;
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(Xc + (size_t)ci[t] * d + c));
+            const double q0 = q.x, q1 = q.y, q2 = q.z, q3 = q.w;
+            acc0[t] = fma(a0, q0, fma(a1, q1, fma(a2, q2, fma(a3, q3, acc0[t]))));
+            acc1[t] = fma(b0, q0, fma(b1, q1, fma(b2, q2, fma(b3, q3, acc1[t]))));
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            acc0[t] += __shfl_xor_sync(0xffffffffu, acc0[t], o);
+            acc1[t] += __shfl_xor_sync(0xffffffffu, acc1[t], o);
+        }
+    }
+    if (lane < 2 * T) {
+        const int t = lane >> 1, which = lane & 1;
+        const int r = which ? r1 : r0;
+        if (which == 0 || r0 + 1 < n) {
+            double dot = 0.0;
+#pragma unroll
+            for (int u = 0; u < T; ++u) if (u == t) dot = which ? acc1[u] : acc0[u];
+            double dd = __dmul_rn(-2.0, dot);
+            dd = __dadd_rn(dd, xx64[ci[t]]);
+            dd = __dadd_rn(dd, xx64[r]);
+            float f = (float)dd;                      // round to nearest even, like astype(float32)
+            f = fmaxf(f, 0.0f);
+            if (closest) f = fminf(closest[r], f);
+            out[(size_t)t * n + r] = f;
+        }
+    }
+}
+
+// OpenBLAS sgemv_t summation order of row `a` (n floats) for column-kernel kind 0 (4-column AVX2 kernel) / 1 (2-column).
+// Executed by 8 cooperating lanes (l = 0..7) of one warp-aligned group; returns the result in lane 0.
+__device__ float km_gemv_order(const float* __restrict__ a, int n, int kind, int l, unsigned mask, int base_lane) {
+    const int m1 = n - (n & 3);
+    float y = 0.f;
+    for (int b0 = 0; b0 < m1; b0 += KM_NB) {
+        const int len = min(KM_NB, m1 - b0);
+        float acc = 0.f;
+        if (kind == 0) {
+            int i = b0;
+            if (len & 4) { if (l < 4) acc = a[b0 + l]; i += 4; }
+            for (; i < b0 + len; i += 8) acc = __fadd_rn(acc, a[i + l]);
+        } else if (l < 4) {
+            for (int i = b0; i < b0 + len; i += 4) acc = __fadd_rn(acc, a[i + l]);
+        }
+        // fold: kind 0: s4[j] = acc[j] + acc[j+4]; then (s0+s1)+(s2+s3)
+        float s = acc;
+        if (kind == 0) s = __fadd_rn(acc, __shfl_sync(mask, acc, base_lane + ((l + 4) & 7)));
+        const float p01 = __fadd_rn(__shfl_sync(mask, s, base_lane + 0), __shfl_sync(mask, s, base_lane + 1));
+        const float p23 = __fadd_rn(__shfl_sync(mask, s, base_lane + 2), __shfl_sync(mask, s, base_lane + 3));
+        y = __fadd_rn(y, __fadd_rn(p01, p23));
+    }
+    if (n & 3) {
+        float t = a[m1];
+        for (int i = m1 + 1; i < n; ++i) t = __fadd_rn(t, a[i]);
+        y = __fadd_rn(y, t);
+    }
+    return y;
+}
+
+// One block (1024 threads) per seeding step: potentials in BLAS order -> best candidate -> closest := its row ->
+// sequential float32 cumsum -> next candidates by searchsorted(left) of uniform * pot.
+// step 0: `newc` holds the distances to the first centre (T_in = 1, potential through the sdot order).
+__global__ void __launch_bounds__(1024) km_select_kernel(const float* __restrict__ newc, int T_in, int n, int step, int k, int T_next,
+                                                         const double* __restrict__ uniforms, float* __restrict__ closest, int* __restrict__ cand,
+                                                         int* __restrict__ chosen, float* __restrict__ pot_io) {
+    extern __shared__ float cs[];                  // n floats: closest, then its cumsum
+    __shared__ float pots[KM_MAXT];
+    __shared__ float acc16[64];
+    __shared__ int s_best;
+    __shared__ float s_pot;
+    __shared__ int counts[KM_MAXT];
+    const int tid = threadIdx.x;
+    if (step == 0) {
+        // cblas_sdot order (see oracle/kmeans_oracle.py: blas_order_sdot)
+        const int n32 = n & ~31, n64 = n32 & ~63;
+        if (tid < 64) {
+            float a = 0.f;
+            for (int b = 0; b < n64; b += 64) a = __fadd_rn(a, newc[b + tid]);
+            acc16[tid] = a;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            float acc[4][8];
+            for (int u = 0; u < 4; ++u)
+                for (int l = 0; l < 8; ++l) acc[u][l] = __fadd_rn(acc16[u * 16 + l], acc16[u * 16 + l + 8]);
+            if (n32 - n64 == 32)
+                for (int u = 0; u < 4; ++u)
+                    for (int l = 0; l < 8; ++l) acc[u][l] = __fadd_rn(acc[u][l], newc[n64 + u * 8 + l]);
+            float t8[8];
+            for (int l = 0; l < 8; ++l) t8[l] = __fadd_rn(__fadd_rn(__fadd_rn(acc[0][l], acc[1][l]), acc[2][l]), acc[3][l]);
+            float s = 0.f;
+            if (n32) {
+                const float h0 = __fadd_rn(t8[0], t8[4]), h1 = __fadd_rn(t8[1], t8[5]), h2 = __fadd_rn(t8[2], t8[6]), h3 = __fadd_rn(t8[3], t8[7]);
+                s = __fadd_rn(__fadd_rn(h0, h1), __fadd_rn(h2, h3));
+            }
+            double dsum = (double)s;
+            for (int i = n32; i < n; ++i) dsum += (double)newc[i];
+            s_pot = (float)dsum; s_best = 0;
+        }
+    } else {
+        // cblas_sgemv order per candidate row (blas_order_gemv_row): warp w handles rows 4w..4w+3, 8 lanes each
+        const int w = tid >> 5, lane = tid & 31;
+        const int t = w * 4 + (lane >> 3), l = lane & 7;
+        if (w * 4 < T_in) {
+            const int rem = T_in & 3;
+            const int tt = min(t, T_in - 1);
+            const int kind = tt < T_in - rem ? 0 : 1;
+            const float y = km_gemv_order(newc + (size_t)tt * n, n, kind, l, 0xffffffffu, lane & ~7);
+            if (l == 0 && t < T_in) pots[t] = y;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int best = 0;
+            for (int t2 = 1; t2 < T_in; ++t2) if (pots[t2] < pots[best]) best = t2;      // np.argmin: first minimum
+            s_best = best; s_pot = pots[best];
+        }
+    }
+    __syncthreads();
+    const int best = s_best;
+    const float pot = s_pot;
+    if (tid == 0) { chosen[step] = cand[best]; *pot_io = pot; }
+    for (int i = tid; i < n; i += blockDim.x) { const float v = newc[(size_t)best * n + i]; closest[i] = v; cs[i] = v; }
+    if (tid < KM_MAXT) counts[tid] = 0;
+    __syncthreads();
+    if (step + 1 >= k) return;
+    if (tid == 0) {                                  // np.cumsum(float32): strictly sequential
+        float a = 0.f;
+        for (int i = 0; i < n; ++i) { a = __fadd_rn(a, cs[i]); cs[i] = a; }
+    }
+    __syncthreads();
+    for (int t = 0; t < T_next; ++t) {
+        const double rv = __dmul_rn(uniforms[(size_t)step * T_next + t], (double)pot);
+        int c = 0;
+        for (int i = tid; i < n; i += blockDim.x) c += ((double)cs[i] < rv) ? 1 : 0;     // searchsorted side='left'
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if ((tid & 31) == 0 && c) atomicAdd(&counts[t], c);
+    }
+    __syncthreads();
+    if (tid < T_next) cand[tid] = min(counts[tid], n - 1);
+}
+
+// ---------------------------------------------------------------- Lloyd iterations
+__global__ void km_gather_centers_kernel(const float* __restrict__ Xc, const int* __restrict__ chosen, int k, int d, float* __restrict__ centers) {
+    const int j = blockIdx.x;
+    for (int c = threadIdx.x * 4; c < d; c += blockDim.x * 4)
+        *reinterpret_cast<float4*>(centers + (size_t)j * d + c) = *reinterpret_cast<const float4*>(Xc + (size_t)chosen[j] * d + c);
+}
+
+__global__ void km_center_norm_kernel(const float* __restrict__ centers, int k, int d, float* __restrict__ csq) {
+    const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (j >= k) return;
+    float a = 0.f;
+    for (int c = lane; c < d; c += 32) { const float v = centers[(size_t)j * d + c]; a = fmaf(v, v, a); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) csq[j] = a;
+}
+
+// label[i] = first argmin_j (csq[j] - 2 <x_i, c_j>) in float32.  Block = 32 rows x 128 centres (looping over centre
+// tiles when k > 128), 256 threads, each 2 rows x 8 centres; K is consumed in chunks of 32 through shared memory.
+__global__ void __launch_bounds__(256) km_assign_kernel(const float* __restrict__ Xc, const float* __restrict__ centers, const float* __restrict__ csq,
+                                                        int n, int d, int k, const int* __restrict__ labels_old, int* __restrict__ labels,
+                                                        KmFlags* flags) {
+    __shared__ float Xs[32][33];      // [k][row]
+    __shared__ float Cs[32][129];     // [k][centre]
+    __shared__ float bestv[32][16];
+    __shared__ int besti[32][16];
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;          // tx: centre group (8 centres), ty: row pair
+    const int row0 = blockIdx.x * 32;
+    float rbest[2] = {INFINITY, INFINITY};
+    int ribest[2] = {0, 0};
+    for (int j0 = 0; j0 < k; j0 += 128) {
+        float acc[2][8];
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[r][c] = 0.f;
+        for (int k0 = 0; k0 < d; k0 += 32) {
+            // stage 32 rows x 32 k of X and 128 centres x 32 k of C (transposed into [k][*])
+            for (int e = tid; e < 32 * 32; e += 256) {
+                const int r = e >> 5, kk = e & 31;
+                const int row = row0 + r;
+                Xs[kk][r] = (row < n && k0 + kk < d) ? Xc[(size_t)row * d + k0 + kk] : 0.f;
+            }
+            for (int e = tid; e < 128 * 32; e += 256) {
+                const int c = e >> 5, kk = e & 31;
+                const int j = j0 + c;
+                Cs[kk][c] = (j < k && k0 + kk < d) ? centers[(size_t)j * d + k0 + kk] : 0.f;
+            }
+            __syncthreads();
+#pragma unroll 8
+            for (int kk = 0; kk < 32; ++kk) {
+                const float x0 = Xs[kk][ty * 2], x1 = Xs[kk][ty * 2 + 1];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float cv = Cs[kk][tx + 16 * c];
+                    acc[0][c] = fmaf(x0, cv, acc[0][c]);
+                    acc[1][c] = fmaf(x1, cv, acc[1][c]);
+                }
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int j = j0 + tx + 16 * c;
+                if (j < k) {
+                    const float dist = fmaf(-2.0f, acc[r][c], csq[j]);
+                    if (dist < rbest[r] || (dist == rbest[r] && j < ribest[r])) { rbest[r] = dist; ribest[r] = j; }
+                }
+            }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) { bestv[ty * 2 + r][tx] = rbest[r]; besti[ty * 2 + r][tx] = ribest[r]; }
+    __syncthreads();
+    if (tid < 32) {
+        const int row = row0 + tid;
+        if (row < n) {
+            float bv = bestv[tid][0]; int bi = besti[tid][0];
+            for (int t = 1; t < 16; ++t) {
+                const float v = bestv[tid][t]; const int i2 = besti[tid][t];
+                if (v < bv || (v == bv && i2 < bi)) { bv = v; bi = i2; }
+            }
+            labels[row] = bi;
+            if (labels_old && labels_old[row] != bi) atomicAdd(&flags->n_changed, 1);
+        }
+    }
+}
+
+// Stable bucketing of rows by label: members[offsets[j] .. offsets[j+1]) = rows with label j, ascending. One block.
+__global__ void __launch_bounds__(1024) km_bucket_kernel(const int* __restrict__ labels, int n, int k, int* __restrict__ offsets,
+                                                         int* __restrict__ members, KmFlags* flags) {
+    extern __shared__ int sl[];                    // n labels, then k+1 offsets
+    int* soff = sl + n;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) sl[i] = labels[i];
+    for (int j = threadIdx.x; j <= k; j += blockDim.x) soff[j] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&soff[sl[i] + 1], 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int empty = 0;
+        for (int j = 0; j < k; ++j) { if (soff[j + 1] == 0) ++empty; soff[j + 1] += soff[j]; }
+        flags->n_empty = empty;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j <= k; j += blockDim.x) offsets[j] = soff[j];
+    for (int j = threadIdx.x; j < k; j += blockDim.x) {
+        int p = soff[j];
+        for (int i = 0; i < n; ++i) if (sl[i] == j) members[p++] = i;
+    }
+}
+
+// out[j, c] = (sum over members of cluster j, ascending rows, of src[row, c]) * (1/count)   [mode 0: sklearn _average_centers]
+//                                                                          / count          [mode 1: np.mean]
+// and, when `old` is given, per-(cluster, block) partial sums of (new - old)^2 for the centre shift.
+__global__ void __launch_bounds__(128) km_segment_mean_kernel(const float* __restrict__ src, const int* __restrict__ offsets,
+                                                              const int* __restrict__ members, int d, int mode, float* __restrict__ out,
+                                                              const float* __restrict__ old, float* __restrict__ shift_part) {
+    __shared__ float red[4];
+    const int j = blockIdx.y;
+    const int c = (blockIdx.x * 128 + threadIdx.x) * 4;
+    const int b = offsets[j], e = offsets[j + 1];
+    float sq = 0.f;
+    if (c < d) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int p = b; p < e; ++p) {
+            const float4 v = *reinterpret_cast<const float4*>(src + (size_t)members[p] * d + c);
+            a.x = __fadd_rn(a.x, v.x); a.y = __fadd_rn(a.y, v.y); a.z = __fadd_rn(a.z, v.z); a.w = __fadd_rn(a.w, v.w);
+        }
+        const float cnt = (float)(e - b);
+        if (mode == 0) { const float inv = __fdiv_rn(1.0f, cnt); a.x = __fmul_rn(a.x, inv); a.y = __fmul_rn(a.y, inv); a.z = __fmul_rn(a.z, inv); a.w = __fmul_rn(a.w, inv); }
+        else { a.x = __fdiv_rn(a.x, cnt); a.y = __fdiv_rn(a.y, cnt); a.z = __fdiv_rn(a.z, cnt); a.w = __fdiv_rn(a.w, cnt); }
+        *reinterpret_cast<float4*>(out + (size_t)j * d + c) = a;
+        if (old) {
+            const float4 o = *reinterpret_cast<const float4*>(old + (size_t)j * d + c);
+            const float e0 = a.x - o.x, e1 = a.y - o.y, e2 = a.z - o.z, e3 = a.w - o.w;
+            sq = e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3;
+        }
+    }
+    if (old) {
+#pragma unroll
+        for (int o2 = 16; o2 > 0; o2 >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o2);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sq;
+        __syncthreads();
+        if (threadIdx.x == 0) shift_part[(size_t)j * gridDim.x + blockIdx.x] = (red[0] + red[1]) + (red[2] + red[3]);
+    }
+}
+
+// center_shift_tot = sum_j ||new_j - old_j||^2 ; tol test (sklearn L717-727)
+__global__ void km_converge_kernel(const float* __restrict__ shift_part, int k, int nparts, KmFlags* flags) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    float tot = 0.f;
+    for (int j = 0; j < k; ++j) {
+        float s = 0.f;
+        for (int p = 0; p < nparts; ++p) s += shift_part[(size_t)j * nparts + p];
+        const float sh = sqrtf(s);
+        tot += sh * sh;
+    }
+    flags->shift_tot = tot;
+    flags->tol_ok = tot <= flags->tol ? 1 : 0;
+}
+
+struct KmWs { size_t xc, xx64, mean, var, closest, newc, cand, chosen, pot, cA, cB, csq, labels_old, offsets, members, shift, flags, total; };
+
+static void km_ws_layout(int n, int d, int k, KmWs* w) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) / 256 * 256; return o; };
+    w->xc = take((size_t)n * d * 4); w->xx64 = take((size_t)n * 8); w->mean = take((size_t)d * 4); w->var = take((size_t)d * 4);
+    w->closest = take((size_t)n * 4); w->newc = take((size_t)KM_MAXT * n * 4); w->cand = take(KM_MAXT * 4); w->chosen = take((size_t)k * 4);
+    w->pot = take(4); w->cA = take((size_t)k * d * 4); w->cB = take((size_t)k * d * 4); w->csq = take((size_t)k * 4);
+    w->labels_old = take((size_t)n * 4); w->offsets = take((size_t)(k + 1) * 4); w->members = take((size_t)n * 4);
+    w->shift = take((size_t)k * ((d + 511) / 512) * 4); w->flags = take(sizeof(KmFlags));
+    w->total = off;
+}
+
+template <int T>
+static void launch_dist(const float* Xc, const double* xx64, const int* cand, const float* closest, int n, int d, float* out, cudaStream_t st) {
+    const int warps = (n + 1) / 2;
+    km_dist_kernel<T><<<(warps + 7) / 8, 256, 0, st>>>(Xc, xx64, cand, closest, n, d, out);
+}
+
+}  // namespace sq
+
+using namespace sq;
+
+extern "C" {
+
+size_t sq_kmeans_workspace_bytes(int n, int d, int k) {
+    if (n <= 0 || d <= 0 || k <= 0) return 0;
+    KmWs w; km_ws_layout(n, d, k, &w);
+    return w.total;
+}
+
+int sq_kmeans_fit(const float* features, int n, int d, int k, int trials, int first_center, const double* uniforms, int max_iter, float tol_scale,
+                  int* labels, float* cluster_means, int* chosen_out, int* n_iter_host, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!features || !uniforms || !labels || !cluster_means) { set_error("kmeans: null pointer"); return -1; }
+    if (n < k || k < 1) { set_error("kmeans: need n >= k >= 1 (n=%d, k=%d)", n, k); return -1; }
+    if (d % 4 != 0) { set_error("kmeans: feature dim %d must be a multiple of 4", d); return -1; }
+    if (trials < 1 || trials > KM_MAXT || !((trials & 3) == 0 || (trials & 3) == 2)) {
+        set_error("kmeans: %d local trials unsupported (the restated sgemv order covers trials %% 4 in {0, 2}; k in [55,148] gives 6)", trials); return -1;
+    }
+    if (first_center < 0 || first_center >= n) { set_error("kmeans: first centre out of range"); return -1; }
+    if ((size_t)n * 4 + (size_t)(k + 1) * 4 > 200 * 1024) { set_error("kmeans: n=%d too large for the single-block selection kernels", n); return -1; }
+    KmWs L; km_ws_layout(n, d, k, &L);
+    if (!workspace || workspace_bytes < L.total) { set_error("kmeans: workspace %zu < %zu", workspace_bytes, L.total); return -1; }
+    cudaStream_t st = (cudaStream_t)stream;
+    uint8_t* ws = (uint8_t*)workspace;
+    float* Xc = (float*)(ws + L.xc); double* xx64 = (double*)(ws + L.xx64);
+    float* mean = (float*)(ws + L.mean); float* var = (float*)(ws + L.var);
+    float* closest = (float*)(ws + L.closest); float* newc = (float*)(ws + L.newc);
+    int* cand = (int*)(ws + L.cand); int* chosen = (int*)(ws + L.chosen); float* pot = (float*)(ws + L.pot);
+    float* cA = (float*)(ws + L.cA); float* cB = (float*)(ws + L.cB); float* csq = (float*)(ws + L.csq);
+    int* labels_old = (int*)(ws + L.labels_old); int* offsets = (int*)(ws + L.offsets); int* members = (int*)(ws + L.members);
+    float* shift = (float*)(ws + L.shift); KmFlags* flags = (KmFlags*)(ws + L.flags);
+
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(km_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(km_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_done = true;
+    }
+    cudaMemsetAsync(flags, 0, sizeof(KmFlags), st);
+    // ---- preparation (fit L1490-1500)
+    km_colstats_kernel<<<(d + 63) / 64, 64, 0, st>>>(features, n, d, mean, var);
+    km_tol_kernel<<<1, 256, 0, st>>>(var, d, tol_scale, flags);
+    km_center_kernel<<<(n + 7) / 8, 256, 0, st>>>(features, mean, n, d, Xc, xx64);
+    // ---- k-means++ (L180-279)
+    cudaMemcpyAsync(cand, &first_center, sizeof(int), cudaMemcpyHostToDevice, st);
+    launch_dist<1>(Xc, xx64, cand, nullptr, n, d, newc, st);
+    km_select_kernel<<<1, 1024, (size_t)n * 4, st>>>(newc, 1, n, 0, k, trials, uniforms, closest, cand, chosen, pot);
+    for (int c = 1; c < k; ++c) {
+        switch (trials) {
+            case 2: launch_dist<2>(Xc, xx64, cand, closest, n, d, newc, st); break;
+            case 4: launch_dist<4>(Xc, xx64, cand, closest, n, d, newc, st); break;
+            case 6: launch_dist<6>(Xc, xx64, cand, closest, n, d, newc, st); break;
+            default: launch_dist<8>(Xc, xx64, cand, closest, n, d, newc, st); break;
+        }
+        km_select_kernel<<<1, 1024, (size_t)n * 4, st>>>(newc, trials, n, c, k, trials, uniforms, closest, cand, chosen, pot);
+    }
+    km_gather_centers_kernel<<<k, 256, 0, st>>>(Xc, chosen, k, d, cA);
+    if (chosen_out) cudaMemcpyAsync(chosen_out, chosen, (size_t)k * 4, cudaMemcpyDeviceToDevice, st);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) { set_error("kmeans seeding: %s", cudaGetErrorString(err)); return -1; }
+    // ---- Lloyd (L630-758). The convergence test needs the host: one 24-byte read + stream sync per iteration.
+    float* cur = cA; float* nxt = cB;
+    const int nparts = (d + 511) / 512;
+    const size_t bucket_smem = (size_t)n * 4 + (size_t)(k + 1) * 4;
+    bool strict = false;
+    int it = 0;
+    KmFlags h;
+    for (it = 0; it < max_iter; ++it) {
+        cudaMemsetAsync(&flags->n_changed, 0, sizeof(int), st);
+        km_center_norm_kernel<<<(k + 7) / 8, 256, 0, st>>>(cur, k, d, csq);
+        km_assign_kernel<<<(n + 31) / 32, 256, 0, st>>>(Xc, cur, csq, n, d, k, it == 0 ? nullptr : labels_old, labels, flags);
+        km_bucket_kernel<<<1, 1024, bucket_smem, st>>>(labels, n, k, offsets, members, flags);
+        km_segment_mean_kernel<<<dim3(nparts, k), 128, 0, st>>>(Xc, offsets, members, d, 0, nxt, cur, shift);
+        km_converge_kernel<<<1, 32, 0, st>>>(shift, k, nparts, flags);
+        cudaMemcpyAsync(labels_old, labels, (size_t)n * 4, cudaMemcpyDeviceToDevice, st);
+        cudaMemcpyAsync(&h, flags, sizeof(KmFlags), cudaMemcpyDeviceToHost, st);
+        err = cudaStreamSynchronize(st);
+        if (err != cudaSuccess) { set_error("kmeans lloyd: %s", cudaGetErrorString(err)); return -1; }
+        if (h.n_empty > 0) { set_error("kmeans: %d empty cluster(s) at iteration %d; sklearn's _relocate_empty_clusters_dense is not implemented", h.n_empty, it); return -2; }
+        float* t = cur; cur = nxt; nxt = t;                    // centers, centers_new = centers_new, centers
+        if (it > 0 && h.n_changed == 0) { strict = true; ++it; break; }
+        if (h.tol_ok) { ++it; break; }
+    }
+    if (!strict) {                                                 // rerun the E-step with the final centres (L741-753)
+        km_center_norm_kernel<<<(k + 7) / 8, 256, 0, st>>>(cur, k, d, csq);
+        km_assign_kernel<<<(n + 31) / 32, 256, 0, st>>>(Xc, cur, csq, n, d, k, nullptr, labels, flags);
+    }
+    if (n_iter_host) *n_iter_host = it > max_iter ? max_iter : it;
+    // ---- cluster features: per-label mean of the RAW features (kmean_features.py:99-105)
+    km_bucket_kernel<<<1, 1024, bucket_smem, st>>>(labels, n, k, offsets, members, flags);
+    km_segment_mean_kernel<<<dim3(nparts, k), 128, 0, st>>>(features, offsets, members, d, 1, cluster_means, nullptr, nullptr);
+    err = cudaGetLastError();
+    if (err != cudaSuccess) { set_error("kmeans: %s", cudaGetErrorString(err)); return -1; }
+    return 0;
+}
+
+}  // extern "C"

@@ -94,6 +94,40 @@ def gen_vis():
     print("vis golden:", {k: v.shape for k, v in out.items() if "grad::" not in k})
 
 
+KMEANS_CASES = [  # (tag, slide_id, n, d, modes)
+    ("s0", 0, 4096, 2048, 150), ("s1", 1, 4096, 2048, 150), ("s2", 2, 4096, 2048, 150),
+    ("uni", 3, 4000, 1024, 120), ("odd", 4, 1237, 512, 110), ("tail", 5, 4099, 256, 130), ("big", 6, 8192, 128, 150),
+]
+
+
+def gen_kmeans():
+    """sklearn.cluster.KMeans(n_clusters=100, random_state=0).fit(X).labels_ (the reference's call,
+    pre_processing/kmean_features.py:96) on synthetic slides, plus the script's per-label means (:99-105)."""
+    import sklearn
+    from sklearn.cluster import KMeans
+    from oracle import kmeans_oracle as K
+    out = {"sklearn_version": np.array(sklearn.__version__)}
+    for tag, sid, n, d, modes in KMEANS_CASES:
+        X = K.make_slide_features(sid, n=n, d=d, modes=modes)
+        km = KMeans(n_clusters=100, random_state=0).fit(X)
+        labels = km.labels_
+        feats = []
+        for pos in range(100):                                   # kmean_features.py:99-105, verbatim semantics
+            feats.append(np.mean(X[np.where(labels == pos)], axis=0))
+        feats = np.asarray(feats)
+        lo, idx, it = K.fit_labels(X)
+        assert np.array_equal(lo, labels), f"oracle restatement differs from sklearn on {tag}"
+        assert np.array_equal(K.fit_labels(X, pot_mode="emulated")[0], labels), f"emulated BLAS order differs on {tag}"
+        assert it == km.n_iter_
+        out[f"{tag}_labels"] = labels.astype(np.int16)
+        out[f"{tag}_seed_rows"] = idx.astype(np.int32)
+        out[f"{tag}_n_iter"] = np.array(km.n_iter_)
+        out[f"{tag}_means_checksum"] = np.array([feats.astype(np.float64).sum(), np.abs(feats.astype(np.float64)).sum()])
+        out[f"{tag}_means_head"] = feats[:, :8].copy()
+        print("kmeans golden", tag, n, d, "iters", km.n_iter_, "sizes", np.bincount(labels).min(), np.bincount(labels).max())
+    np.savez_compressed(os.path.join(HERE, "kmeans_golden.npz"), **out)
+
+
 if __name__ == "__main__":
     what = sys.argv[1:] or ["resnet", "vis", "kmeans"]
     for w in what:

@@ -66,3 +66,31 @@ def test_vis_oracle_train_steps_match_reference_golden():
         with torch.no_grad():
             after = V.forward(sd, x).numpy()
         assert _rel(after, g[f"{tag}_pred_after3"]) < 1e-4
+
+
+def test_kmeans_blas_order_restatement_matches_numpy():
+    """The fp32 summation orders the CUDA seeding reproduces (oracle/kmeans_oracle.py) against numpy's own BLAS calls."""
+    from oracle import kmeans_oracle as K
+    rng = np.random.RandomState(0)
+    for n in (100, 333, 1000, 4000, 4095, 4096, 4099, 8192, 9999):
+        w = np.ones(n, np.float32)
+        M = (np.abs(rng.randn(6, n)) * rng.rand(6, n) * 50).astype(np.float32)
+        ref = (M @ w.reshape(-1, 1))[:, 0]
+        got = np.array([K.blas_order_gemv_row(M[t], t, 6) for t in range(6)], np.float32)
+        assert np.array_equal(ref, got), n
+        assert (M[:1] @ w)[0] == K.blas_order_sdot(M[0]), n
+
+
+def test_kmeans_oracle_matches_sklearn_golden_and_live():
+    from oracle import kmeans_oracle as K
+    g = np.load(os.path.join(GOLD, "kmeans_golden.npz"))
+    for tag, sid, n, d, modes in (("odd", 4, 1237, 512, 110), ("tail", 5, 4099, 256, 130)):
+        X = K.make_slide_features(sid, n=n, d=d, modes=modes)
+        for mode in ("blas", "emulated"):
+            labels, idx, it = K.fit_labels(X, pot_mode=mode)
+            assert np.array_equal(labels, g[f"{tag}_labels"]) and np.array_equal(idx, g[f"{tag}_seed_rows"]), (tag, mode)
+            assert it == int(g[f"{tag}_n_iter"])
+        assert np.array_equal(K.cluster_means(X, labels)[:, :8], g[f"{tag}_means_head"])
+    from sklearn.cluster import KMeans                       # live check on one more slide (sklearn is the reference's dependency)
+    X = K.make_slide_features(21, n=700, d=128, modes=90)
+    assert np.array_equal(K.fit_labels(X)[0], KMeans(n_clusters=100, random_state=0).fit(X).labels_)
