@@ -11,6 +11,12 @@ Workload at N=1 = BASELINE.json configs[1]: ResNet-50 patch feature extraction, 
   cpu_baseline : the oracle restatement of the reference path (torch CPU, all host threads) on a bounded sample
 `--impl reference` times that CPU path alone, on the same config / metric.
 N>1: one process per GPU (torchrun), whole slides sharded across ranks, no data-path collective ("weak" scaling).
+
+BASELINE.json's metric has a second half — slides/sec of the linearized-attention (ViS) train step, configs[2]:
+batch 32 slides/GPU, 100x2048 -> 20530 genes, AdamW — and names the per-slide k-means(100) that joins the two.  Both are
+measured in the same run and reported under the extra keys "vis_train" and "kmeans" of the same JSON line (same
+sub-structure: value / ms_per_step / e2e / roofline / cpu_baseline); at N>1 the ViS step is data parallel with one NCCL
+all-reduce of the flat gradient per step, overlapped stage by stage with the backward pass.
 """
 import argparse
 import json
@@ -40,44 +46,60 @@ def peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clocks / throttle reasons through NVML (in-process; no fork) while the timed region runs."""
 
     def __init__(self, index):
         self.index, self.samples, self.stop, self.th = index, [], threading.Event(), None
+        self.h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(t.strip().isdigit() for t in vis.split(",")) else index
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.h = None
 
     def _run(self):
+        nv = self.nv
         while not self.stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(",")]
-                if len(f) >= 6:
-                    self.samples.append(f)
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((sm, int(r)))
             except Exception:
                 pass
-            self.stop.wait(0.2)
+            self.stop.wait(0.1)
 
     def __enter__(self):
-        self.th = threading.Thread(target=self._run, daemon=True)
-        self.th.start()
+        if self.h is not None:
+            self.th = threading.Thread(target=self._run, daemon=True)
+            self.th.start()
         return self
 
     def __exit__(self, *a):
         self.stop.set()
-        self.th.join(timeout=6)
+        if self.th is not None:
+            self.th.join(timeout=3)
 
     def summary(self):
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
-        sm = sorted(float(s[0]) for s in self.samples)
-        reasons = []
-        for i, name in enumerate(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]):
-            if any(s[2 + i].lower().startswith("active") for s in self.samples):
-                reasons.append(name)
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
-                "samples": len(sm)}
+        sm = sorted(s[0] for s in self.samples)
+        bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        reasons = [name for name, bit in bits.items() if any(s[1] & bit for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_sm, "reasons": reasons, "samples": len(sm), "source": "nvml"}
+
+
+VIS_B, VIS_N, VIS_D, VIS_G, VIS_DEPTH, VIS_H = 32, 100, 2048, 20530, 6, 16
+VIS_FLOP_PER_SLIDE = 45.86e9       # minimal formulation, forward + backward (SURVEY §8d config 3)
+VIS_WORKLOAD = "ViS train step: 32 slides/GPU x 100x2048 -> 20530 genes, depth 6, 16 heads, MSE + AdamW (BASELINE configs[2])"
+KM_N, KM_D, KM_K = 4096, 2048, 100
+KM_WORKLOAD = "KMeans(100, random_state=0) + per-label means on one 4096x2048 fp32 feature matrix"
 
 
 def cpu_reference_rate(n_patches, threads=None):
@@ -99,20 +121,47 @@ def cpu_reference_rate(n_patches, threads=None):
     return done / dt, threads, done
 
 
+def cpu_vis_rate(steps=2, batch=VIS_B):
+    """Reference train step on the CPU (oracle restatement of src/tformer_lin.py + src/vit.py:163-180), all host threads."""
+    import torch
+    from oracle import vis_oracle as V
+    torch.set_num_threads(os.cpu_count())
+    sd = V.make_state_dict(0, VIS_G)
+    x, y = V.make_inputs(0, batch, VIS_G)
+    V.train_steps(sd, [(x, y)])                                # warm-up
+    t0 = time.perf_counter()
+    V.train_steps(sd, [(x, y)] * steps)
+    dt = (time.perf_counter() - t0) / steps
+    return batch / dt, os.cpu_count(), f"{steps} steps of batch {batch} through oracle/vis_oracle.py (torch CPU fp32 autograd + AdamW)"
+
+
+def cpu_kmeans_rate(slides=2):
+    """The reference's own k-means call: sklearn.cluster.KMeans (its pinned third-party dependency) + the mean loop."""
+    from sklearn.cluster import KMeans
+    from oracle import kmeans_oracle as K
+    X = K.make_slide_features(0, n=KM_N, d=KM_D)
+    t0 = time.perf_counter()
+    for _ in range(slides):
+        km = KMeans(n_clusters=KM_K, random_state=0).fit(X)
+        K.cluster_means(X, km.labels_, KM_K)
+    dt = (time.perf_counter() - t0) / slides
+    return 1.0 / dt, os.cpu_count(), f"{slides} slides through sklearn.cluster.KMeans + numpy means"
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     sample = 64
     rates = []
-    for _ in range(args.warmup):
-        pass   # CPU path needs no GPU warm-up; cpu_reference_rate warms itself up
     t_total0 = time.perf_counter()
     for _ in range(args.steps):
         r, cores, done = cpu_reference_rate(sample)
         rates.append(r)
     ms = (time.perf_counter() - t_total0) / args.steps * 1e3
     v = sum(rates) / len(rates)
+    vr, vc, vs = cpu_vis_rate(1)
+    kr, kc, ks = cpu_kmeans_rate(1)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "patches/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -120,8 +169,118 @@ def run_reference(args):
             "cpu_baseline": {"value": v, "unit": "patches/s", "cores": cores, "kind": "port",
                              "sample": f"{sample} patches per step, {args.steps} steps, oracle/resnet50_oracle.py (torch CPU)"},
             "e2e": {"value": v, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "vis_train": {"value": vr, "unit": "slides/s", "cpu_baseline": {"value": vr, "unit": "slides/s", "cores": vc, "kind": "port", "sample": vs}},
+            "kmeans": {"value": kr, "unit": "slides/s", "cpu_baseline": {"value": kr, "unit": "slides/s", "cores": kc, "kind": "reference", "sample": ks}},
             "gpu_launches": 0}
     print(json.dumps(line))
+
+
+def gemm_timing(L, _lib, fn):
+    """Runs fn() once with CUDA events around every tcgen05 GEMM launch; returns (total ms, launches, issued MMA flops)."""
+    import ctypes as C
+    import torch
+    torch.cuda.synchronize()
+    L.sq_gemm_timing_enable(1)
+    fn()
+    torch.cuda.synchronize()
+    tms, n, fl = C.c_double(), C.c_longlong(), C.c_double()
+    _lib.check(L.sq_gemm_timing_read(C.byref(tms), C.byref(n), C.byref(fl)))
+    L.sq_gemm_timing_enable(0)
+    return tms.value, n.value, fl.value
+
+
+def bench_vis(args, dev, rank, world, timed, pk):
+    """slides/s of the fused ViS train step (forward + MSE + backward + [all-reduce] + AdamW), batch 32 per GPU."""
+    import torch
+    import torch.distributed as dist
+    from oracle import vis_oracle as V
+    from sequoia_pub_b200 import _lib
+    from sequoia_pub_b200.tformer_lin import ViS
+    from sequoia_pub_b200.train import FusedTrainer
+    L = _lib.lib()
+    torch.manual_seed(0)
+    model = ViS(num_outputs=VIS_G, input_dim=VIS_D, depth=VIS_DEPTH, nheads=VIS_H, dimensions_f=64, dimensions_s=64, dimensions_c=64,
+                num_clusters=VIS_N, device=str(dev)).to(dev).train()
+    x, y = V.make_inputs(100 + rank, VIS_B, VIS_G)                # a different shard of slides per rank
+    # several distinct batches so consecutive steps do not re-read the same inputs (weights alone are 525 MB > L2)
+    xs = [x.to(dev), x.flip(0).contiguous().to(dev)]
+    ys = [y.to(dev), y.flip(0).contiguous().to(dev)]
+    tr = FusedTrainer(model, lr=1e-3, weight_decay=0.0, process_group=None)
+    state = {"i": 0}
+
+    def step_dev():
+        i = state["i"] = state["i"] + 1
+        tr.step(xs[i & 1], ys[i & 1])
+
+    for _ in range(args.warmup):
+        step_dev()
+    steps = max(args.steps, 5)
+    ms = timed(step_dev, steps) / steps
+    value = world * VIS_B / (ms * 1e-3)
+    # end to end: pinned host batch -> device -> step -> loss back on the host
+    xh = [t.cpu().pin_memory() for t in xs]
+    yh = [t.cpu().pin_memory() for t in ys]
+    xd, yd = torch.empty_like(xs[0]), torch.empty_like(ys[0])
+    loss_h = torch.empty(1, dtype=torch.float32).pin_memory()
+
+    def step_e2e():
+        i = state["i"] = state["i"] + 1
+        xd.copy_(xh[i & 1], non_blocking=True)
+        yd.copy_(yh[i & 1], non_blocking=True)
+        loss_h.copy_(tr.step(xd, yd), non_blocking=True)
+        torch.cuda.current_stream().synchronize()                # the training loop reads the loss every step (src/vit.py:170)
+
+    for _ in range(2):
+        step_e2e()
+    e2e_ms = timed(step_e2e, steps) / steps
+    out = {"value": value, "unit": "slides/s", "ms_per_step": ms, "steps": steps, "dtype": "bf16x3 (split-precision bf16 tensor cores, fp32 accumulate)",
+           "config": {"workload": VIS_WORKLOAD, "global_batch": VIS_B * world, "parallelism": f"dp{world}, flat-gradient NCCL all-reduce per backward stage" if world > 1 else "single GPU",
+                      "l2": "parameters + Adam state (2.1 GB) and activations (1.4 GB) exceed L2 every step"},
+           "e2e": {"value": world * VIS_B / (e2e_ms * 1e-3), "unit": "slides/s", "ms_per_step": e2e_ms,
+                   "h2d_bytes_per_step": xd.numel() * 4 + yd.numel() * 4, "d2h_bytes_per_step": 4},
+           "final_loss": float(loss_h.item())}
+    if rank == 0:
+        tms, n, fl = gemm_timing(L, _lib, step_dev)
+        alg = VIS_FLOP_PER_SLIDE * VIS_B
+        ach = alg / (tms * 1e-3) / 1e12
+        out["roofline"] = {"bound": "tensor", "kernel": "gemm_tc_kernel (split-precision GEMMs of the step, fused epilogues)",
+                           "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_sustained"],
+                           "peak_source": pk["source"] + " bf16 sustained; the path issues 3 bf16 MMAs per algorithmic MAC to keep fp32 parity, "
+                           "so 1/3 is the ceiling of this fraction", "traffic": None, "launches": n,
+                           "avg_launch_us": tms * 1e3 / max(n, 1), "kernel_share_of_step": tms / ms,
+                           "issued_mma_tflops": fl / (tms * 1e-3) / 1e12, "issued_frac_of_peak": fl / (tms * 1e-3) / 1e12 / pk["bf16_sustained"]}
+    del tr, model
+    torch.cuda.empty_cache()
+    return out
+
+
+def bench_kmeans(args, dev, rank, world, pk):
+    """slides/s of the per-slide k-means reduction (independent slides per rank, no collective)."""
+    import torch
+    from oracle import kmeans_oracle as K
+    from sequoia_pub_b200.kmeans import KMeans
+    Xh = torch.from_numpy(K.make_slide_features(rank, n=KM_N, d=KM_D)).pin_memory()
+    Xd = Xh.to(dev)
+    km = KMeans(n_clusters=KM_K, random_state=0, device=dev)
+    km.fit(Xd)
+    torch.cuda.synchronize()
+    reps = 3
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        km.fit(Xd)                         # device-resident features in; labels + cluster features read back on the host
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) / reps * 1e3
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        km.fit(Xh)                         # host features in (H2D inside)
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) / reps * 1e3
+    return {"value": world * 1e3 / ms, "unit": "slides/s", "ms_per_slide": ms, "lloyd_iterations": km.n_iter_,
+            "config": {"workload": KM_WORKLOAD, "timing": "host wall clock around fit() (the call synchronises once per Lloyd iteration)"},
+            "e2e": {"value": world * 1e3 / e2e_ms, "unit": "slides/s", "ms_per_slide": e2e_ms, "h2d_bytes_per_step": KM_N * KM_D * 4,
+                    "d2h_bytes_per_step": KM_N * 4 + KM_K * KM_D * 4},
+            "roofline": {"bound": "latency", "note": "99 dependent k-means++ steps (sequential fp32 cumsum) + ~5 Lloyd iterations of 1.68 GFLOP fp32; "
+                         "label parity with scikit-learn is the gate (SURVEY §8d)", "achieved": None, "peak": None, "frac": None, "traffic": None}}
 
 
 def main():
@@ -132,11 +291,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=256, help="patches timed on the CPU baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--only", default="", help="comma list of {resnet,vis,kmeans}: skip the others (debugging)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":
         return run_reference(args)
+    only = set(filter(None, args.only.split(",")))
 
     import torch
     import torch.distributed as dist
@@ -154,20 +315,7 @@ def main():
     from sequoia_pub_b200.resnet import resnet50
     _lib.require_device()
     L = _lib.lib()
-
-    model = resnet50().eval()
-    model.load_state_dict(O.make_state_dict(0))
-    model = model.to(dev)
-    g = torch.Generator(device=dev).manual_seed(1000 + rank)      # slide id = seed (BASELINE config 2)
-    slide_dev = torch.randint(0, 256, (PATCHES_PER_SLIDE, 256, 256, 3), generator=g, dtype=torch.uint8, device=dev)
-    slide_host = torch.empty(slide_dev.shape, dtype=torch.uint8).pin_memory()
-    slide_host.copy_(slide_dev)
-    feats = torch.empty(PATCHES_PER_SLIDE, 2048, dtype=torch.float32, device=dev)
-    launches_per_step = (PATCHES_PER_SLIDE // BATCH) * (L.sq_resnet50_num_convs() + 3)
-
-    def step_device():
-        for b in range(0, PATCHES_PER_SLIDE, BATCH):
-            model.extract_uint8(slide_dev[b:b + BATCH], out=feats[b:b + BATCH])
+    pk = peaks()
 
     def barrier():
         if world > 1:
@@ -186,6 +334,20 @@ def main():
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
+
+    model = resnet50().eval()
+    model.load_state_dict(O.make_state_dict(0))
+    model = model.to(dev)
+    g = torch.Generator(device=dev).manual_seed(1000 + rank)      # slide id = seed (BASELINE config 2)
+    slide_dev = torch.randint(0, 256, (PATCHES_PER_SLIDE, 256, 256, 3), generator=g, dtype=torch.uint8, device=dev)
+    slide_host = torch.empty(slide_dev.shape, dtype=torch.uint8).pin_memory()
+    slide_host.copy_(slide_dev)
+    feats = torch.empty(PATCHES_PER_SLIDE, 2048, dtype=torch.float32, device=dev)
+    launches_per_step = (PATCHES_PER_SLIDE // BATCH) * (L.sq_resnet50_num_convs() + 3)
+
+    def step_device():
+        for b in range(0, PATCHES_PER_SLIDE, BATCH):
+            model.extract_uint8(slide_dev[b:b + BATCH], out=feats[b:b + BATCH])
 
     # ---- kernel-resident throughput (value)
     for _ in range(args.warmup):
@@ -207,23 +369,21 @@ def main():
     # ---- roofline of the dominant kernel (tcgen05 implicit-GEMM conv), CUDA events around every launch
     roof = None
     if rank == 0:
-        import ctypes as C
-        pk = peaks()
-        torch.cuda.synchronize()
-        L.sq_gemm_timing_enable(1)
-        step_device()
-        torch.cuda.synchronize()
-        tms, n, fl = C.c_double(), C.c_longlong(), C.c_double()
-        _lib.check(L.sq_gemm_timing_read(C.byref(tms), C.byref(n), C.byref(fl)))
-        L.sq_gemm_timing_enable(0)
+        tms, n, fl = gemm_timing(L, _lib, step_device)
         alg_flops = FLOP_PER_PATCH * PATCHES_PER_SLIDE          # algorithmic work of one step
-        achieved = alg_flops / (tms.value * 1e-3) / 1e12
+        achieved = alg_flops / (tms * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (implicit-GEMM conv, bf16 -> fp32 TMEM)",
                 "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
                 "peak_source": pk["source"] + " bf16 sustained", "traffic": None,
-                "launches": n.value, "avg_launch_us": tms.value * 1e3 / max(n.value, 1),
-                "kernel_share_of_step": tms.value / ms_per_step,
-                "issued_mma_tflops": fl.value / (tms.value * 1e-3) / 1e12}
+                "launches": n, "avg_launch_us": tms * 1e3 / max(n, 1),
+                "kernel_share_of_step": tms / ms_per_step,
+                "issued_mma_tflops": fl / (tms * 1e-3) / 1e12}
+    ex_h2d, ex_d2h = ex.h2d_bytes, ex.d2h_bytes
+    del slide_dev, slide_host, ex, feats
+    torch.cuda.empty_cache()
+
+    vis = bench_vis(args, dev, rank, world, timed, pk) if (not only or "vis" in only) else None
+    kmn = bench_kmeans(args, dev, rank, world, pk) if (not only or "kmeans" in only) else None
 
     if rank != 0:
         if world > 1:
@@ -235,6 +395,12 @@ def main():
         r, cores, done = cpu_reference_rate(args.cpu_sample)
         cpu = {"value": r, "unit": "patches/s", "cores": cores, "kind": "port",
                "sample": f"{done} patches (batch 64) through oracle/resnet50_oracle.py, torch CPU fp32"}
+        if vis is not None:
+            vr, vc, vs = cpu_vis_rate(2)
+            vis["cpu_baseline"] = {"value": vr, "unit": "slides/s", "cores": vc, "kind": "port", "sample": vs}
+        if kmn is not None:
+            kr, kc, ks = cpu_kmeans_rate(2)
+            kmn["cpu_baseline"] = {"value": kr, "unit": "slides/s", "cores": kc, "kind": "reference", "sample": ks}
 
     line = {"metric": METRIC, "value": value, "unit": "patches/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -242,10 +408,10 @@ def main():
             "config": {"workload": WORKLOAD, "l2": "inputs (805 MB/slide) larger than L2; no flush needed",
                        "parallelism": f"slide-sharded x{world}, no collective"},
             "clocks": clk.summary(),
-            "e2e": {"value": e2e_value, "unit": "patches/s", "h2d_bytes_per_step": ex.h2d_bytes // e2e_steps,
-                    "d2h_bytes_per_step": ex.d2h_bytes // e2e_steps, "ms_per_step": e2e_ms},
+            "e2e": {"value": e2e_value, "unit": "patches/s", "h2d_bytes_per_step": ex_h2d // e2e_steps,
+                    "d2h_bytes_per_step": ex_d2h // e2e_steps, "ms_per_step": e2e_ms},
             "gpu_launches": launches_per_step * args.steps,
-            "roofline": roof, "cpu_baseline": cpu}
+            "roofline": roof, "cpu_baseline": cpu, "vis_train": vis, "kmeans": kmn}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

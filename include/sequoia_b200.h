@@ -42,6 +42,11 @@ SQ_API int sq_device_ok(void);
 SQ_API int sq_gemm_timing_enable(int on);
 SQ_API int sq_gemm_timing_read(double* total_ms, long long* launches, double* mma_flops);
 
+/* Development aid: when `device_buffer` (>= 148*16 uint64) is non-NULL every following GEMM launch stores per-CTA cycle
+ * counters of its warp roles: [cta][0..1] producer {waiting for a free stage, total}; [2..4] MMA issuer {waiting for
+ * data, waiting for a drained accumulator, total}; [5+2q, 6+2q] epilogue warp q {waiting for an accumulator, total}. */
+SQ_API int sq_gemm_profile(void* device_buffer);
+
 /* ------------------------------------------------------------------ building blocks (exposed for tests) */
 
 /* fp32 [rows, cols] (row stride ld_in) -> bf16 hi / lo planes (row stride ld_out); lo may be NULL. */

@@ -49,6 +49,7 @@ SIGNATURES = {
     "sq_device_ok": (c_int, []),
     "sq_gemm_timing_enable": (c_int, [c_int]),
     "sq_gemm_timing_read": (c_int, [C.POINTER(C.c_double), C.POINTER(c_ll), C.POINTER(C.c_double)]),
+    "sq_gemm_profile": (c_int, [c_void_p]),
     "sq_split_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_ll, c_int, c_ll, c_ll, c_void_p]),
     "sq_gemm_bf16": (c_int, [C.POINTER(GemmDesc), c_void_p]),
     "sq_resnet50_num_convs": (c_int, []),
@@ -110,5 +111,13 @@ def stream_ptr():
     return c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+_device_checked = set()
+
+
 def require_device():
-    check(lib().sq_device_ok())
+    """Fails loudly unless the current CUDA device is an sm_100 part (checked once per device: the query is slow)."""
+    import torch
+    dev = torch.cuda.current_device()
+    if dev not in _device_checked:
+        check(lib().sq_device_ok())
+        _device_checked.add(dev)

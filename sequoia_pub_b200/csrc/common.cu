@@ -38,6 +38,18 @@ PFN_encodeTiled get_encode_fn() {
     return fn;
 }
 
+// One instantiation of the GEMM kernel per (tile width, epilogue class).
+int launch_gemm_dispatch(int bn, int cls, const CUtensorMap* maps, const GemmKParams& kp, int grid, cudaStream_t st) {
+#define SQ_CASE(BN, CLS) if (bn == BN && cls == CLS) return launch_gemm_inst<BN, CLS>(maps, kp, grid, st);
+#define SQ_ALL_BN(CLS) SQ_CASE(64, CLS) SQ_CASE(128, CLS) SQ_CASE(256, CLS)
+    SQ_ALL_BN(EPI_CONV) SQ_ALL_BN(EPI_F32) SQ_ALL_BN(EPI_GELU) SQ_ALL_BN(EPI_DGELU) SQ_CASE(128, EPI_LN64) SQ_CASE(64, EPI_LN64)
+    SQ_CASE(256, EPI_LN64) SQ_ALL_BN(EPI_GENERIC)
+#undef SQ_ALL_BN
+#undef SQ_CASE
+    set_error("gemm: no kernel for block_n %d class %d", bn, cls);
+    return -1;
+}
+
 // ---- per-launch timing of the tensor-core kernel (used by bench.py to report the roofline of the dominant kernel)
 static bool g_timing = false;
 static std::vector<cudaEvent_t> g_ev;       // pairs: begin, end
@@ -57,6 +69,9 @@ void gemm_timing_end(cudaStream_t st) {
     cudaEventRecord(g_ev[g_ev_used + 1], st);
     g_ev_used += 2;
 }
+
+static unsigned long long* g_prof = nullptr;
+unsigned long long* gemm_prof_buffer() { return g_prof; }
 
 // fp32 [rows, cols] (ld_in) -> bf16 hi / lo planes (ld_out); lo may be null
 __global__ void split_planes_kernel(const float* __restrict__ x, bf16* __restrict__ hi, bf16* __restrict__ lo, long long rows,
@@ -93,9 +108,10 @@ int sq_version(void) { return 100; }
 const char* sq_last_error(void) { return g_err; }
 
 int sq_device_ok(void) {
-    int dev = 0; cudaDeviceProp prop;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) { set_error("no CUDA device"); return -1; }
-    if (prop.major != 10) { set_error("sequoia_b200 needs an sm_100 device, found sm_%d%d", prop.major, prop.minor); return -2; }
+    int dev = 0, major = 0, minor = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev) != cudaSuccess) { set_error("no CUDA device"); return -1; }
+    if (major != 10) { set_error("sequoia_b200 needs an sm_100 device, found sm_%d%d", major, minor); return -2; }
     return 0;
 }
 
@@ -118,6 +134,8 @@ int sq_gemm_timing_read(double* total_ms, long long* launches, double* mma_flops
     g_ev_used = 0; g_flops = 0.0;
     return 0;
 }
+
+int sq_gemm_profile(void* device_buffer) { g_prof = (unsigned long long*)device_buffer; return 0; }
 
 int sq_split_bf16(const float* x, void* hi, void* lo, long long rows, int cols, long long ld_in, long long ld_out, void* stream) {
     return split_planes(x, (bf16*)hi, (bf16*)lo, rows, cols, ld_in, ld_out, (cudaStream_t)stream);

@@ -54,6 +54,7 @@ struct GemmKParams {
     // conv mode
     int conv, cblocks, S, stride, pad, tiles_per_img, BH, BIMG;
     float* partial;         // split-K workspace [split][M][N]
+    unsigned long long* prof;   // optional per-CTA cycle counters (sq_gemm_profile): [cta][16]
     EpiParams e;
 };
 
@@ -64,9 +65,50 @@ __device__ __forceinline__ float dgelu_f(float x) {
     return cdf + x * pdf;
 }
 
+// Epilogue classes: the kernel is instantiated per class so that each instantiation only carries the code of the
+// options its class can use (one generic instantiation was ~15k SASS instructions and instruction-fetch bound on
+// small-K launches).  Within a class the options are still runtime switches.
+enum EpiClass {
+    EPI_GENERIC = 0,   // everything (tests, rare combinations)
+    EPI_CONV = 1,      // bias, optional bf16 residual, optional ReLU -> bf16 plane and/or fp32          (ResNet convolutions)
+    EPI_F32 = 2,       // alpha, bias, row bias, fp32 residual -> fp32 and/or planes, no activation     (projections, dgrad, wgrad)
+    EPI_GELU = 3,      // bias, row bias, save_pre, exact GELU -> planes / fp32                         (W1, combine)
+    EPI_DGELU = 4,     // multiply by GELU'(aux) -> planes / fp32                                       (dgrad through a GELU)
+    EPI_LN64 = 5,      // bias, save_pre, per-head LayerNorm(64) + GELU -> planes / fp32                (local branch)
+    EPI_NUM_CLASSES = 6
+};
+__host__ __device__ constexpr bool epi_has(int cls, int opt) {
+    // opt: 0 alpha, 1 bias, 2 rowbias, 3 res_f32, 4 res_bf, 5 save_pre, 6 relu, 7 gelu, 8 dgelu, 9 ln64, 10 out_f32, 11 out_bf, 12 out_lo
+    return cls == EPI_GENERIC ? true
+         : cls == EPI_CONV ? (opt == 1 || opt == 4 || opt == 6 || opt == 10 || opt == 11)
+         : cls == EPI_F32 ? (opt == 0 || opt == 1 || opt == 2 || opt == 3 || opt == 10 || opt == 11 || opt == 12)
+         : cls == EPI_GELU ? (opt == 1 || opt == 2 || opt == 5 || opt == 7 || opt == 10 || opt == 11 || opt == 12)
+         : cls == EPI_DGELU ? (opt == 0 || opt == 8 || opt == 10 || opt == 11 || opt == 12)
+         : cls == EPI_LN64 ? (opt == 1 || opt == 5 || opt == 9 || opt == 10 || opt == 11 || opt == 12)
+         : false;
+}
+
 // Applies the fused epilogue to NC consecutive columns of one row and stores them.
-template <int NC>
-__device__ __forceinline__ void epilogue_apply(float* v, long long row, int col0, int N, const EpiParams& e) {
+template <int NC, int CLS = EPI_GENERIC>
+__device__ __forceinline__ void epilogue_apply(float* v, long long row, int col0, int N, const EpiParams& e0) {
+    // options outside the class are compiled out by nulling them in a local copy the optimiser can see through
+    EpiParams e = e0;
+    if constexpr (!epi_has(CLS, 0)) e.alpha = 1.0f;
+    if constexpr (!epi_has(CLS, 1)) e.bias = nullptr;
+    if constexpr (!epi_has(CLS, 2)) e.rowbias = nullptr;
+    if constexpr (!epi_has(CLS, 3)) e.res_f32 = nullptr;
+    if constexpr (!epi_has(CLS, 4)) e.res_bf = nullptr;
+    if constexpr (!epi_has(CLS, 5)) e.save_pre = nullptr;
+    if constexpr (!epi_has(CLS, 10)) e.out_f32 = nullptr;
+    if constexpr (!epi_has(CLS, 11)) e.out_hi = nullptr;
+    if constexpr (!epi_has(CLS, 12)) e.out_lo = nullptr;
+    if constexpr (CLS != EPI_GENERIC) {
+        if constexpr (CLS == EPI_CONV) e.act = (e.act == ACT_RELU) ? ACT_RELU : ACT_NONE;
+        else if constexpr (CLS == EPI_F32) e.act = ACT_NONE;
+        else if constexpr (CLS == EPI_GELU) e.act = ACT_GELU;
+        else if constexpr (CLS == EPI_DGELU) e.act = ACT_MUL_DGELU;
+        else if constexpr (CLS == EPI_LN64) e.act = ACT_LN64_GELU;
+    }
     const int nvalid = min(NC, N - col0);
     if (e.alpha != 1.0f) {
 #pragma unroll
@@ -202,6 +244,58 @@ __device__ __forceinline__ void epilogue_apply(float* v, long long row, int col0
     }
 }
 
+// ResNet convolution epilogue for 32 full columns: + shift (folded BatchNorm), + bf16 residual, ReLU -> bf16 and/or fp32.
+// All accesses are 16-byte vectors (row strides are multiples of 8 elements, col0 a multiple of 32).
+__device__ __forceinline__ void epilogue_conv32(float* v, long long row, int col0, const EpiParams& e) {
+    if (e.bias) {
+        const float4* b4 = reinterpret_cast<const float4*>(e.bias + col0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float4 b = __ldg(b4 + i);
+            v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+        }
+    }
+    if (e.res_bf) {
+        const uint4* r4 = reinterpret_cast<const uint4*>(e.res_bf + row * e.ld_res + col0);
+        uint4 r[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) r[i] = r4[i];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t w[4] = {r[i].x, r[i].y, r[i].z, r[i].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                v[8 * i + 2 * j] += __uint_as_float(w[j] << 16);
+                v[8 * i + 2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u);
+            }
+        }
+    }
+    if (e.act == ACT_RELU) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
+    }
+    if (e.out_hi) {
+        uint4* o4 = reinterpret_cast<uint4*>(e.out_hi + row * e.ld_bf + col0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            uint4 pk;
+            __nv_bfloat162 t;
+            t = __floats2bfloat162_rn(v[8 * i], v[8 * i + 1]); pk.x = *reinterpret_cast<uint32_t*>(&t);
+            t = __floats2bfloat162_rn(v[8 * i + 2], v[8 * i + 3]); pk.y = *reinterpret_cast<uint32_t*>(&t);
+            t = __floats2bfloat162_rn(v[8 * i + 4], v[8 * i + 5]); pk.z = *reinterpret_cast<uint32_t*>(&t);
+            t = __floats2bfloat162_rn(v[8 * i + 6], v[8 * i + 7]); pk.w = *reinterpret_cast<uint32_t*>(&t);
+            o4[i] = pk;
+        }
+    }
+    if (e.out_f32) {
+        float4* o4 = reinterpret_cast<float4*>(e.out_f32 + row * e.ld_f32 + col0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    }
+}
+
+constexpr int GEMM_THREADS = 384;      // warps 0-3: TMA producer, MMA issuer, TMEM allocator, idle; warps 4-11: epilogue
+constexpr int GEMM_EPI_WARPS = 8;      // two warps per TMEM lane quadrant, each draining half of the tile's columns
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_A_BYTES = GEMM_BM * GEMM_BK * 2;  // 16 KB
@@ -214,8 +308,8 @@ template <int BN> struct GemmCfg {
     static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
 };
 
-template <int BN>
-__global__ void __launch_bounds__(256, 1)
+template <int BN, int CLS>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB1,
                const GemmKParams p) {
@@ -241,7 +335,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], GEMM_EPI_WARPS); }
         mbar_fence_init();
     }
     if (warp == 2) tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
@@ -258,6 +352,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         if (elect_one()) {
             // ===================== TMA producer =====================
             int stage = 0; uint32_t phase = 0;
+            long long pw = 0; const long long pt0 = clock64();
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
                 const int split = t / tiles_mn;
                 const int mn = t - split * tiles_mn;
@@ -272,7 +367,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     else { img = mt * p.BIMG; hin0 = -p.pad; }
                 }
                 for (int kb = kb0; kb < kb1; ++kb) {
+                    const long long w0 = clock64();
                     mbar_wait(&empty[stage], phase ^ 1);
+                    pw += clock64() - w0;
                     mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
                     const int kk = kb / p.nterms, term = kb - kk * p.nterms;
                     const CUtensorMap* ma = (term == 2) ? &mapA1 : &mapA0;
@@ -299,6 +396,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
+            if (p.prof) { p.prof[blockIdx.x * 16 + 0] = pw; p.prof[blockIdx.x * 16 + 1] = clock64() - pt0; }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
@@ -306,16 +404,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         const uint32_t a_kstep = p.a_mn ? 2048u : 32u, b_kstep = p.b_mn ? 2048u : 32u;
         const uint32_t a_lbo = p.a_mn ? 8192u : 0u, b_lbo = p.b_mn ? 8192u : 0u;
         int stage = 0; uint32_t phase = 0; int iter = 0;
+        long long mw_full = 0, mw_tmem = 0; const long long mt0 = clock64();
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++iter) {
             const int split = t / tiles_mn;
             const int kb0 = split * p.kb_per_split;
             const int kb1 = min(kb0 + p.kb_per_split, total_kb);
             const int as = iter & 1; const uint32_t aphase = (iter >> 1) & 1;
+            const long long w1 = clock64();
             mbar_wait(&tmem_empty[as], aphase ^ 1);
+            mw_tmem += clock64() - w1;
             tc_fence_after();
             const uint32_t tacc = tmem_base + as * BN;
             for (int kb = kb0; kb < kb1; ++kb) {
+                const long long w2 = clock64();
                 mbar_wait(&full[stage], phase);
+                mw_full += clock64() - w2;
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t a_base = smem_u32(smemA + stage * GEMM_A_BYTES);
@@ -333,16 +436,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
+        if (p.prof && lane == 0) { p.prof[blockIdx.x * 16 + 2] = mw_full; p.prof[blockIdx.x * 16 + 3] = mw_tmem; p.prof[blockIdx.x * 16 + 4] = clock64() - mt0; }
     } else if (warp >= 4) {
         // ===================== epilogue =====================
-        const int q = warp - 4;
+        const int q = warp & 3;                       // TMEM lane quadrant this warp may read
+        const int cbeg = ((warp - 4) >> 2) * (BN / 2), cend = cbeg + BN / 2;   // its half of the tile's columns
         int iter = 0;
+        long long ew = 0; const long long et0 = clock64();
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++iter) {
             const int split = t / tiles_mn;
             const int mn = t - split * tiles_mn;
             const int mt = mn / p.num_n, nt = mn - mt * p.num_n;
             const int as = iter & 1; const uint32_t aphase = (iter >> 1) & 1;
+            const long long w3 = clock64();
             mbar_wait(&tmem_full[as], aphase);
+            ew += clock64() - w3;
             tc_fence_after();
             const long long row = (long long)mt * GEMM_BM + q * 32 + lane;
             const int n0 = p.diag64 ? (2 * mt + nt) * 64 : nt * BN;
@@ -353,7 +461,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             const int c0 = p.diag64 ? 0 : n0;
             if (p.split_k > 1) {
                 float* dst = p.partial + ((long long)split * p.M + row) * ncols + c0;
-                for (int c = 0; c < BN && n0 + c < p.N; c += 32) {
+                for (int c = cbeg; c < cend && n0 + c < p.N; c += 32) {
                     float v[32];
                     tmem_ld32(tacc + c, v);
                     tmem_ld_wait();
@@ -367,26 +475,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         }
                     }
                 }
-            } else if (p.e.act == ACT_LN64_GELU) {
-                for (int c = 0; c < BN && n0 + c < p.N; c += 64) {
-                    float v[64];
-                    tmem_ld32(tacc + c, v);
-                    tmem_ld32(tacc + c + 32, v + 32);
-                    tmem_ld_wait();
-                    if (row_ok) epilogue_apply<64>(v, row, n0 + c, p.N, p.e);
+            } else if ((CLS == EPI_GENERIC || CLS == EPI_LN64) && p.e.act == ACT_LN64_GELU) {
+                if constexpr (CLS == EPI_GENERIC || CLS == EPI_LN64) {
+                    for (int c = cbeg; c < cend && n0 + c < p.N; c += 64) {
+                        float v[64];
+                        tmem_ld32(tacc + c, v);
+                        tmem_ld32(tacc + c + 32, v + 32);
+                        tmem_ld_wait();
+                        if (row_ok) epilogue_apply<64, CLS>(v, row, n0 + c, p.N, p.e);
+                    }
                 }
-            } else {
-                for (int c = 0; c < BN && n0 + c < p.N; c += 32) {
+            } else if constexpr (CLS != EPI_LN64) {
+                for (int c = cbeg; c < cend && n0 + c < p.N; c += 32) {
                     float v[32];
                     tmem_ld32(tacc + c, v);
                     tmem_ld_wait();
-                    if (row_ok) epilogue_apply<32>(v, row, c0 + c, ncols, p.e);
+                    if (row_ok) {
+                        if constexpr (CLS == EPI_CONV) {
+                            if (c0 + c + 32 <= ncols && ((p.e.ld_bf | p.e.ld_f32 | p.e.ld_res) & 7) == 0 && ((reinterpret_cast<uintptr_t>(p.e.bias) | reinterpret_cast<uintptr_t>(p.e.out_f32) | reinterpret_cast<uintptr_t>(p.e.out_hi) | reinterpret_cast<uintptr_t>(p.e.res_bf)) & 15) == 0) epilogue_conv32(v, row, c0 + c, p.e);
+                            else epilogue_apply<32, CLS>(v, row, c0 + c, ncols, p.e);
+                        } else {
+                            epilogue_apply<32, CLS>(v, row, c0 + c, ncols, p.e);
+                        }
+                    }
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[as]);
         }
+        if (p.prof && lane == 0) { p.prof[blockIdx.x * 16 + 5 + (warp - 4)] = ew; if (warp == 4) p.prof[blockIdx.x * 16 + 13] = clock64() - et0; }
     }
     tc_fence_before();
     __syncthreads();
@@ -476,6 +594,7 @@ int split_planes(const float* x, bf16* hi, bf16* lo, long long rows, int cols, l
 // optional per-launch CUDA-event timing of the GEMM kernel (bench.py's roofline leg); no-ops unless enabled
 void gemm_timing_begin(cudaStream_t st, double flops);
 void gemm_timing_end(cudaStream_t st);
+unsigned long long* gemm_prof_buffer();   // device buffer for per-CTA role cycle counters, or null
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -509,18 +628,40 @@ inline int make_operand_map(CUtensorMap* m, const bf16* base, int mn_major, long
     return encode_map(m, base, 2, dims, strides, box, estr);
 }
 
-template <int BN>
-int launch_gemm_bn(const CUtensorMap* maps, const GemmKParams& kp, int grid, cudaStream_t st) {
+template <int BN, int CLS>
+int launch_gemm_inst(const CUtensorMap* maps, const GemmKParams& kp, int grid, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        cudaError_t err = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::SMEM_BYTES);
+        cudaError_t err = cudaFuncSetAttribute(gemm_tc_kernel<BN, CLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::SMEM_BYTES);
         if (err != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(err)); return -1; }
         configured = true;
     }
-    gemm_tc_kernel<BN><<<grid, 256, GemmCfg<BN>::SMEM_BYTES, st>>>(maps[0], maps[1], maps[2], maps[3], kp);
+    gemm_tc_kernel<BN, CLS><<<grid, GEMM_THREADS, GemmCfg<BN>::SMEM_BYTES, st>>>(maps[0], maps[1], maps[2], maps[3], kp);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) { set_error("gemm launch: %s", cudaGetErrorString(err)); return -1; }
     return 0;
+}
+
+// Defined once in common.cu (explicit dispatch over the instantiated <BN, class> pairs).
+int launch_gemm_dispatch(int bn, int cls, const CUtensorMap* maps, const GemmKParams& kp, int grid, cudaStream_t st);
+
+// The narrowest epilogue class that covers the options a launch uses.
+inline int epi_class_of(const EpiParams& e, bool split) {
+    if (split) return EPI_F32;          // the kernel only writes partials; the reduce kernel applies the epilogue
+    bool used[13] = {e.alpha != 1.0f, e.bias != nullptr, e.rowbias != nullptr, e.res_f32 != nullptr, e.res_bf != nullptr, e.save_pre != nullptr,
+                     e.act == ACT_RELU, e.act == ACT_GELU, e.act == ACT_MUL_DGELU, e.act == ACT_LN64_GELU, e.out_f32 != nullptr,
+                     e.out_hi != nullptr, e.out_lo != nullptr};
+    const int order[5] = {EPI_CONV, EPI_F32, EPI_GELU, EPI_DGELU, EPI_LN64};
+    for (int k = 0; k < 5; ++k) {
+        const int cls = order[k];
+        bool ok = true;
+        for (int o = 0; o < 13; ++o) if (used[o] && !epi_has(cls, o)) ok = false;
+        if (cls == EPI_GELU && e.act != ACT_GELU) ok = false;
+        if (cls == EPI_DGELU && e.act != ACT_MUL_DGELU) ok = false;
+        if (cls == EPI_LN64 && e.act != ACT_LN64_GELU) ok = false;
+        if (ok) return cls;
+    }
+    return EPI_GENERIC;
 }
 
 inline int gemm_launch(const GemmArgs& g, cudaStream_t st) {
@@ -536,7 +677,7 @@ inline int gemm_launch(const GemmArgs& g, cudaStream_t st) {
             // prefer the widest tile that still gives every SM work
             const int mt = (g.M + GEMM_BM - 1) / GEMM_BM;
             const long long t256 = (long long)mt * ((g.N + 255) / 256);
-            bn = (g.N >= 256 && t256 >= 2LL * num_sms()) ? 256 : 128;
+            bn = (g.N >= 256 && t256 >= (long long)num_sms() * 2 / 3) ? 256 : 128;
         }
     }
     if (bn != 64 && bn != 128 && bn != 256) { set_error("gemm: bad block_n %d", bn); return -1; }
@@ -553,6 +694,7 @@ inline int gemm_launch(const GemmArgs& g, cudaStream_t st) {
         kp.num_n = 2;
     }
     kp.e = g.e;
+    kp.prof = gemm_prof_buffer();
     if (kp.e.alpha == 0.0f) kp.e.alpha = 1.0f;
     if (g.nterms != 1 && g.nterms != 3) { set_error("gemm: nterms must be 1 or 3"); return -1; }
     if (g.nterms == 3 && (!g.A.lo || !g.B.lo)) { set_error("gemm: split precision needs lo planes"); return -1; }
@@ -604,9 +746,7 @@ inline int gemm_launch(const GemmArgs& g, cudaStream_t st) {
     const int grid = (int)(total_tiles < num_sms() ? total_tiles : num_sms());
     int rc;
     gemm_timing_begin(st, 2.0 * g.M * g.N * (g.conv.enabled ? (double)kp.nk * 64 : (double)g.K) * g.nterms);
-    if (bn == 64) rc = launch_gemm_bn<64>(maps, kp, grid, st);
-    else if (bn == 128) rc = launch_gemm_bn<128>(maps, kp, grid, st);
-    else rc = launch_gemm_bn<256>(maps, kp, grid, st);
+    rc = launch_gemm_dispatch(bn, epi_class_of(kp.e, split > 1), maps, kp, grid, st);
     gemm_timing_end(st);
     if (rc) return rc;
     if (split > 1) {

@@ -136,43 +136,77 @@ __global__ void __launch_bounds__(256) km_dist_kernel(const float* __restrict__ 
     }
 }
 
-// OpenBLAS sgemv_t summation order of row `a` (n floats) for column-kernel kind 0 (4-column AVX2 kernel) / 1 (2-column).
-// Executed by 8 cooperating lanes (l = 0..7) of one warp-aligned group; returns the result in lane 0.
-__device__ float km_gemv_order(const float* __restrict__ a, int n, int kind, int l, unsigned mask, int base_lane) {
+// OpenBLAS sgemv_t summation order (oracle/kmeans_oracle.py: blas_order_gemv_row) of T rows of length n, executed by
+// the whole block: the rows are streamed through shared memory in chunks of KM_CHUNK elements (coalesced loads by all
+// threads), and 8 lanes per row (lane = element index mod 8, or mod 4 for the 2-column kernel) add their elements in
+// ascending order.  Block boundaries of KM_NB elements fold the lanes: kind 0: (l + l+4) then (s0+s1)+(s2+s3).
+constexpr int KM_CHUNK = 1024;        // divides KM_NB; multiple of 8
+__device__ void km_gemv_order_block(const float* __restrict__ rows, int T, int n, float* __restrict__ stage /*[T][KM_CHUNK]*/,
+                                    float* __restrict__ pots) {
+    const int tid = threadIdx.x;
+    const int t = tid >> 3, l = tid & 7;           // lane-threads: tid < 8*T
+    const bool worker = t < T;
+    const unsigned wmask = __ballot_sync(0xffffffffu, worker);
+    const int rem = T & 3;
+    const int kind = (worker && t < T - rem) ? 0 : 1;
     const int m1 = n - (n & 3);
-    float y = 0.f;
+    float y = 0.f, acc = 0.f;
     for (int b0 = 0; b0 < m1; b0 += KM_NB) {
         const int len = min(KM_NB, m1 - b0);
-        float acc = 0.f;
-        if (kind == 0) {
-            int i = b0;
-            if (len & 4) { if (l < 4) acc = a[b0 + l]; i += 4; }
-            for (; i < b0 + len; i += 8) acc = __fadd_rn(acc, a[i + l]);
-        } else if (l < 4) {
-            for (int i = b0; i < b0 + len; i += 4) acc = __fadd_rn(acc, a[i + l]);
+        acc = 0.f;
+        // a leading group of 4 goes to lanes 0-3 when the block length is not a multiple of 8 (for the 4-lane kernel this
+        // is simply its first group); everything after it is whole groups of 8, so chunks never split a group
+        const int lead = (len & 4) ? 4 : 0;
+        if (worker && lead && l < 4) acc = rows[(size_t)t * n + b0 + l];
+        for (int c0 = lead; c0 < len; c0 += KM_CHUNK) {
+            const int clen = min(KM_CHUNK, len - c0);
+            __syncthreads();
+            for (int e = tid; e < T * clen; e += blockDim.x) {
+                const int tt = e / clen, i = e - tt * clen;
+                stage[tt * KM_CHUNK + i] = rows[(size_t)tt * n + b0 + c0 + i];
+            }
+            __syncthreads();
+            if (worker) {
+                const float* a = stage + t * KM_CHUNK;
+                if (kind == 0) {
+#pragma unroll 4
+                    for (int i = 0; i < clen; i += 8) acc = __fadd_rn(acc, a[i + l]);
+                } else if (l < 4) {
+#pragma unroll 4
+                    for (int i = 0; i < clen; i += 4) acc = __fadd_rn(acc, a[i + l]);
+                }
+            }
         }
-        // fold: kind 0: s4[j] = acc[j] + acc[j+4]; then (s0+s1)+(s2+s3)
-        float s = acc;
-        if (kind == 0) s = __fadd_rn(acc, __shfl_sync(mask, acc, base_lane + ((l + 4) & 7)));
-        const float p01 = __fadd_rn(__shfl_sync(mask, s, base_lane + 0), __shfl_sync(mask, s, base_lane + 1));
-        const float p23 = __fadd_rn(__shfl_sync(mask, s, base_lane + 2), __shfl_sync(mask, s, base_lane + 3));
-        y = __fadd_rn(y, __fadd_rn(p01, p23));
+        if (worker) {
+            const unsigned mask = wmask;
+            const int base = (tid & 31) & ~7;
+            float sfold = acc;
+            if (kind == 0) sfold = __fadd_rn(acc, __shfl_sync(mask, acc, base + ((l + 4) & 7)));
+            const float p01 = __fadd_rn(__shfl_sync(mask, sfold, base + 0), __shfl_sync(mask, sfold, base + 1));
+            const float p23 = __fadd_rn(__shfl_sync(mask, sfold, base + 2), __shfl_sync(mask, sfold, base + 3));
+            y = __fadd_rn(y, __fadd_rn(p01, p23));
+        }
     }
-    if (n & 3) {
-        float t = a[m1];
-        for (int i = m1 + 1; i < n; ++i) t = __fadd_rn(t, a[i]);
-        y = __fadd_rn(y, t);
+    if (worker && l == 0) {
+        if (n & 3) {
+            const float* a = rows + (size_t)t * n;
+            float tt = a[m1];
+            for (int i = m1 + 1; i < n; ++i) tt = __fadd_rn(tt, a[i]);
+            y = __fadd_rn(y, tt);
+        }
+        pots[t] = y;
     }
-    return y;
 }
 
 // One block (1024 threads) per seeding step: potentials in BLAS order -> best candidate -> closest := its row ->
 // sequential float32 cumsum -> next candidates by searchsorted(left) of uniform * pot.
 // step 0: `newc` holds the distances to the first centre (T_in = 1, potential through the sdot order).
+// dynamic shared memory: n floats (closest / cumsum) + KM_MAXT * KM_CHUNK floats (staging)
 __global__ void __launch_bounds__(1024) km_select_kernel(const float* __restrict__ newc, int T_in, int n, int step, int k, int T_next,
                                                          const double* __restrict__ uniforms, float* __restrict__ closest, int* __restrict__ cand,
                                                          int* __restrict__ chosen, float* __restrict__ pot_io) {
     extern __shared__ float cs[];                  // n floats: closest, then its cumsum
+    float* stage = cs + ((n + 31) & ~31);
     __shared__ float pots[KM_MAXT];
     __shared__ float acc16[64];
     __shared__ int s_best;
@@ -184,6 +218,7 @@ __global__ void __launch_bounds__(1024) km_select_kernel(const float* __restrict
         const int n32 = n & ~31, n64 = n32 & ~63;
         if (tid < 64) {
             float a = 0.f;
+#pragma unroll 4
             for (int b = 0; b < n64; b += 64) a = __fadd_rn(a, newc[b + tid]);
             acc16[tid] = a;
         }
@@ -207,16 +242,7 @@ __global__ void __launch_bounds__(1024) km_select_kernel(const float* __restrict
             s_pot = (float)dsum; s_best = 0;
         }
     } else {
-        // cblas_sgemv order per candidate row (blas_order_gemv_row): warp w handles rows 4w..4w+3, 8 lanes each
-        const int w = tid >> 5, lane = tid & 31;
-        const int t = w * 4 + (lane >> 3), l = lane & 7;
-        if (w * 4 < T_in) {
-            const int rem = T_in & 3;
-            const int tt = min(t, T_in - 1);
-            const int kind = tt < T_in - rem ? 0 : 1;
-            const float y = km_gemv_order(newc + (size_t)tt * n, n, kind, l, 0xffffffffu, lane & ~7);
-            if (l == 0 && t < T_in) pots[t] = y;
-        }
+        km_gemv_order_block(newc, T_in, n, stage, pots);
         __syncthreads();
         if (tid == 0) {
             int best = 0;
@@ -234,7 +260,17 @@ __global__ void __launch_bounds__(1024) km_select_kernel(const float* __restrict
     if (step + 1 >= k) return;
     if (tid == 0) {                                  // np.cumsum(float32): strictly sequential
         float a = 0.f;
-        for (int i = 0; i < n; ++i) { a = __fadd_rn(a, cs[i]); cs[i] = a; }
+        int i = 0;
+        for (; i + 8 <= n; i += 8) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = cs[i + u];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { a = __fadd_rn(a, v[u]); v[u] = a; }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) cs[i + u] = v[u];
+        }
+        for (; i < n; ++i) { a = __fadd_rn(a, cs[i]); cs[i] = a; }
     }
     __syncthreads();
     for (int t = 0; t < T_next; ++t) {
@@ -268,55 +304,62 @@ __global__ void km_center_norm_kernel(const float* __restrict__ centers, int k, 
 }
 
 // label[i] = first argmin_j (csq[j] - 2 <x_i, c_j>) in float32.  Block = 32 rows x 128 centres (looping over centre
-// tiles when k > 128), 256 threads, each 2 rows x 8 centres; K is consumed in chunks of 32 through shared memory.
-__global__ void __launch_bounds__(256) km_assign_kernel(const float* __restrict__ Xc, const float* __restrict__ centers, const float* __restrict__ csq,
+// tiles when k > 128), 128 threads, each 4 rows x 8 centres (centres tx*4..+3 and 64+tx*4..+3); K is consumed in
+// ascending chunks of 32 through shared memory, one FMA chain per (row, centre).
+__global__ void __launch_bounds__(128) km_assign_kernel(const float* __restrict__ Xc, const float* __restrict__ centers, const float* __restrict__ csq,
                                                         int n, int d, int k, const int* __restrict__ labels_old, int* __restrict__ labels,
                                                         KmFlags* flags) {
-    __shared__ float Xs[32][33];      // [k][row]
-    __shared__ float Cs[32][129];     // [k][centre]
+    __shared__ __align__(16) float Xs[32][36];       // [k][row]    (+4 padding keeps float4 reads aligned)
+    __shared__ __align__(16) float Cs[32][132];      // [k][centre]
     __shared__ float bestv[32][16];
     __shared__ int besti[32][16];
     const int tid = threadIdx.x;
-    const int tx = tid & 15, ty = tid >> 4;          // tx: centre group (8 centres), ty: row pair
+    const int tx = tid & 15, ty = tid >> 4;          // tx: centre group, ty: row group (4 rows)
     const int row0 = blockIdx.x * 32;
-    float rbest[2] = {INFINITY, INFINITY};
-    int ribest[2] = {0, 0};
+    float rbest[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
+    int ribest[4] = {0, 0, 0, 0};
     for (int j0 = 0; j0 < k; j0 += 128) {
-        float acc[2][8];
+        float acc[4][8];
 #pragma unroll
-        for (int r = 0; r < 2; ++r)
+        for (int r = 0; r < 4; ++r)
 #pragma unroll
             for (int c = 0; c < 8; ++c) acc[r][c] = 0.f;
         for (int k0 = 0; k0 < d; k0 += 32) {
-            // stage 32 rows x 32 k of X and 128 centres x 32 k of C (transposed into [k][*])
-            for (int e = tid; e < 32 * 32; e += 256) {
-                const int r = e >> 5, kk = e & 31;
+            // global reads are float4 along k (d % 4 == 0), stored transposed
+            for (int e = tid; e < 32 * 8; e += 128) {
+                const int r = e >> 3, kq = (e & 7) * 4;
                 const int row = row0 + r;
-                Xs[kk][r] = (row < n && k0 + kk < d) ? Xc[(size_t)row * d + k0 + kk] : 0.f;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (row < n && k0 + kq < d) v = *reinterpret_cast<const float4*>(Xc + (size_t)row * d + k0 + kq);
+                Xs[kq][r] = v.x; Xs[kq + 1][r] = v.y; Xs[kq + 2][r] = v.z; Xs[kq + 3][r] = v.w;
             }
-            for (int e = tid; e < 128 * 32; e += 256) {
-                const int c = e >> 5, kk = e & 31;
+            for (int e = tid; e < 128 * 8; e += 128) {
+                const int c = e >> 3, kq = (e & 7) * 4;
                 const int j = j0 + c;
-                Cs[kk][c] = (j < k && k0 + kk < d) ? centers[(size_t)j * d + k0 + kk] : 0.f;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (j < k && k0 + kq < d) v = *reinterpret_cast<const float4*>(centers + (size_t)j * d + k0 + kq);
+                Cs[kq][c] = v.x; Cs[kq + 1][c] = v.y; Cs[kq + 2][c] = v.z; Cs[kq + 3][c] = v.w;
             }
             __syncthreads();
 #pragma unroll 8
             for (int kk = 0; kk < 32; ++kk) {
-                const float x0 = Xs[kk][ty * 2], x1 = Xs[kk][ty * 2 + 1];
+                const float4 xv = *reinterpret_cast<const float4*>(&Xs[kk][ty * 4]);
+                const float4 c0 = *reinterpret_cast<const float4*>(&Cs[kk][tx * 4]);
+                const float4 c1 = *reinterpret_cast<const float4*>(&Cs[kk][64 + tx * 4]);
+                const float xr[4] = {xv.x, xv.y, xv.z, xv.w};
+                const float cv[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const float cv = Cs[kk][tx + 16 * c];
-                    acc[0][c] = fmaf(x0, cv, acc[0][c]);
-                    acc[1][c] = fmaf(x1, cv, acc[1][c]);
-                }
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) acc[r][c] = fmaf(xr[r], cv[c], acc[r][c]);
             }
             __syncthreads();
         }
 #pragma unroll
-        for (int r = 0; r < 2; ++r)
+        for (int r = 0; r < 4; ++r)
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-                const int j = j0 + tx + 16 * c;
+                const int j = j0 + (c < 4 ? tx * 4 + c : 64 + tx * 4 + (c - 4));
                 if (j < k) {
                     const float dist = fmaf(-2.0f, acc[r][c], csq[j]);
                     if (dist < rbest[r] || (dist == rbest[r] && j < ribest[r])) { rbest[r] = dist; ribest[r] = j; }
@@ -324,7 +367,7 @@ __global__ void __launch_bounds__(256) km_assign_kernel(const float* __restrict_
             }
     }
 #pragma unroll
-    for (int r = 0; r < 2; ++r) { bestv[ty * 2 + r][tx] = rbest[r]; besti[ty * 2 + r][tx] = ribest[r]; }
+    for (int r = 0; r < 4; ++r) { bestv[ty * 4 + r][tx] = rbest[r]; besti[ty * 4 + r][tx] = ribest[r]; }
     __syncthreads();
     if (tid < 32) {
         const int row = row0 + tid;
@@ -453,7 +496,7 @@ int sq_kmeans_fit(const float* features, int n, int d, int k, int trials, int fi
         set_error("kmeans: %d local trials unsupported (the restated sgemv order covers trials %% 4 in {0, 2}; k in [55,148] gives 6)", trials); return -1;
     }
     if (first_center < 0 || first_center >= n) { set_error("kmeans: first centre out of range"); return -1; }
-    if ((size_t)n * 4 + (size_t)(k + 1) * 4 > 200 * 1024) { set_error("kmeans: n=%d too large for the single-block selection kernels", n); return -1; }
+    if ((size_t)n * 4 + (size_t)(k + 1) * 4 > 160 * 1024) { set_error("kmeans: n=%d too large for the single-block selection kernels", n); return -1; }
     KmWs L; km_ws_layout(n, d, k, &L);
     if (!workspace || workspace_bytes < L.total) { set_error("kmeans: workspace %zu < %zu", workspace_bytes, L.total); return -1; }
     cudaStream_t st = (cudaStream_t)stream;
@@ -472,6 +515,7 @@ int sq_kmeans_fit(const float* features, int n, int d, int k, int trials, int fi
         cudaFuncSetAttribute(km_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_done = true;
     }
+    const size_t sel_smem = (size_t)((n + 31) & ~31) * 4 + (size_t)KM_MAXT * KM_CHUNK * 4;
     cudaMemsetAsync(flags, 0, sizeof(KmFlags), st);
     // ---- preparation (fit L1490-1500)
     km_colstats_kernel<<<(d + 63) / 64, 64, 0, st>>>(features, n, d, mean, var);
@@ -480,7 +524,7 @@ int sq_kmeans_fit(const float* features, int n, int d, int k, int trials, int fi
     // ---- k-means++ (L180-279)
     cudaMemcpyAsync(cand, &first_center, sizeof(int), cudaMemcpyHostToDevice, st);
     launch_dist<1>(Xc, xx64, cand, nullptr, n, d, newc, st);
-    km_select_kernel<<<1, 1024, (size_t)n * 4, st>>>(newc, 1, n, 0, k, trials, uniforms, closest, cand, chosen, pot);
+    km_select_kernel<<<1, 1024, sel_smem, st>>>(newc, 1, n, 0, k, trials, uniforms, closest, cand, chosen, pot);
     for (int c = 1; c < k; ++c) {
         switch (trials) {
             case 2: launch_dist<2>(Xc, xx64, cand, closest, n, d, newc, st); break;
@@ -488,7 +532,7 @@ int sq_kmeans_fit(const float* features, int n, int d, int k, int trials, int fi
             case 6: launch_dist<6>(Xc, xx64, cand, closest, n, d, newc, st); break;
             default: launch_dist<8>(Xc, xx64, cand, closest, n, d, newc, st); break;
         }
-        km_select_kernel<<<1, 1024, (size_t)n * 4, st>>>(newc, trials, n, c, k, trials, uniforms, closest, cand, chosen, pot);
+        km_select_kernel<<<1, 1024, sel_smem, st>>>(newc, trials, n, c, k, trials, uniforms, closest, cand, chosen, pot);
     }
     km_gather_centers_kernel<<<k, 256, 0, st>>>(Xc, chosen, k, d, cA);
     if (chosen_out) cudaMemcpyAsync(chosen_out, chosen, (size_t)k * 4, cudaMemcpyDeviceToDevice, st);
@@ -504,7 +548,7 @@ int sq_kmeans_fit(const float* features, int n, int d, int k, int trials, int fi
     for (it = 0; it < max_iter; ++it) {
         cudaMemsetAsync(&flags->n_changed, 0, sizeof(int), st);
         km_center_norm_kernel<<<(k + 7) / 8, 256, 0, st>>>(cur, k, d, csq);
-        km_assign_kernel<<<(n + 31) / 32, 256, 0, st>>>(Xc, cur, csq, n, d, k, it == 0 ? nullptr : labels_old, labels, flags);
+        km_assign_kernel<<<(n + 31) / 32, 128, 0, st>>>(Xc, cur, csq, n, d, k, it == 0 ? nullptr : labels_old, labels, flags);
         km_bucket_kernel<<<1, 1024, bucket_smem, st>>>(labels, n, k, offsets, members, flags);
         km_segment_mean_kernel<<<dim3(nparts, k), 128, 0, st>>>(Xc, offsets, members, d, 0, nxt, cur, shift);
         km_converge_kernel<<<1, 32, 0, st>>>(shift, k, nparts, flags);
@@ -519,7 +563,7 @@ int sq_kmeans_fit(const float* features, int n, int d, int k, int trials, int fi
     }
     if (!strict) {                                                 // rerun the E-step with the final centres (L741-753)
         km_center_norm_kernel<<<(k + 7) / 8, 256, 0, st>>>(cur, k, d, csq);
-        km_assign_kernel<<<(n + 31) / 32, 256, 0, st>>>(Xc, cur, csq, n, d, k, nullptr, labels, flags);
+        km_assign_kernel<<<(n + 31) / 32, 128, 0, st>>>(Xc, cur, csq, n, d, k, nullptr, labels, flags);
     }
     if (n_iter_host) *n_iter_host = it > max_iter ? max_iter : it;
     // ---- cluster features: per-label mean of the RAW features (kmean_features.py:99-105)
