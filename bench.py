@@ -239,8 +239,8 @@ def bench_vis(args, dev, rank, world, timed, pk):
            "e2e": {"value": world * VIS_B / (e2e_ms * 1e-3), "unit": "slides/s", "ms_per_step": e2e_ms,
                    "h2d_bytes_per_step": xd.numel() * 4 + yd.numel() * 4, "d2h_bytes_per_step": 4},
            "final_loss": float(loss_h.item())}
+    tms, n, fl = gemm_timing(L, _lib, step_dev)        # every rank runs it: the step contains the gradient all-reduce
     if rank == 0:
-        tms, n, fl = gemm_timing(L, _lib, step_dev)
         alg = VIS_FLOP_PER_SLIDE * VIS_B
         ach = alg / (tms * 1e-3) / 1e12
         out["roofline"] = {"bound": "tensor", "kernel": "gemm_tc_kernel (split-precision GEMMs of the step, fused epilogues)",

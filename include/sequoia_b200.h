@@ -158,6 +158,21 @@ SQ_API int sq_mse_fwd_bwd(const float* pred, const float* target, int batch, int
 SQ_API int sq_adamw_flat(float* p, const float* g, float* m, float* v, void* p_hi, void* p_lo, long long n, float lr, float beta1,
                          float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream);
 
+/* ------------------------------------------------------------------ UNI ViT-L/16 feature extractor
+ * Replaces the timm model of pre_processing/compute_features_hdf5.py:63-66 and its call `model(image[None,:])` (:128) plus
+ * the ToTensor/Normalize preprocessing (:53-56).  `tensors`: HOST array of sq_vitl16_num_tensors(depth) DEVICE pointers in
+ * timm state_dict order: cls_token, pos_embed, patch_embed.proj.{weight,bias}, per block {norm1.weight, norm1.bias,
+ * attn.qkv.weight, attn.qkv.bias, attn.proj.weight, attn.proj.bias, ls1.gamma, norm2.weight, norm2.bias, mlp.fc1.weight,
+ * mlp.fc1.bias, mlp.fc2.weight, mlp.fc2.bias, ls2.gamma}, norm.weight, norm.bias (all fp32).
+ * input_kind 0: uint8 [batch,224,224,3]; 1: fp32 [batch,3,224,224] normalised.  features: fp32 [batch,1024]. */
+SQ_API int sq_vitl16_num_tensors(int depth);
+SQ_API long long sq_vitl16_packed_weight_elems(int depth);   /* bf16 elements */
+SQ_API long long sq_vitl16_packed_vec_elems(int depth);      /* fp32 elements */
+SQ_API int sq_vitl16_prepack(const void* const* tensors, int depth, void* packed_w, float* packed_v, void* stream);
+SQ_API size_t sq_vitl16_workspace_bytes(int batch);
+SQ_API int sq_vitl16_extract(const void* input, int input_kind, int batch, int depth, const void* packed_w, const float* packed_v,
+                             float* features, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------ per-slide k-means reduction
  * Replaces `KMeans(n_clusters=100, random_state=0).fit(features)` and the per-label mean loop of
  * pre_processing/kmean_features.py:96-105 (the arithmetic is scikit-learn's: init='k-means++', n_init=1,

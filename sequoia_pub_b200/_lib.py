@@ -71,6 +71,12 @@ SIGNATURES = {
     "sq_mse_fwd_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "sq_adamw_flat": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_float, c_float, c_float,
                               c_float, c_float, c_int, c_float, c_void_p]),
+    "sq_vitl16_num_tensors": (c_int, [c_int]),
+    "sq_vitl16_packed_weight_elems": (c_ll, [c_int]),
+    "sq_vitl16_packed_vec_elems": (c_ll, [c_int]),
+    "sq_vitl16_prepack": (c_int, [C.POINTER(c_void_p), c_int, c_void_p, c_void_p, c_void_p]),
+    "sq_vitl16_workspace_bytes": (c_size_t, [c_int]),
+    "sq_vitl16_extract": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "sq_kmeans_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "sq_kmeans_fit": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p,
                               C.POINTER(c_int), c_void_p, c_size_t, c_void_p]),

@@ -13,6 +13,7 @@ import ctypes as C
 import torch
 
 from . import _lib
+from .dist import allreduce_stage, stage_ranges
 from .tformer_lin import ViS
 
 
@@ -40,14 +41,7 @@ class FusedTrainer:
             self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
             self.mse_scratch = torch.empty(1024, dtype=torch.float32, device=dev)
             self._token = m._flat_token
-            # contiguous [begin, end) element ranges of the flat buffer per backward stage (head = stage depth)
-            n = _lib.lib().sq_vis_param_table_len(C.byref(m._cfg))
-            table = (C.c_longlong * n)()
-            total = C.c_longlong()
-            _lib.check(_lib.lib().sq_vis_param_layout(C.byref(m._cfg), table, n, C.byref(total)))
-            depth = m._cfg.depth
-            starts = [table[1 + 18 * l] for l in range(depth)] + [table[n - 4], total.value]
-            self.stage_range = [(0 if l == 0 else starts[l], starts[l + 1]) for l in range(depth)] + [(starts[depth], total.value)]
+            self.stage_range = stage_ranges(m._cfg)      # contiguous slices of the flat buffer per backward stage
         return m
 
     def step(self, x, y):
@@ -67,8 +61,7 @@ class FusedTrainer:
         if self.world > 1 and self.overlap:
             for s in range(cfg.depth, -1, -1):
                 m._backward_impl(act, dpred if s == cfg.depth else None, B, False, gbuf=self.g, stage_hi=s, stage_lo=s)
-                b, e = self.stage_range[s]
-                works.append(torch.distributed.all_reduce(self.g[b:e], group=self.pg, async_op=True))
+                works.append(allreduce_stage(self.g, self.stage_range[s], self.pg))
             for w in works:
                 w.wait()
         else:

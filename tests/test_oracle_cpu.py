@@ -94,3 +94,25 @@ def test_kmeans_oracle_matches_sklearn_golden_and_live():
     from sklearn.cluster import KMeans                       # live check on one more slide (sklearn is the reference's dependency)
     X = K.make_slide_features(21, n=700, d=128, modes=90)
     assert np.array_equal(K.fit_labels(X)[0], KMeans(n_clusters=100, random_state=0).fit(X).labels_)
+
+
+def test_uni_oracle_structure_matches_torchvision_vit_l_16():
+    """UNI parity is unpinned (no timm, no weights); the restatement is cross-checked against torchvision's ViT-L/16,
+    which shares the block structure (cls-first tokens, pre-LN, LN eps 1e-6, exact GELU) when LayerScale gamma = 1."""
+    from torchvision.models import vit_l_16
+    from oracle import uni_oracle as U
+    assert len(U.param_shapes()) == 4 + 24 * 14 + 2
+    sd = U.make_state_dict(0, depth=3)
+    for k in sd:
+        if k.endswith("gamma"):
+            sd[k] = torch.ones_like(sd[k])
+    tv = vit_l_16(weights=None)
+    tv.encoder.layers = tv.encoder.layers[:3]
+    tv.heads = torch.nn.Identity()
+    missing = tv.load_state_dict(U.to_torchvision(sd), strict=True)
+    x = U.preprocess(U.make_patches(0, 2))
+    with torch.no_grad():
+        want = tv.eval()(x).numpy()
+        got = U.forward(sd, x).numpy()
+    assert got.shape == (2, 1024)
+    assert _rel(got, want) < 1e-5
