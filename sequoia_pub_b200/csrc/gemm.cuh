@@ -244,53 +244,83 @@ __device__ __forceinline__ void epilogue_apply(float* v, long long row, int col0
     }
 }
 
-// ResNet convolution epilogue for 32 full columns: + shift (folded BatchNorm), + bf16 residual, ReLU -> bf16 and/or fp32.
-// All accesses are 16-byte vectors (row strides are multiples of 8 elements, col0 a multiple of 32).
-__device__ __forceinline__ void epilogue_conv32(float* v, long long row, int col0, const EpiParams& e) {
+// ResNet convolution epilogue with COALESCED global accesses: one warp owns 32 accumulator rows x NC columns (lane = row
+// after tcgen05.ld).  Row-per-lane 16-byte accesses touch 32 different 128-byte lines per request and are limited by L1
+// tag throughput (measured: ~100 cycles per element on the 64->256 1x1 convolutions), so the residual tile is read and
+// the output tile written in a lines-per-request pattern (32/SEGS rows x SEGS 16-byte segments) and transposed through a
+// per-warp shared-memory staging buffer (32 rows x 144 B, conflict-free for both patterns).
+constexpr int GEMM_STG_LD = 144;
+constexpr int GEMM_STG_BYTES = 32 * GEMM_STG_LD;
+template <int NC>
+__device__ __forceinline__ void epilogue_conv_staged(float* v, long long row_base, int lane, int M, int col0, const EpiParams& e, uint8_t* stg) {
+    constexpr int SEGS = NC / 8;            // 16-byte segments per row of NC bf16
+    constexpr int RPR = 32 / SEGS;          // rows per warp-wide request
+    constexpr int NREQ = 32 / RPR;
+    const int r_sub = lane / SEGS, seg = lane % SEGS;
+    uint4 rr[NREQ];
+    if (e.res_bf) {
+#pragma unroll
+        for (int i = 0; i < NREQ; ++i) {
+            const long long r = row_base + i * RPR + r_sub;
+            rr[i] = make_uint4(0, 0, 0, 0);
+            if (r < M) rr[i] = *reinterpret_cast<const uint4*>(e.res_bf + r * e.ld_res + col0 + seg * 8);
+        }
+    }
     if (e.bias) {
         const float4* b4 = reinterpret_cast<const float4*>(e.bias + col0);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < NC / 4; ++i) {
             const float4 b = __ldg(b4 + i);
             v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
         }
     }
     if (e.res_bf) {
-        const uint4* r4 = reinterpret_cast<const uint4*>(e.res_bf + row * e.ld_res + col0);
-        uint4 r[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) r[i] = r4[i];
+        for (int i = 0; i < NREQ; ++i) *reinterpret_cast<uint4*>(stg + (i * RPR + r_sub) * GEMM_STG_LD + seg * 16) = rr[i];
+        __syncwarp();
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const uint32_t w[4] = {r[i].x, r[i].y, r[i].z, r[i].w};
+        for (int j = 0; j < SEGS; ++j) {
+            const uint4 t = *reinterpret_cast<const uint4*>(stg + lane * GEMM_STG_LD + j * 16);
+            const uint32_t w[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                v[8 * i + 2 * j] += __uint_as_float(w[j] << 16);
-                v[8 * i + 2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u);
+            for (int k = 0; k < 4; ++k) {
+                v[8 * j + 2 * k] += __uint_as_float(w[k] << 16);
+                v[8 * j + 2 * k + 1] += __uint_as_float(w[k] & 0xffff0000u);
             }
         }
+        __syncwarp();
     }
     if (e.act == ACT_RELU) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
+        for (int i = 0; i < NC; ++i) v[i] = fmaxf(v[i], 0.0f);
     }
     if (e.out_hi) {
-        uint4* o4 = reinterpret_cast<uint4*>(e.out_hi + row * e.ld_bf + col0);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int j = 0; j < SEGS; ++j) {
             uint4 pk;
             __nv_bfloat162 t;
-            t = __floats2bfloat162_rn(v[8 * i], v[8 * i + 1]); pk.x = *reinterpret_cast<uint32_t*>(&t);
-            t = __floats2bfloat162_rn(v[8 * i + 2], v[8 * i + 3]); pk.y = *reinterpret_cast<uint32_t*>(&t);
-            t = __floats2bfloat162_rn(v[8 * i + 4], v[8 * i + 5]); pk.z = *reinterpret_cast<uint32_t*>(&t);
-            t = __floats2bfloat162_rn(v[8 * i + 6], v[8 * i + 7]); pk.w = *reinterpret_cast<uint32_t*>(&t);
-            o4[i] = pk;
+            t = __floats2bfloat162_rn(v[8 * j], v[8 * j + 1]); pk.x = *reinterpret_cast<uint32_t*>(&t);
+            t = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]); pk.y = *reinterpret_cast<uint32_t*>(&t);
+            t = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]); pk.z = *reinterpret_cast<uint32_t*>(&t);
+            t = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]); pk.w = *reinterpret_cast<uint32_t*>(&t);
+            *reinterpret_cast<uint4*>(stg + lane * GEMM_STG_LD + j * 16) = pk;
         }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < NREQ; ++i) {
+            const long long r = row_base + i * RPR + r_sub;
+            const uint4 t = *reinterpret_cast<const uint4*>(stg + (i * RPR + r_sub) * GEMM_STG_LD + seg * 16);
+            if (r < M) *reinterpret_cast<uint4*>(e.out_hi + r * e.ld_bf + col0 + seg * 8) = t;
+        }
+        __syncwarp();
     }
     if (e.out_f32) {
-        float4* o4 = reinterpret_cast<float4*>(e.out_f32 + row * e.ld_f32 + col0);
+        const long long r = row_base + lane;
+        if (r < M) {
+            float4* o4 = reinterpret_cast<float4*>(e.out_f32 + r * e.ld_f32 + col0);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            for (int i = 0; i < NC / 4; ++i) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        }
     }
 }
 
@@ -300,11 +330,13 @@ constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_A_BYTES = GEMM_BM * GEMM_BK * 2;  // 16 KB
 
-template <int BN> struct GemmCfg {
+template <int BN, int CLS = 0> struct GemmCfg {
     static constexpr int B_BYTES = BN * GEMM_BK * 2;
     static constexpr int STAGE_BYTES = GEMM_A_BYTES + B_BYTES;
-    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int STAGING = (CLS == EPI_CONV) ? GEMM_EPI_WARPS * GEMM_STG_BYTES : 0;     // per-warp epilogue transposition buffers
+    static constexpr int STAGES = (BN == 256) ? (STAGING ? 3 : 4) : (BN == 128 ? (STAGING ? 5 : 6) : (STAGING ? 6 : 8));
+    static_assert(STAGES * STAGE_BYTES + 1024 + 256 + STAGING <= 232448, "shared memory budget");
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + STAGING;
     static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
 };
 
@@ -313,7 +345,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB1,
                const GemmKParams p) {
-    using Cfg = GemmCfg<BN>;
+    using Cfg = GemmCfg<BN, CLS>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -485,19 +517,44 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         if (row_ok) epilogue_apply<64, CLS>(v, row, n0 + c, p.N, p.e);
                     }
                 }
+            } else if constexpr (CLS == EPI_CONV) {
+                // coalesced path: whole warp cooperates (rows beyond M are predicated inside)
+                const bool staged = !p.diag64 && n0 + cend <= p.N && ((p.e.ld_bf | p.e.ld_f32 | p.e.ld_res) & 7) == 0 &&
+                                    ((reinterpret_cast<uintptr_t>(p.e.bias) | reinterpret_cast<uintptr_t>(p.e.out_f32) |
+                                      reinterpret_cast<uintptr_t>(p.e.out_hi) | reinterpret_cast<uintptr_t>(p.e.res_bf)) & 15) == 0;
+                uint8_t* stg = smem + STAGES * Cfg::STAGE_BYTES + 256 + (warp - 4) * GEMM_STG_BYTES;
+                const long long row_base = (long long)mt * GEMM_BM + q * 32;
+                if (staged) {
+                    if constexpr (BN >= 128) {
+                        for (int c = cbeg; c < cend; c += 64) {
+                            float v[64];
+                            tmem_ld32(tacc + c, v);
+                            tmem_ld32(tacc + c + 32, v + 32);
+                            tmem_ld_wait();
+                            epilogue_conv_staged<64>(v, row_base, lane, p.M, n0 + c, p.e, stg);
+                        }
+                    } else {
+                        for (int c = cbeg; c < cend; c += 32) {
+                            float v[32];
+                            tmem_ld32(tacc + c, v);
+                            tmem_ld_wait();
+                            epilogue_conv_staged<32>(v, row_base, lane, p.M, n0 + c, p.e, stg);
+                        }
+                    }
+                } else {
+                    for (int c = cbeg; c < cend && n0 + c < p.N; c += 32) {
+                        float v[32];
+                        tmem_ld32(tacc + c, v);
+                        tmem_ld_wait();
+                        if (row_ok) epilogue_apply<32, CLS>(v, row, c0 + c, ncols, p.e);
+                    }
+                }
             } else if constexpr (CLS != EPI_LN64) {
                 for (int c = cbeg; c < cend && n0 + c < p.N; c += 32) {
                     float v[32];
                     tmem_ld32(tacc + c, v);
                     tmem_ld_wait();
-                    if (row_ok) {
-                        if constexpr (CLS == EPI_CONV) {
-                            if (c0 + c + 32 <= ncols && ((p.e.ld_bf | p.e.ld_f32 | p.e.ld_res) & 7) == 0 && ((reinterpret_cast<uintptr_t>(p.e.bias) | reinterpret_cast<uintptr_t>(p.e.out_f32) | reinterpret_cast<uintptr_t>(p.e.out_hi) | reinterpret_cast<uintptr_t>(p.e.res_bf)) & 15) == 0) epilogue_conv32(v, row, c0 + c, p.e);
-                            else epilogue_apply<32, CLS>(v, row, c0 + c, ncols, p.e);
-                        } else {
-                            epilogue_apply<32, CLS>(v, row, c0 + c, ncols, p.e);
-                        }
-                    }
+                    if (row_ok) epilogue_apply<32, CLS>(v, row, c0 + c, ncols, p.e);
                 }
             }
             tc_fence_before();
@@ -632,11 +689,11 @@ template <int BN, int CLS>
 int launch_gemm_inst(const CUtensorMap* maps, const GemmKParams& kp, int grid, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        cudaError_t err = cudaFuncSetAttribute(gemm_tc_kernel<BN, CLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::SMEM_BYTES);
+        cudaError_t err = cudaFuncSetAttribute(gemm_tc_kernel<BN, CLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN, CLS>::SMEM_BYTES);
         if (err != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(err)); return -1; }
         configured = true;
     }
-    gemm_tc_kernel<BN, CLS><<<grid, GEMM_THREADS, GemmCfg<BN>::SMEM_BYTES, st>>>(maps[0], maps[1], maps[2], maps[3], kp);
+    gemm_tc_kernel<BN, CLS><<<grid, GEMM_THREADS, GemmCfg<BN, CLS>::SMEM_BYTES, st>>>(maps[0], maps[1], maps[2], maps[3], kp);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) { set_error("gemm launch: %s", cudaGetErrorString(err)); return -1; }
     return 0;

@@ -72,10 +72,14 @@ __global__ void fold_bn_kernel(const float* __restrict__ w, const float* __restr
 // Stem im2col: one block = 32 consecutive output pixels of one output row.
 // kind 0: uint8 NHWC raw patch, applies x/255 then (x-mean)/std  (compute_features_hdf5.py:49-51)
 // kind 1: fp32 NCHW, already normalised (the tensor the reference hands to forward_extract)
+// The 7 input rows x 69 columns x 3 channels the block needs are staged as bf16 in shared memory; for a fixed filter row
+// r the 21 (s, c) taps of output pixel p are CONTIGUOUS there (offset r*207 + 6p), so column k of the im2col row is
+// tile[lut[k] + 6p] with a 192-entry table (-1 = zero padding 147..191).
 __global__ void __launch_bounds__(256) stem_im2col_kernel(const void* __restrict__ in, int kind, int H, int W, int Ho, int Wo,
                                                           bf16* __restrict__ col) {
-    constexpr int TW = 32, IW = TW * 2 + 5;   // 69 input columns
-    __shared__ float tile[7][IW][3];
+    constexpr int TW = 32, IW = TW * 2 + 5, ROW = IW * 3;   // 69 input columns, 207 values per staged row
+    __shared__ bf16 tile[7 * ROW + 1];
+    __shared__ short lut[STEM_K];
     const int tiles_w = Wo / TW;
     int b = blockIdx.x;
     const int tw = b % tiles_w; b /= tiles_w;
@@ -83,8 +87,9 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const void* __restrict
     const int ow0 = tw * TW;
     const int ih0 = oh * 2 - 3, iw0 = ow0 * 2 - 3;
     const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
-    for (int i = threadIdx.x; i < 7 * IW * 3; i += 256) {
-        const int c = i % 3; const int x = (i / 3) % IW; const int r = i / (3 * IW);
+    if (threadIdx.x < STEM_K) { const int k = threadIdx.x; lut[k] = k < 147 ? (short)((k / 21) * ROW + (k % 21)) : (short)-1; }
+    for (int i = threadIdx.x; i < 7 * ROW; i += 256) {
+        const int r = i / ROW; const int xc = i - r * ROW; const int x = xc / 3; const int c = xc - x * 3;
         const int ih = ih0 + r, iw = iw0 + x;
         float v = 0.f;
         if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
@@ -95,19 +100,18 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const void* __restrict
                 v = reinterpret_cast<const float*>(in)[(((long long)img * 3 + c) * H + ih) * W + iw];
             }
         }
-        tile[r][x][c] = v;
+        tile[i] = __float2bfloat16_rn(v);
     }
     __syncthreads();
     bf16* dst = col + (((long long)img * Ho + oh) * Wo + ow0) * STEM_K;
+    const bf16 zero = __float2bfloat16_rn(0.f);
     for (int i = threadIdx.x; i < TW * (STEM_K / 8); i += 256) {
         const int p = i / (STEM_K / 8); const int k8 = (i - p * (STEM_K / 8)) * 8;
         uint4 pack; bf16* h = reinterpret_cast<bf16*>(&pack);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const int k = k8 + j;
-            float v = 0.f;
-            if (k < 147) { const int c = k % 3; const int rs = k / 3; const int s = rs % 7; const int r = rs / 7; v = tile[r][p * 2 + s][c]; }
-            h[j] = __float2bfloat16_rn(v);
+            const int o = lut[k8 + j];
+            h[j] = o >= 0 ? tile[o + p * 6] : zero;
         }
         *reinterpret_cast<uint4*>(dst + (long long)p * STEM_K + k8) = pack;
     }
