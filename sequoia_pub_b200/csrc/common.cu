@@ -38,15 +38,19 @@ PFN_encodeTiled get_encode_fn() {
     return fn;
 }
 
-// One instantiation of the GEMM kernel per (tile width, epilogue class).
-int launch_gemm_dispatch(int bn, int cls, const CUtensorMap* maps, const GemmKParams& kp, int grid, cudaStream_t st) {
-#define SQ_CASE(BN, CLS) if (bn == BN && cls == CLS) return launch_gemm_inst<BN, CLS>(maps, kp, grid, st);
+// One instantiation of the GEMM kernel per (tile width, epilogue class[, fused split-precision staging]).
+int launch_gemm_dispatch(int bn, int cls, int fuse3, const CUtensorMap* maps, const GemmKParams& kp, int grid, cudaStream_t st) {
+#define SQ_CASE(BN, CLS) if (!fuse3 && bn == BN && cls == CLS) return launch_gemm_inst<BN, CLS, 0>(maps, kp, grid, st);
+#define SQ_CASE3(BN, CLS) if (fuse3 && bn == BN && cls == CLS) return launch_gemm_inst<BN, CLS, 1>(maps, kp, grid, st);
 #define SQ_ALL_BN(CLS) SQ_CASE(64, CLS) SQ_CASE(128, CLS) SQ_CASE(256, CLS)
-    SQ_ALL_BN(EPI_CONV) SQ_ALL_BN(EPI_F32) SQ_ALL_BN(EPI_GELU) SQ_ALL_BN(EPI_DGELU) SQ_CASE(128, EPI_LN64) SQ_CASE(64, EPI_LN64)
-    SQ_CASE(256, EPI_LN64) SQ_ALL_BN(EPI_GENERIC)
+#define SQ_FUSED(CLS) SQ_CASE3(128, CLS) SQ_CASE3(192, CLS) SQ_CASE3(256, CLS)
+    SQ_FUSED(EPI_F32) SQ_FUSED(EPI_GELU) SQ_FUSED(EPI_DGELU) SQ_FUSED(EPI_LN64)
+    SQ_ALL_BN(EPI_CONV) SQ_ALL_BN(EPI_F32) SQ_ALL_BN(EPI_GELU) SQ_ALL_BN(EPI_DGELU) SQ_ALL_BN(EPI_LN64) SQ_ALL_BN(EPI_GENERIC)
+#undef SQ_FUSED
 #undef SQ_ALL_BN
+#undef SQ_CASE3
 #undef SQ_CASE
-    set_error("gemm: no kernel for block_n %d class %d", bn, cls);
+    set_error("gemm: no kernel for block_n %d class %d fuse3 %d", bn, cls, fuse3);
     return -1;
 }
 

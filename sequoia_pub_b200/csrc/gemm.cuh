@@ -53,7 +53,10 @@ struct GemmKParams {
     int diag64;             // block-diagonal wgrad: only the 64x64 diagonal blocks of C are produced (BN = 64)
     // conv mode
     int conv, cblocks, S, stride, pad, tiles_per_img, BH, BIMG;
-    float* partial;         // split-K workspace [split][M][N]
+    float* partial;         // split-K workspace [split][M][N]; stream-K: per-CTA partial tiles [cta][BN][128]
+    int streamk;            // 1: the last, partially filled wave of tiles is split evenly over all CTAs (see WorkIter)
+    int sk_t0;              // first tile scheduled stream-K (tiles below it are whole waves)
+    int* sk_flags;          // stream-K: [cta][8] "partial published" flags, zeroed before the launch
     unsigned long long* prof;   // optional per-CTA cycle counters (sq_gemm_profile): [cta][16]
     EpiParams e;
 };
@@ -330,27 +333,79 @@ constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_A_BYTES = GEMM_BM * GEMM_BK * 2;  // 16 KB
 
-template <int BN, int CLS = 0> struct GemmCfg {
+// FUSE3: split-precision launches stage A_hi, A_lo, B_hi, B_lo of a k-block ONCE and issue the three MMA groups
+// (hi*hi, hi*lo, lo*hi) from that stage: 4 tile loads per k-block instead of 6.  The big ViS GEMMs are bound by
+// L2 -> shared-memory operand traffic (~14 TB/s measured), not by the tensor pipe, so this is worth ~1/3 of their time.
+template <int BN, int CLS = 0, int FUSE3 = 0> struct GemmCfg {
     static constexpr int B_BYTES = BN * GEMM_BK * 2;
-    static constexpr int STAGE_BYTES = GEMM_A_BYTES + B_BYTES;
+    static constexpr int STAGE_BYTES = (FUSE3 ? 2 : 1) * (GEMM_A_BYTES + B_BYTES);
     static constexpr int STAGING = (CLS == EPI_CONV) ? GEMM_EPI_WARPS * GEMM_STG_BYTES : 0;     // per-warp epilogue transposition buffers
-    static constexpr int STAGES = (BN == 256) ? (STAGING ? 3 : 4) : (BN == 128 ? (STAGING ? 5 : 6) : (STAGING ? 6 : 8));
+    static constexpr int STAGES = FUSE3 ? (BN >= 192 ? 2 : (BN == 128 ? 3 : 4))
+                                        : (BN == 256) ? (STAGING ? 3 : 4) : (BN == 128 ? (STAGING ? 5 : 6) : (STAGING ? 6 : 8));
     static_assert(STAGES * STAGE_BYTES + 1024 + 256 + STAGING <= 232448, "shared memory budget");
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + STAGING;
     static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
 };
 
-template <int BN, int CLS>
+// Work assignment shared by the three warp roles.
+//  classic : tile t = blockIdx.x + i * gridDim.x over [split][m][n] tiles, k-blocks of the tile's split.
+//  stream-K: whole waves of tiles (t < sk_t0) are processed classic; the CTAs then split the tiles x k-blocks iteration
+//            space of the LAST, partially filled wave evenly.  A CTA walks its share in DESCENDING order as segments
+//            (tile, kb0, kb1).  A segment that does not reach its tile's last k-block is a partial: its accumulator is
+//            published to the workspace (it is always the first stream-K segment of the CTA, so it is published early);
+//            the CTA that owns the tile's last k-block adds the partials (fixed order) and runs the epilogue.
+struct WorkIter {
+    int mode, t, step, total_tiles, tiles_mn, total_kb, kb_per_split, t0;
+    long long s, cur_end;
+    __device__ __forceinline__ WorkIter(int streamk, int sk_t0, int tiles_mn_, int total_tiles_, int total_kb_, int kb_per_split_) {
+        mode = streamk; tiles_mn = tiles_mn_; total_tiles = total_tiles_; total_kb = total_kb_; kb_per_split = kb_per_split_;
+        t = blockIdx.x; step = gridDim.x; s = 0; cur_end = 0; t0 = sk_t0;
+        if (mode) {
+            const long long total = (long long)(tiles_mn_ - sk_t0) * total_kb_;
+            s = total * blockIdx.x / gridDim.x; cur_end = total * (blockIdx.x + 1) / gridDim.x;
+        }
+    }
+    __device__ __forceinline__ bool next(int& tile, int& kb0, int& kb1, bool& first, bool& last) {
+        if (!mode || t < t0) {
+            if (t >= total_tiles) return false;
+            const int split = t / tiles_mn;
+            tile = t; kb0 = split * kb_per_split; kb1 = min(kb0 + kb_per_split, total_kb); first = true; last = true;
+            t += step;
+            return true;
+        }
+        if (cur_end <= s) return false;
+        const long long tt = (cur_end - 1) / total_kb, tb = tt * total_kb;
+        const long long sb = s > tb ? s : tb;
+        tile = t0 + (int)tt; kb0 = (int)(sb - tb); kb1 = (int)(cur_end - tb); first = kb0 == 0; last = kb1 == total_kb;
+        cur_end = sb;
+        return true;
+    }
+};
+__device__ __forceinline__ long long streamk_range_start(int cta, int sk_tiles, int total_kb, int grid) {
+    return (long long)sk_tiles * total_kb * cta / grid;
+}
+
+// adds the partial accumulators the `nprev` preceding CTAs published for this tile (fixed order; L1 bypassed)
+template <int NC>
+__device__ __forceinline__ void streamk_add(float* v, const float* partial, int nprev, int bn, int c, int r_in) {
+    for (int j = 1; j <= nprev; ++j) {
+        const float* ws = partial + ((size_t)(blockIdx.x - j) * bn + c) * 128 + r_in;
+#pragma unroll
+        for (int i = 0; i < NC; ++i) v[i] += __ldcg(ws + (size_t)i * 128);
+    }
+}
+
+template <int BN, int CLS, int FUSE3>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB1,
                const GemmKParams p) {
-    using Cfg = GemmCfg<BN, CLS>;
+    using Cfg = GemmCfg<BN, CLS, FUSE3>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* smemA = smem;
-    uint8_t* smemB = smem + STAGES * GEMM_A_BYTES;
+    // stage layout: [A (hi)][A lo (FUSE3)][B (hi)][B lo (FUSE3)]
+    constexpr int OFF_ALO = GEMM_A_BYTES, OFF_B = (FUSE3 ? 2 : 1) * GEMM_A_BYTES, OFF_BLO = OFF_B + Cfg::B_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
     uint64_t* full = bars;
     uint64_t* empty = bars + STAGES;
@@ -378,19 +433,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 
     const int tiles_mn = p.num_m * p.num_n;
     const int total_tiles = tiles_mn * p.split_k;
-    const int total_kb = p.nk * p.nterms;
+    const int total_kb = FUSE3 ? p.nk : p.nk * p.nterms;
 
     if (warp == 0) {
         if (elect_one()) {
             // ===================== TMA producer =====================
             int stage = 0; uint32_t phase = 0;
             long long pw = 0; const long long pt0 = clock64();
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            WorkIter wi(p.streamk, p.sk_t0, tiles_mn, total_tiles, total_kb, p.kb_per_split);
+            int t, kb0, kb1; bool seg_first, seg_last;
+            while (wi.next(t, kb0, kb1, seg_first, seg_last)) {
                 const int split = t / tiles_mn;
                 const int mn = t - split * tiles_mn;
                 const int mt = mn / p.num_n, nt = mn - mt * p.num_n;
-                const int kb0 = split * p.kb_per_split;
-                const int kb1 = min(kb0 + p.kb_per_split, total_kb);
                 const int m0 = mt * GEMM_BM, n0 = p.diag64 ? (2 * mt + nt) * 64 : nt * BN;
                 const int bn0 = n0 + nt * p.b_nadj_per_ntile, bkoff = nt * p.b_koff_per_ntile;
                 int img = 0, hin0 = 0;
@@ -403,11 +458,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     mbar_wait(&empty[stage], phase ^ 1);
                     pw += clock64() - w0;
                     mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+                    uint8_t* sbase = smem + stage * Cfg::STAGE_BYTES;
+                    if constexpr (FUSE3) {
+                        const int k0 = kb * GEMM_BK;
+                        if (p.a_mn) {
+                            tma_load_2d(&mapA0, &full[stage], sbase, m0, k0);
+                            tma_load_2d(&mapA0, &full[stage], sbase + 8192, m0 + 64, k0);
+                            tma_load_2d(&mapA1, &full[stage], sbase + OFF_ALO, m0, k0);
+                            tma_load_2d(&mapA1, &full[stage], sbase + OFF_ALO + 8192, m0 + 64, k0);
+                        } else {
+                            tma_load_2d(&mapA0, &full[stage], sbase, k0, m0);
+                            tma_load_2d(&mapA1, &full[stage], sbase + OFF_ALO, k0, m0);
+                        }
+                        if (p.b_mn) {
+#pragma unroll
+                            for (int a = 0; a < BN / 64; ++a) {
+                                tma_load_2d(&mapB0, &full[stage], sbase + OFF_B + a * 8192, n0 + a * 64, k0);
+                                tma_load_2d(&mapB1, &full[stage], sbase + OFF_BLO + a * 8192, n0 + a * 64, k0);
+                            }
+                        } else {
+                            tma_load_2d(&mapB0, &full[stage], sbase + OFF_B, k0, n0);
+                            tma_load_2d(&mapB1, &full[stage], sbase + OFF_BLO, k0, n0);
+                        }
+                    } else {
                     const int kk = kb / p.nterms, term = kb - kk * p.nterms;
                     const CUtensorMap* ma = (term == 2) ? &mapA1 : &mapA0;
                     const CUtensorMap* mb = (term == 1) ? &mapB1 : &mapB0;
-                    uint8_t* sa = smemA + stage * GEMM_A_BYTES;
-                    uint8_t* sb = smemB + stage * Cfg::B_BYTES;
+                    uint8_t* sa = sbase;
+                    uint8_t* sb = sbase + OFF_B;
                     const int k0 = kk * GEMM_BK;
                     if (p.conv) {
                         const int tap = kk / p.cblocks, cb = kk - tap * p.cblocks;
@@ -425,6 +503,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     } else {
                         tma_load_2d(mb, &full[stage], sb, k0 + bkoff, bn0);
                     }
+                    }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -437,10 +516,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         const uint32_t a_lbo = p.a_mn ? 8192u : 0u, b_lbo = p.b_mn ? 8192u : 0u;
         int stage = 0; uint32_t phase = 0; int iter = 0;
         long long mw_full = 0, mw_tmem = 0; const long long mt0 = clock64();
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++iter) {
-            const int split = t / tiles_mn;
-            const int kb0 = split * p.kb_per_split;
-            const int kb1 = min(kb0 + p.kb_per_split, total_kb);
+        WorkIter wi(p.streamk, p.sk_t0, tiles_mn, total_tiles, total_kb, p.kb_per_split);
+        int t, kb0, kb1; bool seg_first, seg_last;
+        for (; wi.next(t, kb0, kb1, seg_first, seg_last); ++iter) {
             const int as = iter & 1; const uint32_t aphase = (iter >> 1) & 1;
             const long long w1 = clock64();
             mbar_wait(&tmem_empty[as], aphase ^ 1);
@@ -453,13 +531,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 mw_full += clock64() - w2;
                 tc_fence_after();
                 if (elect_one()) {
-                    const uint32_t a_base = smem_u32(smemA + stage * GEMM_A_BYTES);
-                    const uint32_t b_base = smem_u32(smemB + stage * Cfg::B_BYTES);
+                    const uint32_t sbase = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                    if constexpr (FUSE3) {
+                        // hi*hi, hi*lo, lo*hi from the same stage
+                        const uint32_t abase[3] = {sbase, sbase, sbase + OFF_ALO};
+                        const uint32_t bbase[3] = {sbase + OFF_B, sbase + OFF_BLO, sbase + OFF_B};
 #pragma unroll
-                    for (int k = 0; k < GEMM_BK / 16; ++k) {
-                        const uint64_t da = make_smem_desc(a_base + k * a_kstep, 1024, a_lbo);
-                        const uint64_t db = make_smem_desc(b_base + k * b_kstep, 1024, b_lbo);
-                        umma_bf16(tacc, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        for (int term = 0; term < 3; ++term) {
+#pragma unroll
+                            for (int k = 0; k < GEMM_BK / 16; ++k) {
+                                const uint64_t da = make_smem_desc(abase[term] + k * a_kstep, 1024, a_lbo);
+                                const uint64_t db = make_smem_desc(bbase[term] + k * b_kstep, 1024, b_lbo);
+                                umma_bf16(tacc, da, db, idesc, (kb > kb0 || k > 0 || term > 0) ? 1u : 0u);
+                            }
+                        }
+                    } else {
+                        const uint32_t a_base = sbase;
+                        const uint32_t b_base = sbase + OFF_B;
+#pragma unroll
+                        for (int k = 0; k < GEMM_BK / 16; ++k) {
+                            const uint64_t da = make_smem_desc(a_base + k * a_kstep, 1024, a_lbo);
+                            const uint64_t db = make_smem_desc(b_base + k * b_kstep, 1024, b_lbo);
+                            umma_bf16(tacc, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        }
                     }
                     umma_commit(&empty[stage]);
                     if (kb == kb1 - 1) umma_commit(&tmem_full[as]);
@@ -475,7 +569,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         const int cbeg = ((warp - 4) >> 2) * (BN / 2), cend = cbeg + BN / 2;   // its half of the tile's columns
         int iter = 0;
         long long ew = 0; const long long et0 = clock64();
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++iter) {
+        WorkIter wi(p.streamk, p.sk_t0, tiles_mn, total_tiles, total_kb, p.kb_per_split);
+        int t, kb0, kb1; bool seg_first, seg_last;
+        for (; wi.next(t, kb0, kb1, seg_first, seg_last); ++iter) {
             const int split = t / tiles_mn;
             const int mn = t - split * tiles_mn;
             const int mt = mn / p.num_n, nt = mn - mt * p.num_n;
@@ -491,6 +587,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             const bool row_ok = row < p.M && (!p.diag64 || (row >> 6) == (long long)(n0 >> 6));
             const int ncols = p.diag64 ? 64 : p.N;
             const int c0 = p.diag64 ? 0 : n0;
+            // ---- stream-K: publish a partial segment, or collect the partials of the tile this segment finishes
+            const int r_in = q * 32 + lane;
+            int nprev = 0;
+            if (p.streamk && !seg_last) {
+                float* ws = p.partial + (size_t)blockIdx.x * BN * 128;
+                for (int c = cbeg; c < cend; c += 32) {
+                    float v[32];
+                    tmem_ld32(tacc + c, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) ws[(size_t)(c + i) * 128 + r_in] = v[i];
+                }
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) *reinterpret_cast<volatile int*>(p.sk_flags + blockIdx.x * 8 + (warp - 4)) = 1;
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[as]);
+                continue;
+            }
+            if (p.streamk && !seg_first) {
+                const long long tb = (long long)(t - p.sk_t0) * total_kb;
+                int c2 = blockIdx.x - 1;
+                while (true) { ++nprev; if (c2 <= 0 || streamk_range_start(c2, tiles_mn - p.sk_t0, total_kb, gridDim.x) <= tb) break; --c2; }
+                if (lane == 0)
+                    for (int j = 1; j <= nprev; ++j)
+                        while (*reinterpret_cast<volatile int*>(p.sk_flags + (blockIdx.x - j) * 8 + (warp - 4)) == 0) {}
+                __syncwarp();
+                __threadfence();
+            }
             if (p.split_k > 1) {
                 float* dst = p.partial + ((long long)split * p.M + row) * ncols + c0;
                 for (int c = cbeg; c < cend && n0 + c < p.N; c += 32) {
@@ -514,6 +640,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         tmem_ld32(tacc + c, v);
                         tmem_ld32(tacc + c + 32, v + 32);
                         tmem_ld_wait();
+                        if (nprev) streamk_add<64>(v, p.partial, nprev, BN, c, r_in);
                         if (row_ok) epilogue_apply<64, CLS>(v, row, n0 + c, p.N, p.e);
                     }
                 }
@@ -531,6 +658,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                             tmem_ld32(tacc + c, v);
                             tmem_ld32(tacc + c + 32, v + 32);
                             tmem_ld_wait();
+                            if (nprev) streamk_add<64>(v, p.partial, nprev, BN, c, r_in);
                             epilogue_conv_staged<64>(v, row_base, lane, p.M, n0 + c, p.e, stg);
                         }
                     } else {
@@ -538,6 +666,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                             float v[32];
                             tmem_ld32(tacc + c, v);
                             tmem_ld_wait();
+                            if (nprev) streamk_add<32>(v, p.partial, nprev, BN, c, r_in);
                             epilogue_conv_staged<32>(v, row_base, lane, p.M, n0 + c, p.e, stg);
                         }
                     }
@@ -546,6 +675,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         float v[32];
                         tmem_ld32(tacc + c, v);
                         tmem_ld_wait();
+                        if (nprev) streamk_add<32>(v, p.partial, nprev, BN, c, r_in);
                         if (row_ok) epilogue_apply<32, CLS>(v, row, c0 + c, ncols, p.e);
                     }
                 }
@@ -554,6 +684,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     float v[32];
                     tmem_ld32(tacc + c, v);
                     tmem_ld_wait();
+                    if (nprev) streamk_add<32>(v, p.partial, nprev, BN, c, r_in);
                     if (row_ok) epilogue_apply<32, CLS>(v, row, c0 + c, ncols, p.e);
                 }
             }
@@ -685,32 +816,33 @@ inline int make_operand_map(CUtensorMap* m, const bf16* base, int mn_major, long
     return encode_map(m, base, 2, dims, strides, box, estr);
 }
 
-template <int BN, int CLS>
+template <int BN, int CLS, int FUSE3 = 0>
 int launch_gemm_inst(const CUtensorMap* maps, const GemmKParams& kp, int grid, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        cudaError_t err = cudaFuncSetAttribute(gemm_tc_kernel<BN, CLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN, CLS>::SMEM_BYTES);
+        cudaError_t err = cudaFuncSetAttribute(gemm_tc_kernel<BN, CLS, FUSE3>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN, CLS, FUSE3>::SMEM_BYTES);
         if (err != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(err)); return -1; }
         configured = true;
     }
-    gemm_tc_kernel<BN, CLS><<<grid, GEMM_THREADS, GemmCfg<BN, CLS>::SMEM_BYTES, st>>>(maps[0], maps[1], maps[2], maps[3], kp);
+    gemm_tc_kernel<BN, CLS, FUSE3><<<grid, GEMM_THREADS, GemmCfg<BN, CLS, FUSE3>::SMEM_BYTES, st>>>(maps[0], maps[1], maps[2], maps[3], kp);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) { set_error("gemm launch: %s", cudaGetErrorString(err)); return -1; }
     return 0;
 }
 
 // Defined once in common.cu (explicit dispatch over the instantiated <BN, class> pairs).
-int launch_gemm_dispatch(int bn, int cls, const CUtensorMap* maps, const GemmKParams& kp, int grid, cudaStream_t st);
+int launch_gemm_dispatch(int bn, int cls, int fuse3, const CUtensorMap* maps, const GemmKParams& kp, int grid, cudaStream_t st);
 
 // The narrowest epilogue class that covers the options a launch uses.
-inline int epi_class_of(const EpiParams& e, bool split) {
+inline int epi_class_of(const EpiParams& e, bool split, bool conv_mode) {
     if (split) return EPI_F32;          // the kernel only writes partials; the reduce kernel applies the epilogue
     bool used[13] = {e.alpha != 1.0f, e.bias != nullptr, e.rowbias != nullptr, e.res_f32 != nullptr, e.res_bf != nullptr, e.save_pre != nullptr,
                      e.act == ACT_RELU, e.act == ACT_GELU, e.act == ACT_MUL_DGELU, e.act == ACT_LN64_GELU, e.out_f32 != nullptr,
                      e.out_hi != nullptr, e.out_lo != nullptr};
-    const int order[5] = {EPI_CONV, EPI_F32, EPI_GELU, EPI_DGELU, EPI_LN64};
+    const int order_conv[5] = {EPI_CONV, EPI_F32, EPI_GELU, EPI_DGELU, EPI_LN64};
+    const int order_gemm[5] = {EPI_F32, EPI_CONV, EPI_GELU, EPI_DGELU, EPI_LN64};      // plain GEMMs keep the deeper pipeline of the f32 class
     for (int k = 0; k < 5; ++k) {
-        const int cls = order[k];
+        const int cls = conv_mode ? order_conv[k] : order_gemm[k];
         bool ok = true;
         for (int o = 0; o < 13; ++o) if (used[o] && !epi_has(cls, o)) ok = false;
         if (cls == EPI_GELU && e.act != ACT_GELU) ok = false;
@@ -737,7 +869,16 @@ inline int gemm_launch(const GemmArgs& g, cudaStream_t st) {
             bn = (g.N >= 256 && t256 >= (long long)num_sms() * 2 / 3) ? 256 : 128;
         }
     }
-    if (bn != 64 && bn != 128 && bn != 256) { set_error("gemm: bad block_n %d", bn); return -1; }
+    // split-precision GEMMs may also use 192-wide tiles: for M = 3200, N = 2048 that is 275 tiles = 2 waves of 192 columns
+    // instead of 2 waves of 256 (tile time is proportional to the width)
+    static const int bn192_enabled = getenv("SQ_BN192") ? atoi(getenv("SQ_BN192")) : 1;
+    if (bn192_enabled && g.block_n == 0 && !env_bn && bn == 256 && g.nterms == 3 && !g.conv.enabled && !g.diag64 && g.split_k <= 1 &&
+        g.e.act != ACT_LN64_GELU && !g.a_koff_per_ntile && !g.b_koff_per_ntile) {
+        const long long mt = (g.M + GEMM_BM - 1) / GEMM_BM, G = num_sms();
+        auto cost = [&](int w) { const long long tiles = mt * ((g.N + w - 1) / w); return ((tiles + G - 1) / G) * w; };
+        if (cost(192) < cost(256) && epi_class_of(g.e, false, false) != EPI_GENERIC && epi_class_of(g.e, false, false) != EPI_CONV) bn = 192;
+    }
+    if (bn != 64 && bn != 128 && bn != 192 && bn != 256) { set_error("gemm: bad block_n %d", bn); return -1; }
     kp.M = g.M; kp.N = g.N;
     kp.num_m = (g.M + GEMM_BM - 1) / GEMM_BM;
     kp.num_n = (g.N + bn - 1) / bn;
@@ -788,11 +929,20 @@ inline int gemm_launch(const GemmArgs& g, cudaStream_t st) {
     if (g.nterms == 3) { if (make_operand_map(&maps[3], g.B.lo, g.B.mn_major, g.B.ld, bmn, bk, bn)) return -1; }
     else maps[3] = maps[2];
 
-    const int total_kb = kp.nk * kp.nterms;
-    int split = g.split_k > 1 ? g.split_k : 1;
-    if (split > total_kb) split = total_kb;
-    kp.kb_per_split = (total_kb + split - 1) / split;
-    split = (total_kb + kp.kb_per_split - 1) / kp.kb_per_split;
+    // fused split-precision stages (see GemmCfg): plain 3-term GEMMs with wide tiles, when the epilogue class has a fused build
+    static const int fuse_enabled = getenv("SQ_FUSE3") ? atoi(getenv("SQ_FUSE3")) : 1;
+    int fuse3 = (fuse_enabled && g.nterms == 3 && bn >= 128 && !g.conv.enabled && !g.diag64 && !g.a_koff_per_ntile && !g.b_koff_per_ntile) ? 1 : 0;
+    int total_kb = 0, split = 1, cls = EPI_GENERIC;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        total_kb = fuse3 ? kp.nk : kp.nk * kp.nterms;
+        split = g.split_k > 1 ? g.split_k : 1;
+        if (split > total_kb) split = total_kb;
+        kp.kb_per_split = (total_kb + split - 1) / split;
+        split = (total_kb + kp.kb_per_split - 1) / kp.kb_per_split;
+        cls = epi_class_of(kp.e, split > 1, g.conv.enabled != 0);
+        if (fuse3 && (cls == EPI_GENERIC || cls == EPI_CONV)) { fuse3 = 0; continue; }
+        break;
+    }
     kp.split_k = split;
     if (split > 1) {
         const size_t need = (size_t)split * g.M * (g.diag64 ? 64 : g.N) * sizeof(float);
@@ -800,10 +950,27 @@ inline int gemm_launch(const GemmArgs& g, cudaStream_t st) {
         kp.partial = g.workspace;
     }
     const long long total_tiles = (long long)kp.num_m * kp.num_n * split;
-    const int grid = (int)(total_tiles < num_sms() ? total_tiles : num_sms());
+    int grid = (int)(total_tiles < num_sms() ? total_tiles : num_sms());
+    // stream-K when whole-tile scheduling would leave the last wave mostly empty (e.g. 200 tiles on 148 SMs)
+    static const int sk_enabled = getenv("SQ_STREAMK") ? atoi(getenv("SQ_STREAMK")) : 0;   // correct but not faster yet (r01): opt-in
+    if (sk_enabled && !g.conv.enabled && !g.diag64 && split == 1 && !g.a_koff_per_ntile && !g.b_koff_per_ntile && g.workspace) {
+        const int G = num_sms();
+        const long long rounds = (total_tiles + G - 1) / G;
+        const double eff = (double)total_tiles / (double)(rounds * G);
+        const size_t need = (size_t)G * bn * 128 * 4 + (size_t)G * 8 * 4;
+        const long long t0 = (total_tiles / G) * G;                 // whole waves stay tile-scheduled
+        const long long rem = total_tiles - t0;                     // tiles of the last wave
+        // every CTA must get a non-empty share and a tile may be spread over a handful of CTAs at most
+        if (eff < 0.9 && rem > 0 && rem * (long long)total_kb >= 2LL * G && rem * 8 >= G && total_kb >= 4 && g.workspace_bytes >= need) {
+            kp.streamk = 1; kp.sk_t0 = (int)t0; kp.partial = g.workspace;
+            kp.sk_flags = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(g.workspace) + (size_t)G * bn * 128 * 4);
+            grid = G;
+            cudaMemsetAsync(kp.sk_flags, 0, (size_t)G * 8 * 4, st);
+        }
+    }
     int rc;
     gemm_timing_begin(st, 2.0 * g.M * g.N * (g.conv.enabled ? (double)kp.nk * 64 : (double)g.K) * g.nterms);
-    rc = launch_gemm_dispatch(bn, epi_class_of(kp.e, split > 1), maps, kp, grid, st);
+    rc = launch_gemm_dispatch(bn, cls, fuse3, maps, kp, grid, st);
     gemm_timing_end(st);
     if (rc) return rc;
     if (split > 1) {

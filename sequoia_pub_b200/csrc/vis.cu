@@ -79,7 +79,8 @@ static void vis_act_layout(const VisDims& d, int B, VisAct* A) {
     A->xL = take(M * D * 4);
     A->pooled = take((size_t)B * D * 4); A->hmean = take((size_t)B * 4); A->hrstd = take((size_t)B * 4);
     A->z_hi = take((size_t)B * D * 2); A->z_lo = take((size_t)B * D * 2);
-    A->splitk_bytes = (size_t)16 * 128 * (size_t)(D > HD ? D : HD) * 4;     // small-M split-K partials
+    A->splitk_bytes = (size_t)16 * 128 * (size_t)(D > HD ? D : HD) * 4;     // small-M split-K partials / stream-K partial tiles
+    if (A->splitk_bytes < ((size_t)160 * 256 * 128 * 4 + 8192)) A->splitk_bytes = (size_t)160 * 256 * 128 * 4 + 8192;
     A->splitk = take(A->splitk_bytes);
     A->total = off;
 }
@@ -94,7 +95,9 @@ static void vis_bwd_layout(const VisDims& d, int B, VisBwd* S) {
     auto take = [&](size_t bytes) { size_t o = off; off = aup(off + bytes); return o; };
     const size_t M = (size_t)B * d.N, D = d.D, HD = d.HD, W = D > HD ? D : HD;
     S->dp_hi = take((size_t)B * d.Gpad * 2); S->dp_lo = take((size_t)B * d.Gpad * 2);
-    S->splitk_bytes = (size_t)16 * 128 * W * 4; S->splitk = take(S->splitk_bytes);
+    S->splitk_bytes = (size_t)16 * 128 * W * 4;
+    if (S->splitk_bytes < ((size_t)160 * 256 * 128 * 4 + 8192)) S->splitk_bytes = (size_t)160 * 256 * 128 * 4 + 8192;
+    S->splitk = take(S->splitk_bytes);
     S->dz = take((size_t)B * D * 4); S->dpooled = take((size_t)B * D * 4);
     S->g2_f32 = take(M * D * 4); S->g2_hi = take(M * D * 2); S->g2_lo = take(M * D * 2);
     S->g1_f32 = take(M * D * 4); S->g1_hi = take(M * D * 2); S->g1_lo = take(M * D * 2);
@@ -500,6 +503,8 @@ struct GB {
     GB& akoff(int k) { g.a_koff_per_ntile = k; return *this; }
     GB& bdiag_dgrad(int map_mn, int map_k) { g.b_koff_per_ntile = 64; g.b_nadj_per_ntile = -64; g.b_map_mn = map_mn; g.b_map_k = map_k; return *this; }
     GB& diag64() { g.diag64 = 1; g.block_n = 64; return *this; }
+    // workspace for stream-K scheduling of GEMMs whose tile count does not fill whole waves
+    GB& sk(void* ws, size_t ws_bytes) { g.workspace = (float*)ws; g.workspace_bytes = ws_bytes; return *this; }
     // split-K for GEMMs with too few output tiles to occupy the machine
     GB& auto_split(void* ws, size_t ws_bytes) {
         const int bnn = g.block_n ? g.block_n : 128;
@@ -568,7 +573,7 @@ static int vis_forward(const VisDims& d, const VisLayout& P, const float* prm, c
         SQ_TRY(check_launch("vis prep"));
         // local branch, all heads: GELU(LN64(x Wf^T + bf))                       tformer_lin.py:20
         SQ_TRY(GB(M, HD, D).A(act + a.x_hi, act + a.x_lo, D).B(wh + o.wf, wl + o.wf, D).bias(prm + o.bf).ln64(prm + o.lnl_g, prm + o.lnl_b)
-                   .save_pre((float*)(act + a.fpre), HD).out_planes(act + a.loc_hi, act + a.loc_lo, HD).run(st));
+                   .save_pre((float*)(act + a.fpre), HD).out_planes(act + a.loc_hi, act + a.loc_lo, HD).sk(sk, A.splitk_bytes).run(st));
         // summary branch on the token mean: GELU(LN64(mean(x) Ws^T + bs))           tformer_lin.py:21-22
         SQ_TRY(GB(B, HD, D).A(act + a.xm_hi, act + a.xm_lo, D).B(wh + o.ws, wl + o.ws, D).bias(prm + o.bs).out_f32((float*)(act + a.spre), HD)
                    .bn(128).auto_split(sk, A.splitk_bytes).run(st));
@@ -584,18 +589,19 @@ static int vis_forward(const VisDims& d, const VisLayout& P, const float* prm, c
                    .out_planes(act + a.out_hi, act + a.out_lo, HD).run(st));
         // projection + residual                                                     tformer_lin.py:45-46,75
         SQ_TRY(GB(M, D, HD).A(act + a.out_hi, act + a.out_lo, HD).B(wh + o.wp, wl + o.wp, HD).bias(prm + o.bp).res(x, D)
-                   .out_f32((float*)(act + a.x1), D).run(st));
+                   .out_f32((float*)(act + a.x1), D).sk(sk, A.splitk_bytes).run(st));
         // feed-forward + residual                                                   tformer_lin.py:54-59,76
         ln_rows_fwd_kernel<<<M, 256, 0, st>>>((const float*)(act + a.x1), prm + o.fg, prm + o.fb, D, 1e-5f, (float*)(act + a.ln_mean),
                                               (float*)(act + a.ln_rstd), (bf16*)(act + a.h_hi), (bf16*)(act + a.h_lo));
         SQ_TRY(check_launch("vis ln"));
         SQ_TRY(GB(M, D, D).A(act + a.h_hi, act + a.h_lo, D).B(wh + o.w1, wl + o.w1, D).bias(prm + o.b1).act(ACT_GELU)
-                   .save_pre((float*)(act + a.upre), D).out_planes(act + a.u_hi, act + a.u_lo, D).run(st));
+                   .save_pre((float*)(act + a.upre), D).out_planes(act + a.u_hi, act + a.u_lo, D).sk(sk, A.splitk_bytes).run(st));
         const bool last = (l == d.L - 1);
         float* xn = (float*)(act + (last ? A.xL : A.lay[l + 1].x_f32));
         GB g2(M, D, D);
         g2.A(act + a.u_hi, act + a.u_lo, D).B(wh + o.w2, wl + o.w2, D).bias(prm + o.b2).res((const float*)(act + a.x1), D).out_f32(xn, D);
         if (!last) g2.out_planes(act + A.lay[l + 1].x_hi, act + A.lay[l + 1].x_lo, D);
+        g2.sk(sk, A.splitk_bytes);
         SQ_TRY(g2.run(st));
     }
     // token mean, head LayerNorm, gene regression head                              tformer_lin.py:103-106
@@ -603,7 +609,7 @@ static int vis_forward(const VisDims& d, const VisLayout& P, const float* prm, c
     ln_rows_fwd_kernel<<<B, 256, 0, st>>>((const float*)(act + A.pooled), prm + P.hg, prm + P.hb, D, 1e-5f, (float*)(act + A.hmean),
                                           (float*)(act + A.hrstd), (bf16*)(act + A.z_hi), (bf16*)(act + A.z_lo));
     SQ_TRY(check_launch("vis head ln"));
-    SQ_TRY(GB(B, d.G, D).A(act + A.z_hi, act + A.z_lo, D).B(wh + P.wh, wl + P.wh, D).bias(prm + P.bh).out_f32(pred, d.G).run(st));
+    SQ_TRY(GB(B, d.G, D).A(act + A.z_hi, act + A.z_lo, D).B(wh + P.wh, wl + P.wh, D).bias(prm + P.bh).out_f32(pred, d.G).sk(sk, A.splitk_bytes).run(st));
     return 0;
 }
 
@@ -613,7 +619,7 @@ static int vis_backward_head(const VisDims& d, const VisLayout& P, const float* 
     const int D = d.D, N = d.N, G = d.G;
     SQ_TRY(split_planes(dpred, (bf16*)(sc + S.dp_hi), (bf16*)(sc + S.dp_lo), B, G, G, d.Gpad, st));
     // dWh = dpred^T z ; dbh = colsum(dpred)
-    SQ_TRY(GB(G, D, B).A(sc + S.dp_hi, sc + S.dp_lo, d.Gpad, 1).B(act + A.z_hi, act + A.z_lo, D, 1).out_f32(grads + P.wh, D).run(st));
+    SQ_TRY(GB(G, D, B).A(sc + S.dp_hi, sc + S.dp_lo, d.Gpad, 1).B(act + A.z_hi, act + A.z_lo, D, 1).out_f32(grads + P.wh, D).sk(sc + S.splitk, S.splitk_bytes).run(st));
     colsum_kernel<<<(G + 31) / 32, 256, 0, st>>>(dpred, B, G, G, 1.0f, grads + P.bh);
     // dz = dpred Wh
     SQ_TRY(GB(B, D, G).A(sc + S.dp_hi, sc + S.dp_lo, d.Gpad).B(wh + P.wh, wl + P.wh, D, 1).out_f32((float*)(sc + S.dz), D)
@@ -635,19 +641,19 @@ static int vis_backward_layer(const VisDims& d, const VisLayout& P, int l, const
     float* part = (float*)(sc + S.part);
     // ---- feed-forward (x2 = W2 GELU(W1 LN(x1) + b1) + b2 + x1)
     SQ_TRY(GB(M, D, D).A(sc + S.g2_hi, sc + S.g2_lo, D).B(wh + o.w2, wl + o.w2, D, 1).dgelu((const float*)(act + a.upre), D)
-               .out_planes(sc + S.du_hi, sc + S.du_lo, D).run(st));
-    SQ_TRY(GB(D, D, M).A(sc + S.g2_hi, sc + S.g2_lo, D, 1).B(act + a.u_hi, act + a.u_lo, D, 1).out_f32(grads + o.w2, D).run(st));
+               .out_planes(sc + S.du_hi, sc + S.du_lo, D).sk(sc + S.splitk, S.splitk_bytes).run(st));
+    SQ_TRY(GB(D, D, M).A(sc + S.g2_hi, sc + S.g2_lo, D, 1).B(act + a.u_hi, act + a.u_lo, D, 1).out_f32(grads + o.w2, D).sk(sc + S.splitk, S.splitk_bytes).run(st));
     SQ_TRY(launch_bias_grad((bf16*)(sc + S.g2_hi), (bf16*)(sc + S.g2_lo), B, N, D, gsum, grads + o.b2, st));
-    SQ_TRY(GB(M, D, D).A(sc + S.du_hi, sc + S.du_lo, D).B(wh + o.w1, wl + o.w1, D, 1).out_f32((float*)(sc + S.dh), D).run(st));
-    SQ_TRY(GB(D, D, M).A(sc + S.du_hi, sc + S.du_lo, D, 1).B(act + a.h_hi, act + a.h_lo, D, 1).out_f32(grads + o.w1, D).run(st));
+    SQ_TRY(GB(M, D, D).A(sc + S.du_hi, sc + S.du_lo, D).B(wh + o.w1, wl + o.w1, D, 1).out_f32((float*)(sc + S.dh), D).sk(sc + S.splitk, S.splitk_bytes).run(st));
+    SQ_TRY(GB(D, D, M).A(sc + S.du_hi, sc + S.du_lo, D, 1).B(act + a.h_hi, act + a.h_lo, D, 1).out_f32(grads + o.w1, D).sk(sc + S.splitk, S.splitk_bytes).run(st));
     SQ_TRY(launch_bias_grad((bf16*)(sc + S.du_hi), (bf16*)(sc + S.du_lo), B, N, D, gsum, grads + o.b1, st));
     SQ_TRY(launch_ln_rows_bwd((const float*)(sc + S.dh), (const float*)(act + a.x1), (const float*)(act + a.ln_mean), (const float*)(act + a.ln_rstd),
                               prm + o.fg, (const float*)(sc + S.g2_f32), M, D, (float*)(sc + S.g1_f32), (bf16*)(sc + S.g1_hi), (bf16*)(sc + S.g1_lo),
                               part, grads + o.fg, st));
     // ---- mixer (x1 = Wp out + bp + x)
     SQ_TRY(GB(M, HD, D).A(sc + S.g1_hi, sc + S.g1_lo, D).B(wh + o.wp, wl + o.wp, HD, 1).dgelu((const float*)(act + a.cpre), HD)
-               .out_planes(sc + S.dc_hi, sc + S.dc_lo, HD).run(st));
-    SQ_TRY(GB(D, HD, M).A(sc + S.g1_hi, sc + S.g1_lo, D, 1).B(act + a.out_hi, act + a.out_lo, HD, 1).out_f32(grads + o.wp, HD).run(st));
+               .out_planes(sc + S.dc_hi, sc + S.dc_lo, HD).sk(sc + S.splitk, S.splitk_bytes).run(st));
+    SQ_TRY(GB(D, HD, M).A(sc + S.g1_hi, sc + S.g1_lo, D, 1).B(act + a.out_hi, act + a.out_lo, HD, 1).out_f32(grads + o.wp, HD).sk(sc + S.splitk, S.splitk_bytes).run(st));
     SQ_TRY(launch_bias_grad((bf16*)(sc + S.g1_hi), (bf16*)(sc + S.g1_lo), B, N, D, gsum, grads + o.bp, st));
     // dlocal = dCpre Wc[:, :64] per head ; dWc[:, :64] = dCpre^T local per head
     SQ_TRY(GB(M, HD, 64).A(sc + S.dc_hi, sc + S.dc_lo, HD).akoff(64).B(wh + o.wc, wl + o.wc, 128, 1).bdiag_dgrad(64, HD).bn(64)
@@ -673,13 +679,14 @@ static int vis_backward_layer(const VisDims& d, const VisLayout& P, int l, const
     SQ_TRY(GB(B, D, HD).A(sc + S.ds_hi, sc + S.ds_lo, HD).B(wh + o.ws, wl + o.ws, D, 1).alpha(1.0f / (float)N).out_f32((float*)(sc + S.dxm), D)
                .auto_split(sc + S.splitk, S.splitk_bytes).run(st));
     // local branch weights and the gradient w.r.t. the layer input
-    SQ_TRY(GB(HD, D, M).A(sc + S.df_hi, sc + S.df_lo, HD, 1).B(act + a.x_hi, act + a.x_lo, D, 1).out_f32(grads + o.wf, D).run(st));
+    SQ_TRY(GB(HD, D, M).A(sc + S.df_hi, sc + S.df_lo, HD, 1).B(act + a.x_hi, act + a.x_lo, D, 1).out_f32(grads + o.wf, D).sk(sc + S.splitk, S.splitk_bytes).run(st));
     SQ_TRY(launch_bias_grad((bf16*)(sc + S.df_hi), (bf16*)(sc + S.df_lo), B, N, HD, gsum, grads + o.bf, st));
     float* gout = (l == 0 && dx_out) ? dx_out : (float*)(sc + S.g2_f32);
     GB gx(M, D, HD);
     gx.A(sc + S.df_hi, sc + S.df_lo, HD).B(wh + o.wf, wl + o.wf, D, 1).res((const float*)(sc + S.g1_f32), D)
         .rowbias((const float*)(sc + S.dxm), N, D).out_f32(gout, D);
     if (l > 0) gx.out_planes(sc + S.g2_hi, sc + S.g2_lo, D);
+    gx.sk(sc + S.splitk, S.splitk_bytes);
     SQ_TRY(gx.run(st));
     if (l == 0) {
         pos_grad_kernel<<<(int)(((long long)N * D / 4 + 255) / 256), 256, 0, st>>>(gout, B, N, D, grads + P.pos);

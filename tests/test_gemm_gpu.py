@@ -226,3 +226,50 @@ def test_block_diagonal_backward_modes():
     ref = torch.einsum("mhj,mhi->hji", dC.double().view(M, H, d), local.double().view(M, H, d)).reshape(H * d, d)
     assert _rel(dW[:, :64], ref) < 2e-5
     assert torch.isnan(dW[:, 64:]).all()                      # the other half of c.weight's gradient is untouched
+
+
+@pytest.mark.parametrize("case", [(3200, 2048, 2048, 3, False, False, 0), (3200, 2048, 2048, 3, True, True, 0), (1000, 1024, 1536, 1, False, False, 0),
+                                  (3200, 1024, 2048, 3, False, False, 128), (2500, 2304, 1024, 1, False, True, 256), (32, 20530, 2048, 3, False, False, 0)])
+def test_stream_k_scheduling(case):
+    """GEMMs whose tile count leaves the last wave mostly empty are scheduled stream-K (equal k-block shares per CTA,
+    partial tiles exchanged through the workspace); results must not depend on it."""
+    gm = _mods()
+    M, N, K, nt, a_mn, b_mn, bn = case
+    A = _mk(M, K, 31); B = _mk(N, K, 32)
+    As, Bs = _store(A, a_mn), _store(B, b_mn)
+    a_hi, a_lo = gm.split_planes(As); b_hi, b_lo = gm.split_planes(Bs)
+    ws = torch.empty(160 * 256 * 128 + 4096, dtype=torch.float32, device="cuda")
+    bias = torch.randn(N, device="cuda")
+    ldc = (N + 3) // 4 * 4
+    out = torch.full((M, ldc), float("nan"), device="cuda")[:, :N]
+    ref_out = torch.full((M, ldc), float("nan"), device="cuda")[:, :N]
+    kw = dict(a_mn=a_mn, b_mn=b_mn, nterms=nt, bias=bias, act="gelu", block_n=bn)
+    gm.gemm(M, N, K, a_hi, b_hi, a_lo if nt == 3 else None, b_lo if nt == 3 else None, out_f32=out, workspace=ws, **kw)
+    gm.gemm(M, N, K, a_hi, b_hi, a_lo if nt == 3 else None, b_lo if nt == 3 else None, out_f32=ref_out, **kw)      # classic scheduling
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all()
+    if nt == 3:
+        ref = F.gelu(A.double() @ B.double().t() + bias.double())
+        assert _rel(out, ref) < 2e-5
+    assert _rel(out, ref_out) < 5e-6          # same products, different (fixed) fp32 summation grouping
+    again = torch.empty_like(out)
+    gm.gemm(M, N, K, a_hi, b_hi, a_lo if nt == 3 else None, b_lo if nt == 3 else None, out_f32=again, workspace=ws, **kw)
+    torch.cuda.synchronize()
+    assert torch.equal(again, out)            # deterministic
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True)])
+def test_split3_auto_tile_width_192(a_mn, b_mn):
+    """M=3200, N=2048 picks 192-wide tiles (275 tiles = 2 waves on 148 SMs); last n-tile is 128 columns wide."""
+    gm = _mods()
+    M, N, K = 3200, 2048, 1024
+    A = _mk(M, K, 41); B = _mk(N, K, 42)
+    As, Bs = _store(A, a_mn), _store(B, b_mn)
+    a_hi, a_lo = gm.split_planes(As); b_hi, b_lo = gm.split_planes(Bs)
+    bias = torch.randn(N, device="cuda"); res = torch.randn(M, N, device="cuda")
+    out = torch.full((M, N), float("nan"), device="cuda"); ohi = torch.empty(M, N, device="cuda", dtype=torch.bfloat16); olo = torch.empty_like(ohi)
+    gm.gemm(M, N, K, a_hi, b_hi, a_lo, b_lo, a_mn=a_mn, b_mn=b_mn, nterms=3, out_f32=out, out_hi=ohi, out_lo=olo, bias=bias, res_f32=res)
+    torch.cuda.synchronize()
+    ref = A.double() @ B.double().t() + bias.double() + res.double()
+    assert _rel(out, ref) < 2e-5
+    assert _rel(ohi.float() + olo.float(), out) < 1e-4
