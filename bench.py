@@ -254,6 +254,61 @@ def bench_vis(args, dev, rank, world, timed, pk):
     return out
 
 
+UNI_BATCH, UNI_PATCHES = 64, 1024
+UNI_FLOP_PER_PATCH = 123.107e9
+UNI_WORKLOAD = "UNI ViT-L/16 extraction: 1024 synthetic 224x224x3 uint8 patches per rank per step, batch 64 (BASELINE configs[3] shape, slide-sharded)"
+
+
+def bench_uni(args, dev, rank, world, timed, pk):
+    """patches/s of the UNI ViT-L/16 extractor (parity unpinned: no timm / UNI weights offline; see oracle/uni_oracle.py)."""
+    import torch
+    from oracle import uni_oracle as U
+    from sequoia_pub_b200 import _lib
+    from sequoia_pub_b200.uni import VisionTransformer
+    L = _lib.lib()
+    m = VisionTransformer().eval()
+    m.load_state_dict(U.make_state_dict(0))
+    m = m.to(dev)
+    g = torch.Generator(device=dev).manual_seed(2000 + rank)
+    tiles = torch.randint(0, 256, (UNI_PATCHES, 224, 224, 3), generator=g, dtype=torch.uint8, device=dev)     # 154 MB > L2
+    host = torch.empty(tiles.shape, dtype=torch.uint8).pin_memory()
+    host.copy_(tiles)
+    feats = torch.empty(UNI_PATCHES, 1024, dtype=torch.float32, device=dev)
+    stage = torch.empty(UNI_BATCH, 224, 224, 3, dtype=torch.uint8, device=dev)
+    out_h = torch.empty(UNI_PATCHES, 1024, dtype=torch.float32).pin_memory()
+
+    def step_dev():
+        for b in range(0, UNI_PATCHES, UNI_BATCH):
+            m.extract_uint8(tiles[b:b + UNI_BATCH], out=feats[b:b + UNI_BATCH])
+
+    def step_e2e():
+        for b in range(0, UNI_PATCHES, UNI_BATCH):
+            stage.copy_(host[b:b + UNI_BATCH], non_blocking=True)
+            m.extract_uint8(stage, out=feats[b:b + UNI_BATCH])
+        out_h.copy_(feats, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(2):
+        step_dev()
+    steps = 3
+    ms = timed(step_dev, steps) / steps
+    step_e2e()
+    e2e_ms = timed(step_e2e, steps) / steps
+    out = {"value": world * UNI_PATCHES / (ms * 1e-3), "unit": "patches/s", "ms_per_step": ms, "dtype": "bf16",
+           "config": {"workload": UNI_WORKLOAD, "parity": "unpinned (restatement of timm's forward)"},
+           "e2e": {"value": world * UNI_PATCHES / (e2e_ms * 1e-3), "unit": "patches/s", "ms_per_step": e2e_ms,
+                   "h2d_bytes_per_step": host.numel(), "d2h_bytes_per_step": out_h.numel() * 4}}
+    if rank == 0:
+        tms, n, fl = gemm_timing(L, _lib, step_dev)
+        ach = UNI_FLOP_PER_PATCH * UNI_PATCHES / (tms * 1e-3) / 1e12
+        out["roofline"] = {"bound": "tensor", "kernel": "gemm_tc_kernel (qkv / proj / fc1 / fc2 / patch-embed GEMMs)", "achieved": ach,
+                           "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_sustained"], "traffic": None, "launches": n,
+                           "kernel_share_of_step": tms / ms}
+    del m, tiles, host, feats
+    torch.cuda.empty_cache()
+    return out
+
+
 def bench_kmeans(args, dev, rank, world, pk):
     """slides/s of the per-slide k-means reduction (independent slides per rank, no collective)."""
     import torch
@@ -291,7 +346,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=256, help="patches timed on the CPU baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--only", default="", help="comma list of {resnet,vis,kmeans}: skip the others (debugging)")
+    ap.add_argument("--only", default="", help="comma list of {vis,kmeans,uni}: run only these extra legs (debugging)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -384,6 +439,7 @@ def main():
 
     vis = bench_vis(args, dev, rank, world, timed, pk) if (not only or "vis" in only) else None
     kmn = bench_kmeans(args, dev, rank, world, pk) if (not only or "kmeans" in only) else None
+    uni = bench_uni(args, dev, rank, world, timed, pk) if (not only or "uni" in only) else None
 
     if rank != 0:
         if world > 1:
@@ -411,7 +467,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "patches/s", "h2d_bytes_per_step": ex_h2d // e2e_steps,
                     "d2h_bytes_per_step": ex_d2h // e2e_steps, "ms_per_step": e2e_ms},
             "gpu_launches": launches_per_step * args.steps,
-            "roofline": roof, "cpu_baseline": cpu, "vis_train": vis, "kmeans": kmn}
+            "roofline": roof, "cpu_baseline": cpu, "vis_train": vis, "kmeans": kmn, "uni_extract": uni}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
