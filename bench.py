@@ -172,7 +172,7 @@ def run_reference(args):
             "vis_train": {"value": vr, "unit": "slides/s", "cpu_baseline": {"value": vr, "unit": "slides/s", "cores": vc, "kind": "port", "sample": vs}},
             "kmeans": {"value": kr, "unit": "slides/s", "cpu_baseline": {"value": kr, "unit": "slides/s", "cores": kc, "kind": "reference", "sample": ks}},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 def gemm_timing(L, _lib, fn):
@@ -338,7 +338,16 @@ def bench_kmeans(args, dev, rank, world, pk):
                          "label parity with scikit-learn is the gate (SURVEY §8d)", "achieved": None, "peak": None, "frac": None, "traffic": None}}
 
 
+def emit(line):
+    """Prints the ONE JSON line on the real stdout (libraries such as NCCL write banners to fd 1, which is redirected to stderr)."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = os.dup(1)
+
+
 def main():
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -468,7 +477,7 @@ def main():
                     "d2h_bytes_per_step": ex_d2h // e2e_steps, "ms_per_step": e2e_ms},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": roof, "cpu_baseline": cpu, "vis_train": vis, "kmeans": kmn, "uni_extract": uni}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 

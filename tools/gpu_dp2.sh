@@ -1,7 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
 nvidia-smi -L
-timeout 200 python -m pytest tests/test_dp_gpu.py -m gpu -q -s 2>&1 | tail -5
+
 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 3 --warmup 3 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err; echo "rc=$?"; tail -3 gpurun_out/bench_n2.err
 python - <<'PY'
 import json
