@@ -175,6 +175,15 @@ def run_reference(args):
     emit(line)
 
 
+def ncu_traffic(key):
+    """DRAM bytes per launch of gemm_tc_kernel from the committed ncu capture (tools/gpu_traffic.sh -> profiles/r01_traffic.json)."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        return json.load(open(p))[key]["traffic_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 def gemm_timing(L, _lib, fn):
     """Runs fn() once with CUDA events around every tcgen05 GEMM launch; returns (total ms, launches, issued MMA flops)."""
     import ctypes as C
@@ -246,7 +255,7 @@ def bench_vis(args, dev, rank, world, timed, pk):
         out["roofline"] = {"bound": "tensor", "kernel": "gemm_tc_kernel (split-precision GEMMs of the step, fused epilogues)",
                            "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_sustained"],
                            "peak_source": pk["source"] + " bf16 sustained; the path issues 3 bf16 MMAs per algorithmic MAC to keep fp32 parity, "
-                           "so 1/3 is the ceiling of this fraction", "traffic": None, "launches": n,
+                           "so 1/3 is the ceiling of this fraction", "traffic": ncu_traffic("vis"), "launches": n,
                            "avg_launch_us": tms * 1e3 / max(n, 1), "kernel_share_of_step": tms / ms,
                            "issued_mma_tflops": fl / (tms * 1e-3) / 1e12, "issued_frac_of_peak": fl / (tms * 1e-3) / 1e12 / pk["bf16_sustained"]}
     del tr, model
@@ -438,7 +447,8 @@ def main():
         achieved = alg_flops / (tms * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (implicit-GEMM conv, bf16 -> fp32 TMEM)",
                 "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
-                "peak_source": pk["source"] + " bf16 sustained", "traffic": None,
+                "peak_source": pk["source"] + " bf16 sustained", "traffic": ncu_traffic("resnet"),
+                "traffic_note": "dram read+write bytes per launch, mean over the 53 launches of one batch (ncu, profiles/r01_traffic.json)",
                 "launches": n, "avg_launch_us": tms * 1e3 / max(n, 1),
                 "kernel_share_of_step": tms / ms_per_step,
                 "issued_mma_tflops": fl / (tms * 1e-3) / 1e12}

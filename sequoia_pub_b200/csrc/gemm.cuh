@@ -453,10 +453,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     if (p.BIMG == 1) { img = mt / p.tiles_per_img; hin0 = (mt - img * p.tiles_per_img) * p.BH * p.stride - p.pad; }
                     else { img = mt * p.BIMG; hin0 = -p.pad; }
                 }
+                // running (k-block, term) and (filter row, filter column, channel block) counters: no divisions in the loop
+                int kk = FUSE3 ? kb0 : kb0 / p.nterms, term = FUSE3 ? 0 : kb0 - kk * p.nterms;
+                int tap_r = 0, tap_s = 0, cb = 0;
+                if (p.conv) { const int tap = kk / p.cblocks; cb = kk - tap * p.cblocks; tap_r = tap / p.S; tap_s = tap - tap_r * p.S; }
+                const bool prof_on = p.prof != nullptr;
                 for (int kb = kb0; kb < kb1; ++kb) {
-                    const long long w0 = clock64();
-                    mbar_wait(&empty[stage], phase ^ 1);
-                    pw += clock64() - w0;
+                    if (prof_on) {
+                        const long long w0 = clock64();
+                        mbar_wait(&empty[stage], phase ^ 1);
+                        pw += clock64() - w0;
+                    } else {
+                        mbar_wait(&empty[stage], phase ^ 1);
+                    }
                     mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
                     uint8_t* sbase = smem + stage * Cfg::STAGE_BYTES;
                     if constexpr (FUSE3) {
@@ -481,16 +490,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                             tma_load_2d(&mapB1, &full[stage], sbase + OFF_BLO, k0, n0);
                         }
                     } else {
-                    const int kk = kb / p.nterms, term = kb - kk * p.nterms;
                     const CUtensorMap* ma = (term == 2) ? &mapA1 : &mapA0;
                     const CUtensorMap* mb = (term == 1) ? &mapB1 : &mapB0;
                     uint8_t* sa = sbase;
                     uint8_t* sb = sbase + OFF_B;
                     const int k0 = kk * GEMM_BK;
                     if (p.conv) {
-                        const int tap = kk / p.cblocks, cb = kk - tap * p.cblocks;
-                        const int r = tap / p.S, s = tap - r * p.S;
-                        tma_load_4d(ma, &full[stage], sa, cb * GEMM_BK, s - p.pad, hin0 + r, img);
+                        tma_load_4d(ma, &full[stage], sa, cb * GEMM_BK, tap_s - p.pad, hin0 + tap_r, img);
                     } else if (p.a_mn) {
                         tma_load_2d(ma, &full[stage], sa, m0, k0);
                         tma_load_2d(ma, &full[stage], sa + 8192, m0 + 64, k0);
@@ -502,6 +508,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         for (int a = 0; a < BN / 64; ++a) tma_load_2d(mb, &full[stage], sb + a * 8192, bn0 + a * 64, k0 + bkoff);
                     } else {
                         tma_load_2d(mb, &full[stage], sb, k0 + bkoff, bn0);
+                    }
+                    if (++term == p.nterms) {
+                        term = 0; ++kk;
+                        if (p.conv && ++cb == p.cblocks) { cb = 0; if (++tap_s == p.S) { tap_s = 0; ++tap_r; } }
                     }
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
