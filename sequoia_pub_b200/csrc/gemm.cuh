@@ -780,6 +780,7 @@ struct GemmArgs {
     int b_koff_per_ntile, b_nadj_per_ntile;   // block-diagonal dgrad (see GemmKParams)
     int b_map_mn, b_map_k;   // explicit extents of B's tensor map (0 = N / K)
     int diag64;              // block-diagonal wgrad
+    int epi_conv_pref;       // prefer the coalesced convolution epilogue class even for a plain GEMM (1x1 convolutions)
     int block_n;             // 0 = auto
     ConvGeom conv;
     float* workspace; size_t workspace_bytes;   // for split-K partials
@@ -949,7 +950,7 @@ inline int gemm_launch(const GemmArgs& g, cudaStream_t st) {
         if (split > total_kb) split = total_kb;
         kp.kb_per_split = (total_kb + split - 1) / split;
         split = (total_kb + kp.kb_per_split - 1) / kp.kb_per_split;
-        cls = epi_class_of(kp.e, split > 1, g.conv.enabled != 0);
+        cls = epi_class_of(kp.e, split > 1, g.conv.enabled != 0 || g.epi_conv_pref != 0);
         if (fuse3 && (cls == EPI_GENERIC || cls == EPI_CONV)) { fuse3 = 0; continue; }
         break;
     }

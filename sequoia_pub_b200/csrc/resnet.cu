@@ -183,7 +183,9 @@ static int run_conv(const ConvSpec& c, const bf16* wbase, const float* sbase, co
     g.A.hi = in; g.A.ld = c.cin;
     g.B.hi = wbase + c.w_off; g.B.ld = g.K;
     g.nterms = 1;
-    g.conv.enabled = 1; g.conv.batch = batch; g.conv.H = H; g.conv.W = W; g.conv.C = c.cin; g.conv.Ho = Ho; g.conv.Wo = Wo;
+    // 1x1 stride-1 convolutions are plain GEMMs over [pixels, Cin] (2-D tensor maps: cheaper to issue than 4-D boxes)
+    g.epi_conv_pref = 1;
+    g.conv.enabled = (c.k == 1 && c.stride == 1) ? 0 : 1; g.conv.batch = batch; g.conv.H = H; g.conv.W = W; g.conv.C = c.cin; g.conv.Ho = Ho; g.conv.Wo = Wo;
     g.conv.R = c.k; g.conv.S = c.k; g.conv.stride = c.stride; g.conv.pad = c.pad;
     g.e.bias = sbase + c.s_off;
     g.e.out_hi = out_bf; g.e.ld_bf = c.cout;
