@@ -158,6 +158,15 @@ SQ_API int sq_mse_fwd_bwd(const float* pred, const float* target, int batch, int
 SQ_API int sq_adamw_flat(float* p, const float* g, float* m, float* v, void* p_hi, void* p_lo, long long n, float lr, float beta1,
                          float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream);
 
+/* ------------------------------------------------------------------ per-step training metrics
+ * Replaces sklearn mean_absolute_error + he2rna.compute_correlations of the training loop (src/vit.py:167-168,
+ * src/he2rna.py:140-149).  labels, preds: fp32 [batch, num_outputs] (device).  out3 (device): {mean absolute error,
+ * mean over genes of the Pearson correlation (genes with constant labels skipped, NaN correlations dropped),
+ * number of genes that entered the mean}. */
+SQ_API size_t sq_step_metrics_scratch_bytes(int num_outputs);
+SQ_API int sq_step_metrics(const float* labels, const float* preds, int batch, int num_outputs, float* out3, void* scratch,
+                           size_t scratch_bytes, void* stream);
+
 /* ------------------------------------------------------------------ UNI ViT-L/16 feature extractor
  * Replaces the timm model of pre_processing/compute_features_hdf5.py:63-66 and its call `model(image[None,:])` (:128) plus
  * the ToTensor/Normalize preprocessing (:53-56).  `tensors`: HOST array of sq_vitl16_num_tensors(depth) DEVICE pointers in

@@ -71,6 +71,8 @@ SIGNATURES = {
     "sq_mse_fwd_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "sq_adamw_flat": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_float, c_float, c_float,
                               c_float, c_float, c_int, c_float, c_void_p]),
+    "sq_step_metrics_scratch_bytes": (c_size_t, [c_int]),
+    "sq_step_metrics": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "sq_vitl16_num_tensors": (c_int, [c_int]),
     "sq_vitl16_packed_weight_elems": (c_ll, [c_int]),
     "sq_vitl16_packed_vec_elems": (c_ll, [c_int]),

@@ -128,6 +128,26 @@ def gen_kmeans():
     np.savez_compressed(os.path.join(HERE, "kmeans_golden.npz"), **out)
 
 
+def gen_metrics():
+    """The reference's own compute_correlations (src/he2rna.py:140-149), extracted with ast (the module imports tkinter),
+    and sklearn's mean_absolute_error (src/vit.py:167) on synthetic batches."""
+    import ast
+    from sklearn.metrics import mean_absolute_error
+    from oracle import metrics_oracle as MO
+    src = open("/root/reference/src/he2rna.py").read()
+    fn = [n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "compute_correlations"][0]
+    ns = {"np": np}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "he2rna.py", "exec"), ns)
+    out = {}
+    for tag, seed, b, g in (("cfg3", 0, 32, 20530), ("small", 1, 5, 301), ("b2", 2, 2, 64)):
+        y, p = MO.make_batch(seed, b, g)
+        out[f"{tag}_corr"] = np.array(ns["compute_correlations"](y, p))
+        out[f"{tag}_mae"] = np.array(mean_absolute_error(y, p))
+        assert abs(MO.compute_correlations(y, p) - out[f"{tag}_corr"]) < 1e-12
+        print("metrics golden", tag, float(out[f"{tag}_corr"]), float(out[f"{tag}_mae"]))
+    np.savez_compressed(os.path.join(HERE, "metrics_golden.npz"), **out)
+
+
 if __name__ == "__main__":
     what = sys.argv[1:] or ["resnet", "vis", "kmeans"]
     for w in what:
