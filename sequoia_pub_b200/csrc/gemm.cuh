@@ -83,7 +83,7 @@ enum EpiClass {
 __host__ __device__ constexpr bool epi_has(int cls, int opt) {
     // opt: 0 alpha, 1 bias, 2 rowbias, 3 res_f32, 4 res_bf, 5 save_pre, 6 relu, 7 gelu, 8 dgelu, 9 ln64, 10 out_f32, 11 out_bf, 12 out_lo
     return cls == EPI_GENERIC ? true
-         : cls == EPI_CONV ? (opt == 1 || opt == 4 || opt == 6 || opt == 10 || opt == 11)
+         : cls == EPI_CONV ? (opt == 1 || opt == 4 || opt == 6 || opt == 7 || opt == 10 || opt == 11)
          : cls == EPI_F32 ? (opt == 0 || opt == 1 || opt == 2 || opt == 3 || opt == 10 || opt == 11 || opt == 12)
          : cls == EPI_GELU ? (opt == 1 || opt == 2 || opt == 5 || opt == 7 || opt == 10 || opt == 11 || opt == 12)
          : cls == EPI_DGELU ? (opt == 0 || opt == 8 || opt == 10 || opt == 11 || opt == 12)
@@ -106,7 +106,7 @@ __device__ __forceinline__ void epilogue_apply(float* v, long long row, int col0
     if constexpr (!epi_has(CLS, 11)) e.out_hi = nullptr;
     if constexpr (!epi_has(CLS, 12)) e.out_lo = nullptr;
     if constexpr (CLS != EPI_GENERIC) {
-        if constexpr (CLS == EPI_CONV) e.act = (e.act == ACT_RELU) ? ACT_RELU : ACT_NONE;
+        if constexpr (CLS == EPI_CONV) e.act = (e.act == ACT_RELU || e.act == ACT_GELU) ? e.act : ACT_NONE;
         else if constexpr (CLS == EPI_F32) e.act = ACT_NONE;
         else if constexpr (CLS == EPI_GELU) e.act = ACT_GELU;
         else if constexpr (CLS == EPI_DGELU) e.act = ACT_MUL_DGELU;
@@ -296,6 +296,9 @@ __device__ __forceinline__ void epilogue_conv_staged(float* v, long long row_bas
     if (e.act == ACT_RELU) {
 #pragma unroll
         for (int i = 0; i < NC; ++i) v[i] = fmaxf(v[i], 0.0f);
+    } else if (e.act == ACT_GELU) {
+#pragma unroll
+        for (int i = 0; i < NC; ++i) v[i] = gelu_f(v[i]);
     }
     if (e.out_hi) {
 #pragma unroll
@@ -856,6 +859,7 @@ inline int epi_class_of(const EpiParams& e, bool split, bool conv_mode) {
         const int cls = conv_mode ? order_conv[k] : order_gemm[k];
         bool ok = true;
         for (int o = 0; o < 13; ++o) if (used[o] && !epi_has(cls, o)) ok = false;
+        if (cls == EPI_CONV && e.act == ACT_GELU && !conv_mode) ok = false;     // plain GEMMs keep the GELU class unless asked
         if (cls == EPI_GELU && e.act != ACT_GELU) ok = false;
         if (cls == EPI_DGELU && e.act != ACT_MUL_DGELU) ok = false;
         if (cls == EPI_LN64 && e.act != ACT_LN64_GELU) ok = false;

@@ -246,6 +246,7 @@ static int uni_gemm(int M, int N, int K, const bf16* a, const bf16* w, const flo
     g.A.hi = a; g.A.ld = K; g.B.hi = w; g.B.ld = K;
     g.e.bias = bias; g.e.res_f32 = res; g.e.ld_res = N; g.e.out_f32 = out_f32; g.e.ld_f32 = N; g.e.out_hi = out_bf; g.e.ld_bf = N;
     g.e.act = act; g.e.alpha = 1.0f; g.e.rowbias_div = 1;
+    g.epi_conv_pref = out_bf != nullptr;       // bf16 outputs go through the coalesced (staged) epilogue
     return gemm_launch(g, st);
 }
 
