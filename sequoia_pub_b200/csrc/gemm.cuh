@@ -419,6 +419,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
+    // Programmatic dependent launch: let the next kernel of the stream become resident as soon as SMs free up, and run this
+    // kernel's own prologue (barrier init, TMEM allocation, descriptor prefetch) while the previous kernel is still draining.
+    asm volatile("griddepcontrol.launch_dependents;");
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&mapA0); tma_prefetch_desc(&mapA1);
         tma_prefetch_desc(&mapB0); tma_prefetch_desc(&mapB1);
@@ -433,6 +436,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    // everything below reads or writes global memory produced by earlier kernels of the stream
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     const int tiles_mn = p.num_m * p.num_n;
     const int total_tiles = tiles_mn * p.split_k;
@@ -838,8 +843,16 @@ int launch_gemm_inst(const CUtensorMap* maps, const GemmKParams& kp, int grid, c
         if (err != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(err)); return -1; }
         configured = true;
     }
-    gemm_tc_kernel<BN, CLS, FUSE3><<<grid, GEMM_THREADS, GemmCfg<BN, CLS, FUSE3>::SMEM_BYTES, st>>>(maps[0], maps[1], maps[2], maps[3], kp);
-    cudaError_t err = cudaGetLastError();
+    static const int pdl = getenv("SQ_PDL") ? atoi(getenv("SQ_PDL")) : 1;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = GemmCfg<BN, CLS, FUSE3>::SMEM_BYTES; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    cudaError_t err = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CLS, FUSE3>, maps[0], maps[1], maps[2], maps[3], kp);
+    if (err == cudaSuccess) err = cudaGetLastError();
     if (err != cudaSuccess) { set_error("gemm launch: %s", cudaGetErrorString(err)); return -1; }
     return 0;
 }
