@@ -60,7 +60,11 @@ __global__ void fold_bn_kernel(const float* __restrict__ w, const float* __restr
         const int o = (int)(i / row); const int j = (int)(i - (long long)o * row);
         const float sc = gamma[o] / sqrtf(var[o] + eps);
         float v = 0.f;
-        if (j < kk) {
+        if (kpad) {
+            // stem: K index = r * 24 + (s * 3 + c), 21 taps per filter row padded to 24 (keeps the im2col rows 4-byte aligned)
+            const int r = j / 24, q = j - r * 24;
+            if (r < k && q < k * cin) { const int s = q / cin, c = q - s * cin; v = w[(((long long)o * cin + c) * k + r) * k + s] * sc; }
+        } else if (j < kk) {
             const int c = j % cin; const int rs = j / cin; const int s = rs % k; const int r = rs / k;
             v = w[(((long long)o * cin + c) * k + r) * k + s] * sc;
         }
@@ -72,14 +76,13 @@ __global__ void fold_bn_kernel(const float* __restrict__ w, const float* __restr
 // Stem im2col: one block = 32 consecutive output pixels of one output row.
 // kind 0: uint8 NHWC raw patch, applies x/255 then (x-mean)/std  (compute_features_hdf5.py:49-51)
 // kind 1: fp32 NCHW, already normalised (the tensor the reference hands to forward_extract)
-// The 7 input rows x 69 columns x 3 channels the block needs are staged as bf16 in shared memory; for a fixed filter row
-// r the 21 (s, c) taps of output pixel p are CONTIGUOUS there (offset r*207 + 6p), so column k of the im2col row is
-// tile[lut[k] + 6p] with a 192-entry table (-1 = zero padding 147..191).
+// The 7 input rows x 69 columns x 3 channels the block needs are staged as bf16 in shared memory (row stride 208, even, so
+// every 2-element group is 4-byte aligned); for a fixed filter row r the 21 (s, c) taps of output pixel p are CONTIGUOUS
+// there (offset r*208 + 6p), so an im2col row is 7 segments of 24 = 21 taps + 3 zeros, then zeros up to K = 192.
 __global__ void __launch_bounds__(256) stem_im2col_kernel(const void* __restrict__ in, int kind, int H, int W, int Ho, int Wo,
                                                           bf16* __restrict__ col) {
-    constexpr int TW = 32, IW = TW * 2 + 5, ROW = IW * 3;   // 69 input columns, 207 values per staged row
-    __shared__ bf16 tile[7 * ROW + 1];
-    __shared__ short lut[STEM_K];
+    constexpr int TW = 32, IW = TW * 2 + 5, ROW = 208;      // 69 input columns -> 207 values (+1 pad) per staged row
+    __shared__ __align__(16) bf16 tile[7 * ROW + 8];
     const int tiles_w = Wo / TW;
     int b = blockIdx.x;
     const int tw = b % tiles_w; b /= tiles_w;
@@ -87,12 +90,11 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const void* __restrict
     const int ow0 = tw * TW;
     const int ih0 = oh * 2 - 3, iw0 = ow0 * 2 - 3;
     const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
-    if (threadIdx.x < STEM_K) { const int k = threadIdx.x; lut[k] = k < 147 ? (short)((k / 21) * ROW + (k % 21)) : (short)-1; }
     for (int i = threadIdx.x; i < 7 * ROW; i += 256) {
         const int r = i / ROW; const int xc = i - r * ROW; const int x = xc / 3; const int c = xc - x * 3;
         const int ih = ih0 + r, iw = iw0 + x;
         float v = 0.f;
-        if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
+        if (xc < IW * 3 && ih >= 0 && ih < H && iw >= 0 && iw < W) {
             if (kind == 0) {
                 const uint8_t u = reinterpret_cast<const uint8_t*>(in)[(((long long)img * H + ih) * W + iw) * 3 + c];
                 v = (static_cast<float>(u) / 255.0f - mean[c]) / stdv[c];
@@ -104,14 +106,15 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const void* __restrict
     }
     __syncthreads();
     bf16* dst = col + (((long long)img * Ho + oh) * Wo + ow0) * STEM_K;
-    const bf16 zero = __float2bfloat16_rn(0.f);
+    const uint32_t* t32 = reinterpret_cast<const uint32_t*>(tile);
     for (int i = threadIdx.x; i < TW * (STEM_K / 8); i += 256) {
         const int p = i / (STEM_K / 8); const int k8 = (i - p * (STEM_K / 8)) * 8;
-        uint4 pack; bf16* h = reinterpret_cast<bf16*>(&pack);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int o = lut[k8 + j];
-            h[j] = o >= 0 ? tile[o + p * 6] : zero;
+        const int r = k8 / 24, q0 = k8 - r * 24;            // q0 in {0, 8, 16}
+        uint4 pack = make_uint4(0u, 0u, 0u, 0u);
+        if (r < 7) {
+            const int e = (r * ROW + p * 6 + q0) >> 1;      // 32-bit word index (r*208 + 6p + q0 is even)
+            pack.x = t32[e]; pack.y = t32[e + 1]; pack.z = t32[e + 2]; pack.w = t32[e + 3];
+            if (q0 == 16) { pack.z &= 0x0000ffffu; pack.w = 0u; }      // taps 16..20 valid, 21..23 are zero padding
         }
         *reinterpret_cast<uint4*>(dst + (long long)p * STEM_K + k8) = pack;
     }
