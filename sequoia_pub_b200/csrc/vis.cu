@@ -13,6 +13,7 @@
 //   * c(cat[local, t]) = Wc[:, :64] local + (Wc[:, 64:] t + bc) -> per-head 64x64 block-diagonal GEMM + per-slide row bias.
 #include "gemm.cuh"
 #include "../../include/sequoia_b200.h"
+#include <stdlib.h>
 
 namespace sq {
 
@@ -58,7 +59,7 @@ static void vis_layout(const VisDims& d, VisLayout* L) {
 static inline size_t aup(size_t x) { return (x + 1023) / 1024 * 1024; }
 
 struct LayerAct { size_t x_f32, x_hi, x_lo, xm_hi, xm_lo, fpre, loc_hi, loc_lo, spre, t_hi, t_lo, rb, cpre, out_hi, out_lo, x1, ln_mean, ln_rstd, h_hi, h_lo, upre, u_hi, u_lo; };
-struct VisAct { LayerAct lay[MAXL]; size_t xL, pooled, hmean, hrstd, z_hi, z_lo, splitk, splitk_bytes, total; };
+struct VisAct { LayerAct lay[MAXL]; size_t xL, pooled, hmean, hrstd, z_hi, z_lo, splitk, splitk_bytes, splitk2, splitk2_bytes, total; };
 
 static void vis_act_layout(const VisDims& d, int B, VisAct* A) {
     size_t off = 0;
@@ -82,11 +83,13 @@ static void vis_act_layout(const VisDims& d, int B, VisAct* A) {
     A->splitk_bytes = (size_t)16 * 128 * (size_t)(D > HD ? D : HD) * 4;     // small-M split-K partials / stream-K partial tiles
     if (A->splitk_bytes < ((size_t)160 * 256 * 128 * 4 + 8192)) A->splitk_bytes = (size_t)160 * 256 * 128 * 4 + 8192;
     A->splitk = take(A->splitk_bytes);
+    A->splitk2_bytes = (size_t)16 * 128 * (size_t)(D > HD ? D : HD) * 4;    // split-K partials of the side-stream (summary branch) GEMMs
+    A->splitk2 = take(A->splitk2_bytes);
     A->total = off;
 }
 
 struct VisBwd { size_t dp_hi, dp_lo, splitk, splitk_bytes, dz, dpooled, g2_f32, g2_hi, g2_lo, g1_f32, g1_hi, g1_lo, du_hi, du_lo, dh,
-                dc_hi, dc_lo, dlocal, df_hi, df_lo, drb, drb_hi, drb_lo, dt, ds_hi, ds_lo, dxm, part, part_bytes, gsum, total; };
+                dc_hi, dc_lo, dlocal, df_hi, df_lo, drb, drb_hi, drb_lo, dt, ds_hi, ds_lo, dxm, part, part_bytes, gsum, splitk2, splitk2_bytes, part2, total; };
 
 constexpr int LN_RPB = 16;    // rows per block in the row-LayerNorm backward
 
@@ -110,6 +113,8 @@ static void vis_bwd_layout(const VisDims& d, int B, VisBwd* S) {
     const size_t nblk = (M + 7) / 8 + 128;
     S->part_bytes = nblk * 2 * W * 4; S->part = take(S->part_bytes);
     S->gsum = take((size_t)B * W * 4);
+    S->splitk2_bytes = (size_t)16 * 128 * W * 4; S->splitk2 = take(S->splitk2_bytes);     // side-stream copies (summary branch)
+    S->part2 = take((size_t)((B + 7) / 8 + 8) * 2 * W * 4);
     S->total = off;
 }
 
@@ -522,6 +527,36 @@ struct GB {
 
 #define SQ_TRY(x) do { if ((x) != 0) return -1; } while (0)
 
+// The summary branch of a layer is a chain of tiny, latency-bound kernels that is independent of the big local-branch
+// GEMMs next to it; it is enqueued on a side stream (fork / join with events) so that it soaks up the SMs the persistent
+// GEMM kernels leave idle in their last, partially filled wave.  One side stream + two events per device (created lazily).
+struct SideStream { cudaStream_t s; cudaEvent_t fork, join; bool ok; };
+static SideStream* side_stream() {
+    static SideStream tab[16];
+    static bool init[16] = {false};
+    static const int enabled = getenv("SQ_SIDE_STREAM") ? atoi(getenv("SQ_SIDE_STREAM")) : 1;
+    int dev = 0;
+    if (!enabled || cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+    if (!init[dev]) {
+        init[dev] = true;
+        tab[dev].ok = cudaStreamCreateWithFlags(&tab[dev].s, cudaStreamNonBlocking) == cudaSuccess &&
+                      cudaEventCreateWithFlags(&tab[dev].fork, cudaEventDisableTiming) == cudaSuccess &&
+                      cudaEventCreateWithFlags(&tab[dev].join, cudaEventDisableTiming) == cudaSuccess;
+    }
+    return tab[dev].ok ? &tab[dev] : nullptr;
+}
+static cudaStream_t side_fork(SideStream* ss, cudaStream_t st) {
+    if (!ss) return st;
+    cudaEventRecord(ss->fork, st);
+    cudaStreamWaitEvent(ss->s, ss->fork, 0);
+    return ss->s;
+}
+static void side_join(SideStream* ss, cudaStream_t st) {
+    if (!ss) return;
+    cudaEventRecord(ss->join, ss->s);
+    cudaStreamWaitEvent(st, ss->join, 0);
+}
+
 static int check_launch(const char* what) {
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) { set_error("%s: %s", what, cudaGetErrorString(err)); return -1; }
@@ -569,20 +604,25 @@ static int vis_forward(const VisDims& d, const VisLayout& P, const float* prm, c
         if (l == 0) {
             prep_input_kernel<<<148 * 8, 256, 0, st>>>(x_in, prm + P.pos, x, (bf16*)(act + a.x_hi), (bf16*)(act + a.x_lo), N, D, (long long)M * D / 4);
         }
-        group_mean_kernel<<<dim3((D + 127) / 128, B), 256, 0, st>>>(x, N, D, 1.0f / (float)N, nullptr, (bf16*)(act + a.xm_hi), (bf16*)(act + a.xm_lo));
         SQ_TRY(check_launch("vis prep"));
-        // local branch, all heads: GELU(LN64(x Wf^T + bf))                       tformer_lin.py:20
-        SQ_TRY(GB(M, HD, D).A(act + a.x_hi, act + a.x_lo, D).B(wh + o.wf, wl + o.wf, D).bias(prm + o.bf).ln64(prm + o.lnl_g, prm + o.lnl_b)
-                   .save_pre((float*)(act + a.fpre), HD).out_planes(act + a.loc_hi, act + a.loc_lo, HD).sk(sk, A.splitk_bytes).run(st));
-        // summary branch on the token mean: GELU(LN64(mean(x) Ws^T + bs))           tformer_lin.py:21-22
-        SQ_TRY(GB(B, HD, D).A(act + a.xm_hi, act + a.xm_lo, D).B(wh + o.ws, wl + o.ws, D).bias(prm + o.bs).out_f32((float*)(act + a.spre), HD)
-                   .bn(128).auto_split(sk, A.splitk_bytes).run(st));
-        ln64_fwd_kernel<<<dim3((HD + 127) / 128, (B + 7) / 8), 256, 0, st>>>((const float*)(act + a.spre), prm + o.lns_g, prm + o.lns_b, B, HD,
-                                                                            (bf16*)(act + a.t_hi), (bf16*)(act + a.t_lo));
-        SQ_TRY(check_launch("vis ln64 fwd"));
-        // per-slide row bias: Wc[:, 64:] t + bc (per head)                          tformer_lin.py:23-24
-        SQ_TRY(GB(B, HD, 64).A(act + a.t_hi, act + a.t_lo, HD).akoff(64).B(wh + o.wc + 64, wl + o.wc + 64, 128).bn(64).bias(prm + o.bc)
-                   .out_f32((float*)(act + a.rb), HD).run(st));
+        // ---- summary branch on the token mean, on the side stream: GELU(LN64(mean(x) Ws^T + bs)), then the per-slide row
+        //      bias Wc[:, 64:] t + bc (per head)                                    tformer_lin.py:21-24
+        {
+            SideStream* ss = side_stream();
+            cudaStream_t s2 = side_fork(ss, st);
+            group_mean_kernel<<<dim3((D + 127) / 128, B), 256, 0, s2>>>(x, N, D, 1.0f / (float)N, nullptr, (bf16*)(act + a.xm_hi), (bf16*)(act + a.xm_lo));
+            SQ_TRY(GB(B, HD, D).A(act + a.xm_hi, act + a.xm_lo, D).B(wh + o.ws, wl + o.ws, D).bias(prm + o.bs).out_f32((float*)(act + a.spre), HD)
+                       .bn(128).auto_split(act + A.splitk2, A.splitk2_bytes).run(s2));
+            ln64_fwd_kernel<<<dim3((HD + 127) / 128, (B + 7) / 8), 256, 0, s2>>>((const float*)(act + a.spre), prm + o.lns_g, prm + o.lns_b, B, HD,
+                                                                                (bf16*)(act + a.t_hi), (bf16*)(act + a.t_lo));
+            SQ_TRY(check_launch("vis ln64 fwd"));
+            SQ_TRY(GB(B, HD, 64).A(act + a.t_hi, act + a.t_lo, HD).akoff(64).B(wh + o.wc + 64, wl + o.wc + 64, 128).bn(64).bias(prm + o.bc)
+                       .out_f32((float*)(act + a.rb), HD).run(s2));
+            // ---- local branch, all heads, on the main stream: GELU(LN64(x Wf^T + bf))            tformer_lin.py:20
+            SQ_TRY(GB(M, HD, D).A(act + a.x_hi, act + a.x_lo, D).B(wh + o.wf, wl + o.wf, D).bias(prm + o.bf).ln64(prm + o.lnl_g, prm + o.lnl_b)
+                       .save_pre((float*)(act + a.fpre), HD).out_planes(act + a.loc_hi, act + a.loc_lo, HD).sk(sk, A.splitk_bytes).run(st));
+            side_join(ss, st);
+        }
         // combine: GELU(Wc[:, :64] local + rowbias) (per head)                      tformer_lin.py:24
         SQ_TRY(GB(M, HD, 64).A(act + a.loc_hi, act + a.loc_lo, HD).akoff(64).B(wh + o.wc, wl + o.wc, 128).bn(64)
                    .rowbias((const float*)(act + a.rb), N, HD).act(ACT_GELU).save_pre((float*)(act + a.cpre), HD)
@@ -655,32 +695,38 @@ static int vis_backward_layer(const VisDims& d, const VisLayout& P, int l, const
                .out_planes(sc + S.dc_hi, sc + S.dc_lo, HD).sk(sc + S.splitk, S.splitk_bytes).run(st));
     SQ_TRY(GB(D, HD, M).A(sc + S.g1_hi, sc + S.g1_lo, D, 1).B(act + a.out_hi, act + a.out_lo, HD, 1).out_f32(grads + o.wp, HD).sk(sc + S.splitk, S.splitk_bytes).run(st));
     SQ_TRY(launch_bias_grad((bf16*)(sc + S.g1_hi), (bf16*)(sc + S.g1_lo), B, N, D, gsum, grads + o.bp, st));
-    // dlocal = dCpre Wc[:, :64] per head ; dWc[:, :64] = dCpre^T local per head
+    // ---- summary branch on the side stream: per-slide sums of dCpre (gradient of the row bias and of bc), back through
+    //      Wc[:, 64:], LayerNorm64+GELU and Ws; ends with dxm, the per-slide term of the input gradient
+    SideStream* ss = side_stream();
+    {
+        cudaStream_t s2 = side_fork(ss, st);
+        float* part2 = (float*)(sc + S.part2);
+        group_sum_planes_kernel<<<dim3((HD + 255) / 256, B), 256, 0, s2>>>((bf16*)(sc + S.dc_hi), (bf16*)(sc + S.dc_lo), HD, N, HD, (float*)(sc + S.drb),
+                                                                               (bf16*)(sc + S.drb_hi), (bf16*)(sc + S.drb_lo));
+        colsum_kernel<<<(HD + 31) / 32, 256, 0, s2>>>((const float*)(sc + S.drb), B, HD, HD, 1.0f, grads + o.bc);
+        SQ_TRY(check_launch("vis drb"));
+        SQ_TRY(GB(B, HD, 64).A(sc + S.drb_hi, sc + S.drb_lo, HD).akoff(64).B(wh + o.wc + 64, wl + o.wc + 64, 128, 1).bdiag_dgrad(64, HD).bn(64)
+                   .out_f32((float*)(sc + S.dt), HD).run(s2));
+        SQ_TRY(GB(HD, HD, B).A(sc + S.drb_hi, sc + S.drb_lo, HD, 1).B(act + a.t_hi, act + a.t_lo, HD, 1).diag64().out_f32(grads + o.wc + 64, 128).run(s2));
+        SQ_TRY(launch_ln64_bwd((const float*)(sc + S.dt), (const float*)(act + a.spre), prm + o.lns_g, prm + o.lns_b, B, HD, (bf16*)(sc + S.ds_hi),
+                               (bf16*)(sc + S.ds_lo), part2, grads + o.lns_g, s2));
+        SQ_TRY(GB(HD, D, B).A(sc + S.ds_hi, sc + S.ds_lo, HD, 1).B(act + a.xm_hi, act + a.xm_lo, D, 1).out_f32(grads + o.ws, D).run(s2));
+        group_sum_planes_kernel<<<dim3((HD + 255) / 256, 1), 256, 0, s2>>>((bf16*)(sc + S.ds_hi), (bf16*)(sc + S.ds_lo), HD, B, HD, grads + o.bs, nullptr, nullptr);
+        SQ_TRY(check_launch("vis dbs"));
+        SQ_TRY(GB(B, D, HD).A(sc + S.ds_hi, sc + S.ds_lo, HD).B(wh + o.ws, wl + o.ws, D, 1).alpha(1.0f / (float)N).out_f32((float*)(sc + S.dxm), D)
+                   .auto_split(sc + S.splitk2, S.splitk2_bytes).run(s2));
+    }
+    // ---- local branch on the main stream: dlocal = dCpre Wc[:, :64] per head ; dWc[:, :64] = dCpre^T local per head
     SQ_TRY(GB(M, HD, 64).A(sc + S.dc_hi, sc + S.dc_lo, HD).akoff(64).B(wh + o.wc, wl + o.wc, 128, 1).bdiag_dgrad(64, HD).bn(64)
                .out_f32((float*)(sc + S.dlocal), HD).run(st));
     SQ_TRY(GB(HD, HD, M).A(sc + S.dc_hi, sc + S.dc_lo, HD, 1).B(act + a.loc_hi, act + a.loc_lo, HD, 1).diag64().out_f32(grads + o.wc, 128)
                .auto_split(sc + S.splitk, S.splitk_bytes).run(st));
-    // per-slide sums of dCpre: gradient of the row bias (and of bc)
-    group_sum_planes_kernel<<<dim3((HD + 255) / 256, B), 256, 0, st>>>((bf16*)(sc + S.dc_hi), (bf16*)(sc + S.dc_lo), HD, N, HD, (float*)(sc + S.drb),
-                                                                           (bf16*)(sc + S.drb_hi), (bf16*)(sc + S.drb_lo));
-    colsum_kernel<<<(HD + 31) / 32, 256, 0, st>>>((const float*)(sc + S.drb), B, HD, HD, 1.0f, grads + o.bc);
-    SQ_TRY(check_launch("vis drb"));
     SQ_TRY(launch_ln64_bwd((const float*)(sc + S.dlocal), (const float*)(act + a.fpre), prm + o.lnl_g, prm + o.lnl_b, M, HD, (bf16*)(sc + S.df_hi),
                            (bf16*)(sc + S.df_lo), part, grads + o.lnl_g, st));
-    // summary branch
-    SQ_TRY(GB(B, HD, 64).A(sc + S.drb_hi, sc + S.drb_lo, HD).akoff(64).B(wh + o.wc + 64, wl + o.wc + 64, 128, 1).bdiag_dgrad(64, HD).bn(64)
-               .out_f32((float*)(sc + S.dt), HD).run(st));
-    SQ_TRY(GB(HD, HD, B).A(sc + S.drb_hi, sc + S.drb_lo, HD, 1).B(act + a.t_hi, act + a.t_lo, HD, 1).diag64().out_f32(grads + o.wc + 64, 128).run(st));
-    SQ_TRY(launch_ln64_bwd((const float*)(sc + S.dt), (const float*)(act + a.spre), prm + o.lns_g, prm + o.lns_b, B, HD, (bf16*)(sc + S.ds_hi),
-                           (bf16*)(sc + S.ds_lo), part, grads + o.lns_g, st));
-    SQ_TRY(GB(HD, D, B).A(sc + S.ds_hi, sc + S.ds_lo, HD, 1).B(act + a.xm_hi, act + a.xm_lo, D, 1).out_f32(grads + o.ws, D).run(st));
-    group_sum_planes_kernel<<<dim3((HD + 255) / 256, 1), 256, 0, st>>>((bf16*)(sc + S.ds_hi), (bf16*)(sc + S.ds_lo), HD, B, HD, grads + o.bs, nullptr, nullptr);
-    SQ_TRY(check_launch("vis dbs"));
-    SQ_TRY(GB(B, D, HD).A(sc + S.ds_hi, sc + S.ds_lo, HD).B(wh + o.ws, wl + o.ws, D, 1).alpha(1.0f / (float)N).out_f32((float*)(sc + S.dxm), D)
-               .auto_split(sc + S.splitk, S.splitk_bytes).run(st));
     // local branch weights and the gradient w.r.t. the layer input
     SQ_TRY(GB(HD, D, M).A(sc + S.df_hi, sc + S.df_lo, HD, 1).B(act + a.x_hi, act + a.x_lo, D, 1).out_f32(grads + o.wf, D).sk(sc + S.splitk, S.splitk_bytes).run(st));
     SQ_TRY(launch_bias_grad((bf16*)(sc + S.df_hi), (bf16*)(sc + S.df_lo), B, N, HD, gsum, grads + o.bf, st));
+    side_join(ss, st);
     float* gout = (l == 0 && dx_out) ? dx_out : (float*)(sc + S.g2_f32);
     GB gx(M, D, HD);
     gx.A(sc + S.df_hi, sc + S.df_lo, HD).B(wh + o.wf, wl + o.wf, D, 1).res((const float*)(sc + S.g1_f32), D)
