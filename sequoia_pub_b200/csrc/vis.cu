@@ -679,27 +679,34 @@ static int vis_backward_layer(const VisDims& d, const VisLayout& P, int l, const
     const LayerOff& o = P.lay[l];
     float* gsum = (float*)(sc + S.gsum);
     float* part = (float*)(sc + S.part);
+    // Main stream = the dgrad chain (critical path to the next layer's gradient); side stream = every weight / bias gradient
+    // and the summary branch.  Side work is forked right after the tensor it consumes is produced and joined before a
+    // buffer it reads is overwritten; both streams run persistent GEMMs, so the side stream's CTAs fill the SMs that the
+    // main stream's partially filled waves leave idle (and vice versa).
+    SideStream* ss = side_stream();
+    cudaStream_t s2 = side_fork(ss, st);                                       // g2 (and its planes) are complete on `st`
     // ---- feed-forward (x2 = W2 GELU(W1 LN(x1) + b1) + b2 + x1)
+    SQ_TRY(GB(D, D, M).A(sc + S.g2_hi, sc + S.g2_lo, D, 1).B(act + a.u_hi, act + a.u_lo, D, 1).out_f32(grads + o.w2, D).run(s2));
+    SQ_TRY(launch_bias_grad((bf16*)(sc + S.g2_hi), (bf16*)(sc + S.g2_lo), B, N, D, gsum, grads + o.b2, s2));
     SQ_TRY(GB(M, D, D).A(sc + S.g2_hi, sc + S.g2_lo, D).B(wh + o.w2, wl + o.w2, D, 1).dgelu((const float*)(act + a.upre), D)
                .out_planes(sc + S.du_hi, sc + S.du_lo, D).sk(sc + S.splitk, S.splitk_bytes).run(st));
-    SQ_TRY(GB(D, D, M).A(sc + S.g2_hi, sc + S.g2_lo, D, 1).B(act + a.u_hi, act + a.u_lo, D, 1).out_f32(grads + o.w2, D).sk(sc + S.splitk, S.splitk_bytes).run(st));
-    SQ_TRY(launch_bias_grad((bf16*)(sc + S.g2_hi), (bf16*)(sc + S.g2_lo), B, N, D, gsum, grads + o.b2, st));
+    s2 = side_fork(ss, st);                                                    // dUpre planes
+    SQ_TRY(GB(D, D, M).A(sc + S.du_hi, sc + S.du_lo, D, 1).B(act + a.h_hi, act + a.h_lo, D, 1).out_f32(grads + o.w1, D).run(s2));
+    SQ_TRY(launch_bias_grad((bf16*)(sc + S.du_hi), (bf16*)(sc + S.du_lo), B, N, D, gsum, grads + o.b1, s2));
     SQ_TRY(GB(M, D, D).A(sc + S.du_hi, sc + S.du_lo, D).B(wh + o.w1, wl + o.w1, D, 1).out_f32((float*)(sc + S.dh), D).sk(sc + S.splitk, S.splitk_bytes).run(st));
-    SQ_TRY(GB(D, D, M).A(sc + S.du_hi, sc + S.du_lo, D, 1).B(act + a.h_hi, act + a.h_lo, D, 1).out_f32(grads + o.w1, D).sk(sc + S.splitk, S.splitk_bytes).run(st));
-    SQ_TRY(launch_bias_grad((bf16*)(sc + S.du_hi), (bf16*)(sc + S.du_lo), B, N, D, gsum, grads + o.b1, st));
     SQ_TRY(launch_ln_rows_bwd((const float*)(sc + S.dh), (const float*)(act + a.x1), (const float*)(act + a.ln_mean), (const float*)(act + a.ln_rstd),
                               prm + o.fg, (const float*)(sc + S.g2_f32), M, D, (float*)(sc + S.g1_f32), (bf16*)(sc + S.g1_hi), (bf16*)(sc + S.g1_lo),
                               part, grads + o.fg, st));
     // ---- mixer (x1 = Wp out + bp + x)
+    s2 = side_fork(ss, st);                                                    // g1
+    SQ_TRY(GB(D, HD, M).A(sc + S.g1_hi, sc + S.g1_lo, D, 1).B(act + a.out_hi, act + a.out_lo, HD, 1).out_f32(grads + o.wp, HD).run(s2));
+    SQ_TRY(launch_bias_grad((bf16*)(sc + S.g1_hi), (bf16*)(sc + S.g1_lo), B, N, D, gsum, grads + o.bp, s2));
     SQ_TRY(GB(M, HD, D).A(sc + S.g1_hi, sc + S.g1_lo, D).B(wh + o.wp, wl + o.wp, HD, 1).dgelu((const float*)(act + a.cpre), HD)
                .out_planes(sc + S.dc_hi, sc + S.dc_lo, HD).sk(sc + S.splitk, S.splitk_bytes).run(st));
-    SQ_TRY(GB(D, HD, M).A(sc + S.g1_hi, sc + S.g1_lo, D, 1).B(act + a.out_hi, act + a.out_lo, HD, 1).out_f32(grads + o.wp, HD).sk(sc + S.splitk, S.splitk_bytes).run(st));
-    SQ_TRY(launch_bias_grad((bf16*)(sc + S.g1_hi), (bf16*)(sc + S.g1_lo), B, N, D, gsum, grads + o.bp, st));
-    // ---- summary branch on the side stream: per-slide sums of dCpre (gradient of the row bias and of bc), back through
-    //      Wc[:, 64:], LayerNorm64+GELU and Ws; ends with dxm, the per-slide term of the input gradient
-    SideStream* ss = side_stream();
+    s2 = side_fork(ss, st);                                                    // dCpre planes
     {
-        cudaStream_t s2 = side_fork(ss, st);
+        // summary branch: per-slide sums of dCpre (gradient of the row bias and of bc), back through Wc[:, 64:],
+        // LayerNorm64+GELU and Ws; ends with dxm, the per-slide term of the input gradient
         float* part2 = (float*)(sc + S.part2);
         group_sum_planes_kernel<<<dim3((HD + 255) / 256, B), 256, 0, s2>>>((bf16*)(sc + S.dc_hi), (bf16*)(sc + S.dc_lo), HD, N, HD, (float*)(sc + S.drb),
                                                                                (bf16*)(sc + S.drb_hi), (bf16*)(sc + S.drb_lo));
@@ -715,18 +722,19 @@ static int vis_backward_layer(const VisDims& d, const VisLayout& P, int l, const
         SQ_TRY(check_launch("vis dbs"));
         SQ_TRY(GB(B, D, HD).A(sc + S.ds_hi, sc + S.ds_lo, HD).B(wh + o.ws, wl + o.ws, D, 1).alpha(1.0f / (float)N).out_f32((float*)(sc + S.dxm), D)
                    .auto_split(sc + S.splitk2, S.splitk2_bytes).run(s2));
+        // dWc[:, :64] = dCpre^T local per head (split-K partials in the side stream's workspace, in order after dxm's)
+        SQ_TRY(GB(HD, HD, M).A(sc + S.dc_hi, sc + S.dc_lo, HD, 1).B(act + a.loc_hi, act + a.loc_lo, HD, 1).diag64().out_f32(grads + o.wc, 128)
+                   .auto_split(sc + S.splitk2, S.splitk2_bytes).run(s2));
     }
-    // ---- local branch on the main stream: dlocal = dCpre Wc[:, :64] per head ; dWc[:, :64] = dCpre^T local per head
+    // local branch on the main stream: dlocal = dCpre Wc[:, :64] per head, back through LayerNorm64+GELU
     SQ_TRY(GB(M, HD, 64).A(sc + S.dc_hi, sc + S.dc_lo, HD).akoff(64).B(wh + o.wc, wl + o.wc, 128, 1).bdiag_dgrad(64, HD).bn(64)
                .out_f32((float*)(sc + S.dlocal), HD).run(st));
-    SQ_TRY(GB(HD, HD, M).A(sc + S.dc_hi, sc + S.dc_lo, HD, 1).B(act + a.loc_hi, act + a.loc_lo, HD, 1).diag64().out_f32(grads + o.wc, 128)
-               .auto_split(sc + S.splitk, S.splitk_bytes).run(st));
     SQ_TRY(launch_ln64_bwd((const float*)(sc + S.dlocal), (const float*)(act + a.fpre), prm + o.lnl_g, prm + o.lnl_b, M, HD, (bf16*)(sc + S.df_hi),
                            (bf16*)(sc + S.df_lo), part, grads + o.lnl_g, st));
-    // local branch weights and the gradient w.r.t. the layer input
-    SQ_TRY(GB(HD, D, M).A(sc + S.df_hi, sc + S.df_lo, HD, 1).B(act + a.x_hi, act + a.x_lo, D, 1).out_f32(grads + o.wf, D).sk(sc + S.splitk, S.splitk_bytes).run(st));
-    SQ_TRY(launch_bias_grad((bf16*)(sc + S.df_hi), (bf16*)(sc + S.df_lo), B, N, HD, gsum, grads + o.bf, st));
-    side_join(ss, st);
+    side_join(ss, st);                                                         // dxm is needed now; everything forked so far is done
+    s2 = side_fork(ss, st);                                                    // dFpre planes
+    SQ_TRY(GB(HD, D, M).A(sc + S.df_hi, sc + S.df_lo, HD, 1).B(act + a.x_hi, act + a.x_lo, D, 1).out_f32(grads + o.wf, D).run(s2));
+    SQ_TRY(launch_bias_grad((bf16*)(sc + S.df_hi), (bf16*)(sc + S.df_lo), B, N, HD, gsum, grads + o.bf, s2));
     float* gout = (l == 0 && dx_out) ? dx_out : (float*)(sc + S.g2_f32);
     GB gx(M, D, HD);
     gx.A(sc + S.df_hi, sc + S.df_lo, HD).B(wh + o.wf, wl + o.wf, D, 1).res((const float*)(sc + S.g1_f32), D)
@@ -738,6 +746,7 @@ static int vis_backward_layer(const VisDims& d, const VisLayout& P, int l, const
         pos_grad_kernel<<<(int)(((long long)N * D / 4 + 255) / 256), 256, 0, st>>>(gout, B, N, D, grads + P.pos);
         SQ_TRY(check_launch("vis pos grad"));
     }
+    side_join(ss, st);          // the layer's weight gradients are complete on `st` (all-reduce / AdamW / next layer follow)
     return 0;
 }
 
