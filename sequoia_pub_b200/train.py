@@ -28,6 +28,7 @@ class FusedTrainer:
             self.world = torch.distributed.get_world_size(process_group)
         self.overlap = overlap
         self._token = None
+        self._opt_stream = None
         self.launch_count = 0     # sq_* calls of the last step (bench.py reports kernels separately)
 
     def _bind(self):
@@ -64,13 +65,36 @@ class FusedTrainer:
                 works.append(allreduce_stage(self.g, self.stage_range[s], self.pg))
             for w in works:
                 w.wait()
-        else:
+        elif self.world > 1 or not self.overlap:
             m._backward_impl(act, dpred, B, False, gbuf=self.g)
             if self.world > 1:
                 torch.distributed.all_reduce(self.g, group=self.pg)
+        else:
+            # single GPU: the AdamW update of a stage (HBM-bound) runs on a side stream while the backward pass of the
+            # stages below it (tensor-bound) continues; a stage's weights are not read again after its own backward
+            self.step_count += 1
+            main = torch.cuda.current_stream()
+            if self._opt_stream is None:
+                self._opt_stream = torch.cuda.Stream()
+            for s in range(cfg.depth, -1, -1):
+                m._backward_impl(act, dpred if s == cfg.depth else None, B, False, gbuf=self.g, stage_hi=s, stage_lo=s)
+                ev = torch.cuda.Event()
+                ev.record(main)
+                with torch.cuda.stream(self._opt_stream):
+                    self._opt_stream.wait_event(ev)
+                    self._adamw(m, *self.stage_range[s])
+            main.wait_stream(self._opt_stream)
+            m._planes_are_fresh()
+            return self.loss
         self.step_count += 1
-        _lib.check(L.sq_adamw_flat(_lib.ptr(m._flat), _lib.ptr(self.g), _lib.ptr(self.m), _lib.ptr(self.v), _lib.ptr(m._w_hi),
-                                   _lib.ptr(m._w_lo), m._total, self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
-                                   self.step_count, 1.0 / self.world, _lib.stream_ptr()))
+        self._adamw(m, 0, m._total)
         m._planes_are_fresh()
         return self.loss
+
+    def _adamw(self, m, b, e):
+        off = 4 * b
+        _lib.check(_lib.lib().sq_adamw_flat(C.c_void_p(m._flat.data_ptr() + off), C.c_void_p(self.g.data_ptr() + off),
+                                            C.c_void_p(self.m.data_ptr() + off), C.c_void_p(self.v.data_ptr() + off),
+                                            C.c_void_p(m._w_hi.data_ptr() + off // 2), C.c_void_p(m._w_lo.data_ptr() + off // 2), e - b, self.lr,
+                                            self.betas[0], self.betas[1], self.eps, self.wd, self.step_count, 1.0 / self.world,
+                                            _lib.stream_ptr()))
