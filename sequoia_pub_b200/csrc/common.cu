@@ -38,6 +38,35 @@ PFN_encodeTiled get_encode_fn() {
     return fn;
 }
 
+// Side stream for work that is independent of the main chain of a forward / backward pass (fork / join with events): its
+// kernels soak up the SMs that the persistent GEMM kernels leave idle in partially filled waves.  One side stream + two
+// events per device, created lazily (handles only; no device memory).
+SideStream* side_stream() {
+    static SideStream tab[16];
+    static bool init[16] = {false};
+    static const int enabled = getenv("SQ_SIDE_STREAM") ? atoi(getenv("SQ_SIDE_STREAM")) : 1;
+    int dev = 0;
+    if (!enabled || cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+    if (!init[dev]) {
+        init[dev] = true;
+        tab[dev].ok = cudaStreamCreateWithFlags(&tab[dev].s, cudaStreamNonBlocking) == cudaSuccess &&
+                      cudaEventCreateWithFlags(&tab[dev].fork, cudaEventDisableTiming) == cudaSuccess &&
+                      cudaEventCreateWithFlags(&tab[dev].join, cudaEventDisableTiming) == cudaSuccess;
+    }
+    return tab[dev].ok ? &tab[dev] : nullptr;
+}
+cudaStream_t side_fork(SideStream* ss, cudaStream_t st) {
+    if (!ss) return st;
+    cudaEventRecord(ss->fork, st);
+    cudaStreamWaitEvent(ss->s, ss->fork, 0);
+    return ss->s;
+}
+void side_join(SideStream* ss, cudaStream_t st) {
+    if (!ss) return;
+    cudaEventRecord(ss->join, ss->s);
+    cudaStreamWaitEvent(st, ss->join, 0);
+}
+
 // One instantiation of the GEMM kernel per (tile width, epilogue class[, fused split-precision staging]).
 int launch_gemm_dispatch(int bn, int cls, int fuse3, const CUtensorMap* maps, const GemmKParams& kp, int grid, cudaStream_t st) {
 #define SQ_CASE(BN, CLS) if (!fuse3 && bn == BN && cls == CLS) return launch_gemm_inst<BN, CLS, 0>(maps, kp, grid, st);

@@ -801,7 +801,11 @@ int split_planes(const float* x, bf16* hi, bf16* lo, long long rows, int cols, l
 // optional per-launch CUDA-event timing of the GEMM kernel (bench.py's roofline leg); no-ops unless enabled
 void gemm_timing_begin(cudaStream_t st, double flops);
 void gemm_timing_end(cudaStream_t st);
-unsigned long long* gemm_prof_buffer();   // device buffer for per-CTA role cycle counters, or null
+unsigned long long* gemm_prof_buffer();
+struct SideStream { cudaStream_t s; cudaEvent_t fork, join; bool ok; };
+SideStream* side_stream();                                   // null when disabled (SQ_SIDE_STREAM=0) or unavailable
+cudaStream_t side_fork(SideStream* ss, cudaStream_t st);     // side stream now waits for everything enqueued on st so far
+void side_join(SideStream* ss, cudaStream_t st);             // st now waits for everything enqueued on the side stream so far   // device buffer for per-CTA role cycle counters, or null
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,

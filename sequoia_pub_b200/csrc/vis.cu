@@ -528,34 +528,8 @@ struct GB {
 #define SQ_TRY(x) do { if ((x) != 0) return -1; } while (0)
 
 // The summary branch of a layer is a chain of tiny, latency-bound kernels that is independent of the big local-branch
-// GEMMs next to it; it is enqueued on a side stream (fork / join with events) so that it soaks up the SMs the persistent
-// GEMM kernels leave idle in their last, partially filled wave.  One side stream + two events per device (created lazily).
-struct SideStream { cudaStream_t s; cudaEvent_t fork, join; bool ok; };
-static SideStream* side_stream() {
-    static SideStream tab[16];
-    static bool init[16] = {false};
-    static const int enabled = getenv("SQ_SIDE_STREAM") ? atoi(getenv("SQ_SIDE_STREAM")) : 1;
-    int dev = 0;
-    if (!enabled || cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
-    if (!init[dev]) {
-        init[dev] = true;
-        tab[dev].ok = cudaStreamCreateWithFlags(&tab[dev].s, cudaStreamNonBlocking) == cudaSuccess &&
-                      cudaEventCreateWithFlags(&tab[dev].fork, cudaEventDisableTiming) == cudaSuccess &&
-                      cudaEventCreateWithFlags(&tab[dev].join, cudaEventDisableTiming) == cudaSuccess;
-    }
-    return tab[dev].ok ? &tab[dev] : nullptr;
-}
-static cudaStream_t side_fork(SideStream* ss, cudaStream_t st) {
-    if (!ss) return st;
-    cudaEventRecord(ss->fork, st);
-    cudaStreamWaitEvent(ss->s, ss->fork, 0);
-    return ss->s;
-}
-static void side_join(SideStream* ss, cudaStream_t st) {
-    if (!ss) return;
-    cudaEventRecord(ss->join, ss->s);
-    cudaStreamWaitEvent(st, ss->join, 0);
-}
+// GEMMs next to it; it is enqueued on the library's side stream (common.cu: side_stream / side_fork / side_join) so that it
+// soaks up the SMs the persistent GEMM kernels leave idle in their last, partially filled wave.
 
 static int check_launch(const char* what) {
     cudaError_t err = cudaGetLastError();
