@@ -58,13 +58,22 @@ class FusedTrainer:
         dpred = torch.empty_like(pred)
         _lib.check(L.sq_mse_fwd_bwd(_lib.ptr(pred), _lib.ptr(y), B, cfg.num_outputs, _lib.ptr(self.loss), _lib.ptr(dpred),
                                     _lib.ptr(self.mse_scratch), _lib.stream_ptr()))
-        works = []
         if self.world > 1 and self.overlap:
+            # data parallel: a stage's gradient slice is all-reduced (NCCL) as soon as the stage is enqueued, and its AdamW
+            # update runs on a side stream right after that all-reduce, while the backward pass continues below
+            self.step_count += 1
+            main = torch.cuda.current_stream()
+            if self._opt_stream is None:
+                self._opt_stream = torch.cuda.Stream()
             for s in range(cfg.depth, -1, -1):
                 m._backward_impl(act, dpred if s == cfg.depth else None, B, False, gbuf=self.g, stage_hi=s, stage_lo=s)
-                works.append(allreduce_stage(self.g, self.stage_range[s], self.pg))
-            for w in works:
-                w.wait()
+                w = allreduce_stage(self.g, self.stage_range[s], self.pg)
+                with torch.cuda.stream(self._opt_stream):
+                    w.wait()
+                    self._adamw(m, *self.stage_range[s])
+            main.wait_stream(self._opt_stream)
+            m._planes_are_fresh()
+            return self.loss
         elif self.world > 1 or not self.overlap:
             m._backward_impl(act, dpred, B, False, gbuf=self.g)
             if self.world > 1:
