@@ -42,6 +42,11 @@ SQ_API int sq_device_ok(void);
 SQ_API int sq_gemm_timing_enable(int on);
 SQ_API int sq_gemm_timing_read(double* total_ms, long long* launches, double* mma_flops);
 
+/* Independent sub-chains of a pass (ViS summary branch, weight gradients) are enqueued on a library-owned side stream so
+ * that they fill SMs the main chain leaves idle (default on; environment SQ_SIDE_STREAM=0 disables).  Measurement code
+ * turns it off to time kernels without overlap. */
+SQ_API int sq_side_stream_enable(int on);
+
 /* Development aid: when `device_buffer` (>= 148*16 uint64) is non-NULL every following GEMM launch stores per-CTA cycle
  * counters of its warp roles: [cta][0..1] producer {waiting for a free stage, total}; [2..4] MMA issuer {waiting for
  * data, waiting for a drained accumulator, total}; [5+2q, 6+2q] epilogue warp q {waiting for an accumulator, total}. */

@@ -50,6 +50,7 @@ SIGNATURES = {
     "sq_gemm_timing_enable": (c_int, [c_int]),
     "sq_gemm_timing_read": (c_int, [C.POINTER(C.c_double), C.POINTER(c_ll), C.POINTER(C.c_double)]),
     "sq_gemm_profile": (c_int, [c_void_p]),
+    "sq_side_stream_enable": (c_int, [c_int]),
     "sq_split_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_ll, c_int, c_ll, c_ll, c_void_p]),
     "sq_gemm_bf16": (c_int, [C.POINTER(GemmDesc), c_void_p]),
     "sq_resnet50_num_convs": (c_int, []),

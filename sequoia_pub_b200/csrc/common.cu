@@ -41,10 +41,12 @@ PFN_encodeTiled get_encode_fn() {
 // Side stream for work that is independent of the main chain of a forward / backward pass (fork / join with events): its
 // kernels soak up the SMs that the persistent GEMM kernels leave idle in partially filled waves.  One side stream + two
 // events per device, created lazily (handles only; no device memory).
+static int g_side_enabled = -1;      // -1: not decided yet (environment SQ_SIDE_STREAM, default on)
 SideStream* side_stream() {
     static SideStream tab[16];
     static bool init[16] = {false};
-    static const int enabled = getenv("SQ_SIDE_STREAM") ? atoi(getenv("SQ_SIDE_STREAM")) : 1;
+    if (g_side_enabled < 0) g_side_enabled = getenv("SQ_SIDE_STREAM") ? atoi(getenv("SQ_SIDE_STREAM")) : 1;
+    const int enabled = g_side_enabled;
     int dev = 0;
     if (!enabled || cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
     if (!init[dev]) {
@@ -167,6 +169,8 @@ int sq_gemm_timing_read(double* total_ms, long long* launches, double* mma_flops
     g_ev_used = 0; g_flops = 0.0;
     return 0;
 }
+
+int sq_side_stream_enable(int on) { g_side_enabled = on ? 1 : 0; return 0; }
 
 int sq_gemm_profile(void* device_buffer) { g_prof = (unsigned long long*)device_buffer; return 0; }
 

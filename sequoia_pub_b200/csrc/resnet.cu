@@ -279,18 +279,14 @@ int sq_resnet50_extract(const void* input, int input_kind, int batch, int H, int
             const bool down = (b == 0);
             const ConvSpec& c1 = p.conv[ci]; const ConvSpec& c2 = p.conv[ci + 1]; const ConvSpec& c3 = p.conv[ci + 2];
             int h1, w1, h2, w2, h3, w3, hd, wd;
-            // the downsample convolution of a stage's first block only depends on the block input: side stream
-            SideStream* ss = down ? side_stream() : nullptr;
+            if (run_conv(c1, wp, shifts, big[x], batch, h, w, small_[0], nullptr, nullptr, true, st, &h1, &w1)) return -1;
+            if (run_conv(c2, wp, shifts, small_[0], batch, h1, w1, small_[1], nullptr, nullptr, true, st, &h2, &w2)) return -1;
             const bf16* res = big[x];
             const int y = (x + 1) % 3, d = (x + 2) % 3;
             if (down) {
-                cudaStream_t s2 = side_fork(ss, st);
-                if (run_conv(p.conv[ci + 3], wp, shifts, big[x], batch, h, w, big[d], nullptr, nullptr, false, s2, &hd, &wd)) return -1;
+                if (run_conv(p.conv[ci + 3], wp, shifts, big[x], batch, h, w, big[d], nullptr, nullptr, false, st, &hd, &wd)) return -1;
                 res = big[d];
             }
-            if (run_conv(c1, wp, shifts, big[x], batch, h, w, small_[0], nullptr, nullptr, true, st, &h1, &w1)) return -1;
-            if (run_conv(c2, wp, shifts, small_[0], batch, h1, w1, small_[1], nullptr, nullptr, true, st, &h2, &w2)) return -1;
-            if (down) side_join(ss, st);
             if (run_conv(c3, wp, shifts, small_[1], batch, h2, w2, last ? nullptr : big[y], last ? fmap : nullptr, res, true, st, &h3, &w3)) return -1;
             x = y; h = h3; w = w3;
             ci += down ? 4 : 3;

@@ -27,20 +27,34 @@ def select_keys(keys, max_patch_number=4000, rng=_random):
 
 
 class SlideExtractor:
-    """Runs `model.extract_uint8` over all tiles of a slide with H2D copies overlapped with compute."""
+    """Runs `model.extract_uint8` over all tiles of a slide.  H2D copies (pinned staging, copy stream) overlap compute, and
+    consecutive batches alternate between two compute lanes (stream + extractor workspace + device tile buffer each), so the
+    persistent convolution kernels of one batch fill the SMs the other leaves idle in partial waves and launch gaps."""
+
+    LANES = 2
 
     def __init__(self, model, batch_size=64, tile_hw=(256, 256), device=None):
         self.model = model
         self.bs = batch_size
         self.device = torch.device(device if device is not None else "cuda")
         h, w = tile_hw
+        n = self.LANES
         self.copy_stream = torch.cuda.Stream(device=self.device)
-        self.dev_buf = [torch.empty(batch_size, h, w, 3, dtype=torch.uint8, device=self.device) for _ in range(2)]
-        self.pin_buf = [torch.empty(batch_size, h, w, 3, dtype=torch.uint8).pin_memory() for _ in range(2)]
-        self.copied = [torch.cuda.Event() for _ in range(2)]
-        self.consumed = [torch.cuda.Event() for _ in range(2)]
+        self.lanes = [torch.cuda.Stream(device=self.device) for _ in range(n)]
+        self.dev_buf = [torch.empty(batch_size, h, w, 3, dtype=torch.uint8, device=self.device) for _ in range(n)]
+        self.pin_buf = [torch.empty(batch_size, h, w, 3, dtype=torch.uint8).pin_memory() for _ in range(n)]
+        self.copied = [torch.cuda.Event() for _ in range(n)]
+        self.consumed = [torch.cuda.Event() for _ in range(n)]
+        self.workspaces = [None] * n
         self.h2d_bytes = 0
         self.d2h_bytes = 0
+
+    def _workspace(self, slot, h, w):
+        from . import _lib
+        need = _lib.lib().sq_resnet50_workspace_bytes(self.bs, h, w)
+        if self.workspaces[slot] is None or self.workspaces[slot].numel() < need:
+            self.workspaces[slot] = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self.workspaces[slot]
 
     def __call__(self, tiles):
         """tiles: host uint8 [n, H, W, 3] (numpy array or CPU tensor, pinned or pageable) -> np.float32 [n, D]."""
@@ -53,28 +67,35 @@ class SlideExtractor:
             return np.zeros((0, 2048), dtype=np.float32)
         pinned = tiles.is_pinned()
         main = torch.cuda.current_stream(self.device)
-        out = None
+        out = torch.empty(n, 2048, dtype=torch.float32, device=self.device)
+        self.model._prepack()
+        for s in self.lanes:
+            s.wait_stream(main)
         nb = (n + self.bs - 1) // self.bs
+        L = self.LANES
         for b in range(nb):
             lo, hi = b * self.bs, min(n, (b + 1) * self.bs)
-            slot = b & 1
+            slot = b % L
             with torch.cuda.stream(self.copy_stream):
-                if b >= 2:
+                if b >= L:
                     self.copy_stream.wait_event(self.consumed[slot])    # device buffer free again
                 src = tiles[lo:hi]
                 if not pinned:
-                    if b >= 2:
+                    if b >= L:
                         self.copied[slot].synchronize()                 # staging buffer free again
                     self.pin_buf[slot][: hi - lo].copy_(src)
                     src = self.pin_buf[slot][: hi - lo]
                 self.dev_buf[slot][: hi - lo].copy_(src, non_blocking=True)
                 self.copied[slot].record(self.copy_stream)
-            main.wait_event(self.copied[slot])
-            if out is None:
-                out = torch.empty(n, 2048, dtype=torch.float32, device=self.device)
-            self.model.extract_uint8(self.dev_buf[slot][: hi - lo], out=out[lo:hi])
-            self.consumed[slot].record(main)
+            lane = self.lanes[slot]
+            with torch.cuda.stream(lane):
+                lane.wait_event(self.copied[slot])
+                buf = self.dev_buf[slot][: hi - lo]
+                self.model._run(buf, 0, hi - lo, buf.shape[1], buf.shape[2], out[lo:hi], workspace=self._workspace(slot, buf.shape[1], buf.shape[2]))
+                self.consumed[slot].record(lane)
             self.h2d_bytes += (hi - lo) * tiles[0].numel()
+        for s in self.lanes:
+            main.wait_stream(s)
         host = torch.empty(out.shape, dtype=torch.float32).pin_memory()
         host.copy_(out, non_blocking=True)
         main.synchronize()

@@ -66,6 +66,7 @@ class ResNet(nn.Module):
                 m.bias.data.zero_()
         self._packed = None          # (versions, packed_w, shifts)
         self._workspace = None
+        self._lanes = None           # [(stream, workspace)] for extract_many
 
     def _stage(self, planes, blocks, stride):
         down = None
@@ -109,7 +110,7 @@ class ResNet(nn.Module):
         self._packed = (key, packed_w, shifts)
         return packed_w, shifts
 
-    def _run(self, inp, kind, batch, H, W, out=None):
+    def _run(self, inp, kind, batch, H, W, out=None, workspace=None):
         if self.training:
             raise RuntimeError("sequoia_b200 ResNet implements eval-mode BatchNorm only; call .eval() "
                                "(the reference does: pre_processing/compute_features_hdf5.py:60)")
@@ -117,15 +118,48 @@ class ResNet(nn.Module):
         packed_w, shifts = self._prepack()
         L = _lib.lib()
         need = L.sq_resnet50_workspace_bytes(batch, H, W)
-        if self._workspace is None or self._workspace.numel() < need or self._workspace.device != inp.device:
-            self._workspace = torch.empty(need, dtype=torch.uint8, device=inp.device)
+        if workspace is not None:
+            if workspace.numel() < need:
+                raise ValueError("workspace too small")
+            ws = workspace
+        else:
+            if self._workspace is None or self._workspace.numel() < need or self._workspace.device != inp.device:
+                self._workspace = torch.empty(need, dtype=torch.uint8, device=inp.device)
+            ws = self._workspace
         if out is None:
             out = torch.empty(batch, 2048, dtype=torch.float32, device=inp.device)
         elif out.shape != (batch, 2048) or out.dtype != torch.float32 or not out.is_contiguous() or out.device != inp.device:
             raise ValueError("out must be a contiguous float32 [B,2048] tensor on the input's device")
         _lib.check(L.sq_resnet50_extract(_lib.ptr(inp), kind, batch, H, W, _lib.ptr(packed_w), _lib.ptr(shifts),
-                                         _lib.ptr(out), _lib.ptr(self._workspace), self._workspace.numel(),
+                                         _lib.ptr(out), _lib.ptr(ws), ws.numel(),
                                          _lib.stream_ptr()))
+        return out
+
+    @torch.no_grad()
+    def extract_many(self, patches, out=None, batch_size=64, lanes=2):
+        """All tiles of a slide resident on the device: uint8 [n,H,W,3] -> float32 [n,2048].  Batches alternate between
+        `lanes` CUDA streams with their own workspaces, so the persistent convolution kernels of one batch fill the SMs
+        the other batch leaves idle in partial waves, prologues and launch gaps."""
+        if patches.dim() != 4 or patches.shape[3] != 3 or patches.dtype != torch.uint8 or not patches.is_cuda:
+            raise ValueError("extract_many expects a CUDA uint8 [n,H,W,3] tensor")
+        patches = patches.contiguous()
+        n, H, W = patches.shape[0], patches.shape[1], patches.shape[2]
+        if out is None:
+            out = torch.empty(n, 2048, dtype=torch.float32, device=patches.device)
+        need = _lib.lib().sq_resnet50_workspace_bytes(min(batch_size, max(n, 1)), H, W)
+        if self._lanes is None or len(self._lanes) != lanes or self._lanes[0][1].numel() < need or self._lanes[0][1].device != patches.device:
+            self._lanes = [(torch.cuda.Stream(device=patches.device), torch.empty(need, dtype=torch.uint8, device=patches.device))
+                           for _ in range(lanes)]
+        self._prepack()
+        main = torch.cuda.current_stream(patches.device)
+        for s, _ in self._lanes:
+            s.wait_stream(main)
+        for i, b in enumerate(range(0, n, batch_size)):
+            s, ws = self._lanes[i % lanes]
+            with torch.cuda.stream(s):
+                self._run(patches[b:b + batch_size], 0, min(batch_size, n - b), H, W, out[b:b + batch_size], workspace=ws)
+        for s, _ in self._lanes:
+            main.wait_stream(s)
         return out
 
     # ------------------------------------------------------------------ reference surface

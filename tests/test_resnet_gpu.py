@@ -90,3 +90,23 @@ def test_throughput_report(capsys):
     ms = s.elapsed_time(e) / 10
     with capsys.disabled():
         print(f"\n[resnet timing] batch 64: {ms:.3f} ms -> {64 / ms * 1e3:.0f} patches/s")
+
+
+@pytest.mark.gpu
+def test_two_lane_extraction_is_bit_identical_to_sequential():
+    """extract_many / SlideExtractor alternate batches between two CUDA streams with separate workspaces; the features must
+    equal the one-batch-at-a-time result bit for bit (ragged last batch included)."""
+    from oracle import resnet50_oracle as O
+    from sequoia_pub_b200.extract import SlideExtractor
+    from sequoia_pub_b200.resnet import resnet50
+    m = resnet50().eval(); m.load_state_dict(O.make_state_dict(0)); m = m.cuda()
+    tiles = O.make_patches(21, 150)
+    seq = torch.cat([m.extract_uint8(tiles[b:b + 64].cuda()) for b in range(0, 150, 64)])
+    many = m.extract_many(tiles.cuda(), batch_size=64, lanes=2)
+    torch.cuda.synchronize()
+    assert torch.equal(many, seq)
+    ex = SlideExtractor(m, 64, (256, 256))
+    for src in (tiles, tiles.pin_memory(), tiles.numpy()):
+        got = ex(src)
+        assert got.shape == (150, 2048) and np.array_equal(got, seq.cpu().numpy())
+    assert ex(tiles[:0]).shape == (0, 2048)
