@@ -107,3 +107,47 @@ class FusedTrainer:
                                             C.c_void_p(m._w_hi.data_ptr() + off // 2), C.c_void_p(m._w_lo.data_ptr() + off // 2), e - b, self.lr,
                                             self.betas[0], self.betas[1], self.eps, self.wd, self.step_count, 1.0 / self.world,
                                             _lib.stream_ptr()))
+
+
+class HostBatchFeeder:
+    """Double-buffered host -> device feed for the training loop (the reference's DataLoader uses pin_memory=True and moves each
+    batch with `.to(model.device)`, src/main.py:120-135, src/vit.py:160-161): the H2D copy of batch i+1 runs on a copy stream
+    while step i computes.  Iterate over it to get (x, y) device tensors that are safe to use on the current stream."""
+
+    def __init__(self, batches, device, slots=2):
+        self.batches = batches                      # sequence of (x_host, y_host) float32 CPU tensors (ideally pinned)
+        self.device = torch.device(device)
+        self.slots = slots
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.bufs = [None] * slots
+        self.ready = [torch.cuda.Event() for _ in range(slots)]
+        self.free = [torch.cuda.Event() for _ in range(slots)]
+        self.h2d_bytes = 0
+
+    def _issue(self, i):
+        slot = i % self.slots
+        xh, yh = self.batches[i]
+        with torch.cuda.stream(self.copy_stream):
+            if i >= self.slots:
+                self.copy_stream.wait_event(self.free[slot])            # the step that used this slot has been enqueued and finished
+            if self.bufs[slot] is None or self.bufs[slot][0].shape != xh.shape or self.bufs[slot][1].shape != yh.shape:
+                self.bufs[slot] = (torch.empty(xh.shape, dtype=torch.float32, device=self.device),
+                                   torch.empty(yh.shape, dtype=torch.float32, device=self.device))
+            xd, yd = self.bufs[slot]
+            xd.copy_(xh, non_blocking=True)
+            yd.copy_(yh, non_blocking=True)
+            self.ready[slot].record(self.copy_stream)
+        self.h2d_bytes += xh.numel() * 4 + yh.numel() * 4
+
+    def __iter__(self):
+        n = len(self.batches)
+        main = torch.cuda.current_stream(self.device)
+        for i in range(min(self.slots - 1, n)):
+            self._issue(i)
+        for i in range(n):
+            if i + self.slots - 1 < n:
+                self._issue(i + self.slots - 1)
+            slot = i % self.slots
+            main.wait_event(self.ready[slot])
+            yield self.bufs[slot]
+            self.free[slot].record(main)

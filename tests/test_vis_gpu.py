@@ -192,3 +192,16 @@ def test_ragged_batches(B):
     x, _ = V.make_inputs(6, B, G, input_dim=D)
     with torch.no_grad():
         assert _rel(m(x.cuda()), V.forward(sd, x)) < TOL
+
+
+@pytest.mark.gpu
+def test_host_batch_feeder_delivers_batches_in_order():
+    from sequoia_pub_b200.train import HostBatchFeeder
+    g = torch.Generator().manual_seed(0)
+    batches = [(torch.randn(3, 100, 64, generator=g).pin_memory(), torch.randn(3, 7, generator=g).pin_memory()) for _ in range(5)]
+    seen = []
+    for xd, yd in HostBatchFeeder(batches, "cuda"):
+        seen.append((xd.cpu().clone(), yd.cpu().clone()))        # consumed on the current stream before the slot is reused
+    assert len(seen) == 5
+    for (xa, ya), (xb, yb) in zip(seen, batches):
+        assert torch.equal(xa, xb) and torch.equal(ya, yb)
