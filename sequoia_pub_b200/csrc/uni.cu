@@ -144,8 +144,64 @@ constexpr int AT_LD = 72;           // smem row stride (bf16): 144 B keeps ldmat
 constexpr int AT_WARPS = 7;         // 13 query tiles over 7 warps
 constexpr int AT_SMEM = 3 * AT_TP * AT_LD * 2;
 
+// One chunk of NT key tiles (8 keys each) starting at key tile NT0: scores, online-softmax update of (m, l, o), P V.
+template <int NT0, int NT>
+__device__ __forceinline__ void attn_chunk(const uint32_t (&qa)[4][4], const bf16* sk, const bf16* sv, int lane, int tq, float sl2,
+                                           float& m0, float& m1, float& l0, float& l1, float (&o)[8][4]) {
+    float s[NT][4];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+        s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+#pragma unroll
+        for (int kp = 0; kp < 2; ++kp) {
+            uint32_t kb[4];
+            ldsm_x4(kb, sk + ((NT0 + nt) * 8 + (lane & 7)) * AT_LD + kp * 32 + (lane >> 3) * 8);
+            mma_bf16_16816(s[nt], qa[kp * 2], kb[0], kb[1]);
+            mma_bf16_16816(s[nt], qa[kp * 2 + 1], kb[2], kb[3]);
+        }
+    }
+    float c0 = -INFINITY, c1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+        const int c = (NT0 + nt) * 8 + tq * 2;
+        if (c >= U_TOK) { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
+        if (c + 1 >= U_TOK) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
+        c0 = fmaxf(c0, fmaxf(s[nt][0], s[nt][1])); c1 = fmaxf(c1, fmaxf(s[nt][2], s[nt][3]));
+    }
+    c0 = fmaxf(c0, __shfl_xor_sync(0xffffffffu, c0, 1)); c0 = fmaxf(c0, __shfl_xor_sync(0xffffffffu, c0, 2));
+    c1 = fmaxf(c1, __shfl_xor_sync(0xffffffffu, c1, 1)); c1 = fmaxf(c1, __shfl_xor_sync(0xffffffffu, c1, 2));
+    const float n0 = fmaxf(m0, c0), n1 = fmaxf(m1, c1);            // every chunk holds at least one real key, so n0/n1 are finite
+    const float a0 = exp2f((m0 - n0) * sl2), a1 = exp2f((m1 - n1) * sl2);     // exp2(-inf) = 0 on the first chunk
+    m0 = n0; m1 = n1;
+    l0 *= a0; l1 *= a1;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) { o[nt][0] *= a0; o[nt][1] *= a0; o[nt][2] *= a1; o[nt][3] *= a1; }
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+        s[nt][0] = exp2f((s[nt][0] - m0) * sl2); s[nt][1] = exp2f((s[nt][1] - m0) * sl2);
+        s[nt][2] = exp2f((s[nt][2] - m1) * sl2); s[nt][3] = exp2f((s[nt][3] - m1) * sl2);
+        l0 += s[nt][0] + s[nt][1]; l1 += s[nt][2] + s[nt][3];
+    }
+#pragma unroll
+    for (int j = 0; j < NT / 2; ++j) {
+        uint32_t pa[4];
+        __nv_bfloat162 t;
+        t = __floats2bfloat162_rn(s[2 * j][0], s[2 * j][1]); pa[0] = *reinterpret_cast<uint32_t*>(&t);
+        t = __floats2bfloat162_rn(s[2 * j][2], s[2 * j][3]); pa[1] = *reinterpret_cast<uint32_t*>(&t);
+        t = __floats2bfloat162_rn(s[2 * j + 1][0], s[2 * j + 1][1]); pa[2] = *reinterpret_cast<uint32_t*>(&t);
+        t = __floats2bfloat162_rn(s[2 * j + 1][2], s[2 * j + 1][3]); pa[3] = *reinterpret_cast<uint32_t*>(&t);
+#pragma unroll
+        for (int np = 0; np < 4; ++np) {
+            uint32_t vb[4];
+            ldsm_x4_t(vb, sv + ((NT0 / 2 + j) * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * AT_LD + np * 16 + (lane >> 4) * 8);
+            mma_bf16_16816(o[np * 2], pa, vb[0], vb[1]);
+            mma_bf16_16816(o[np * 2 + 1], pa, vb[2], vb[3]);
+        }
+    }
+}
+
 // qkv: bf16 [B*197, 3*1024] = [q | k | v] x [head][64] per token (timm reshape (B,N,3,H,hd)); out: bf16 [B*197, 1024]
-__global__ void __launch_bounds__(AT_WARPS * 32) uni_attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out) {
+__global__ void __launch_bounds__(AT_WARPS * 32, 2) uni_attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out) {
     extern __shared__ __align__(16) uint8_t at_smem[];
     bf16* sq_ = reinterpret_cast<bf16*>(at_smem);
     bf16* sk = sq_ + AT_TP * AT_LD;
@@ -167,57 +223,15 @@ __global__ void __launch_bounds__(AT_WARPS * 32) uni_attention_kernel(const bf16
         uint32_t qa[4][4];
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) ldsm_x4(qa[ks], sq_ + (r0 + (lane & 7) + ((lane >> 3) & 1) * 8) * AT_LD + ks * 16 + (lane >> 4) * 8);
-        float s[26][4];
-#pragma unroll
-        for (int nt = 0; nt < 26; ++nt) {
-            s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-#pragma unroll
-            for (int kp = 0; kp < 2; ++kp) {
-                uint32_t kb[4];
-                ldsm_x4(kb, sk + (nt * 8 + (lane & 7)) * AT_LD + kp * 32 + (lane >> 3) * 8);
-                mma_bf16_16816(s[nt], qa[kp * 2], kb[0], kb[1]);
-                mma_bf16_16816(s[nt], qa[kp * 2 + 1], kb[2], kb[3]);
-            }
-        }
-        // mask the padded keys, row max / sum over the quad
-        float m0 = -INFINITY, m1 = -INFINITY;
-#pragma unroll
-        for (int nt = 0; nt < 26; ++nt) {
-            const int c = nt * 8 + tq * 2;
-            if (c >= U_TOK) { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
-            if (c + 1 >= U_TOK) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
-            m0 = fmaxf(m0, fmaxf(s[nt][0], s[nt][1])); m1 = fmaxf(m1, fmaxf(s[nt][2], s[nt][3]));
-        }
-        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
-        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
-        float l0 = 0.f, l1 = 0.f;
-#pragma unroll
-        for (int nt = 0; nt < 26; ++nt) {
-            s[nt][0] = exp2f((s[nt][0] - m0) * sl2); s[nt][1] = exp2f((s[nt][1] - m0) * sl2);
-            s[nt][2] = exp2f((s[nt][2] - m1) * sl2); s[nt][3] = exp2f((s[nt][3] - m1) * sl2);
-            l0 += s[nt][0] + s[nt][1]; l1 += s[nt][2] + s[nt][3];
-        }
-        l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-        l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
         float o[8][4];
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f;
-#pragma unroll
-        for (int j = 0; j < 13; ++j) {
-            uint32_t pa[4];
-            __nv_bfloat162 t;
-            t = __floats2bfloat162_rn(s[2 * j][0], s[2 * j][1]); pa[0] = *reinterpret_cast<uint32_t*>(&t);
-            t = __floats2bfloat162_rn(s[2 * j][2], s[2 * j][3]); pa[1] = *reinterpret_cast<uint32_t*>(&t);
-            t = __floats2bfloat162_rn(s[2 * j + 1][0], s[2 * j + 1][1]); pa[2] = *reinterpret_cast<uint32_t*>(&t);
-            t = __floats2bfloat162_rn(s[2 * j + 1][2], s[2 * j + 1][3]); pa[3] = *reinterpret_cast<uint32_t*>(&t);
-#pragma unroll
-            for (int np = 0; np < 4; ++np) {
-                uint32_t vb[4];
-                ldsm_x4_t(vb, sv + (j * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * AT_LD + np * 16 + (lane >> 4) * 8);
-                mma_bf16_16816(o[np * 2], pa, vb[0], vb[1]);
-                mma_bf16_16816(o[np * 2 + 1], pa, vb[2], vb[3]);
-            }
-        }
+        float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+        // keys in two chunks (112 + 96) with an online softmax: halves the score registers so that two CTAs fit on an SM
+        attn_chunk<0, 14>(qa, sk, sv, lane, tq, sl2, m0, m1, l0, l1, o);
+        attn_chunk<14, 12>(qa, sk, sv, lane, tq, sl2, m0, m1, l0, l1, o);
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
         const float i0 = 1.0f / l0, i1 = 1.0f / l1;
         bf16* ob = out + (long long)b * U_TOK * U_DIM + hd * U_HD;
 #pragma unroll
