@@ -257,6 +257,8 @@ class ViS(nn.Module, PyTorchModelHubMixin):
         if x.device != self._flat.device or x.dtype != torch.float32:
             raise ValueError("ViS.forward expects a float32 tensor on the model's CUDA device")
         B = x.shape[0]
+        if B == 0:
+            return torch.empty(0, cfg.num_outputs, dtype=torch.float32, device=x.device), None
         x = x.reshape(B, -1, x.shape[-1]).contiguous()            # rearrange 'b ... d -> b (...) d' (tformer_lin.py:100)
         if x.shape[1] != cfg.num_clusters or x.shape[2] != cfg.input_dim:
             raise ValueError(f"expected [B, {cfg.num_clusters}, {cfg.input_dim}] cluster features, got {tuple(x.shape)}")
@@ -335,6 +337,7 @@ class FusedAdamW(torch.optim.Optimizer):
         self._token = None
         self._m = self._v = None
         self._step = 0
+        self._step_t = torch.tensor(0.0)          # shared by every per-parameter state entry (torch keeps one per tensor)
 
     def _bind(self):
         ps = self.param_groups[0]["params"]
@@ -358,7 +361,7 @@ class FusedAdamW(torch.optim.Optimizer):
             self._bound_params, self._old_split, self._old_chunks = list(model._params), model._split_sizes, model._param_chunks
             self._token = model._flat_token
             for p, mv, vv in zip(model._params, model._split_views(self._m), model._split_views(self._v)):
-                self.state[p] = {"step": torch.tensor(float(self._step)), "exp_avg": mv, "exp_avg_sq": vv}
+                self.state[p] = {"step": self._step_t, "exp_avg": mv, "exp_avg_sq": vv}
         self._model_ref = weakref.ref(model)
         return model
 
@@ -389,6 +392,7 @@ class FusedAdamW(torch.optim.Optimizer):
             torch._foreach_copy_(views, [p.grad if p.grad is not None else torch.zeros_like(p) for p in model._params])
         grp = self.param_groups[0]
         self._step += 1
+        self._step_t.fill_(float(self._step))
         _lib.check(_lib.lib().sq_adamw_flat(_lib.ptr(model._flat), _lib.ptr(gbuf), _lib.ptr(self._m), _lib.ptr(self._v),
                                             _lib.ptr(model._w_hi), _lib.ptr(model._w_lo), model._total, grp["lr"], grp["betas"][0],
                                             grp["betas"][1], grp["eps"], grp["weight_decay"], self._step, self.grad_scale,

@@ -205,3 +205,34 @@ def test_host_batch_feeder_delivers_batches_in_order():
     assert len(seen) == 5
     for (xa, ya), (xb, yb) in zip(seen, batches):
         assert torch.equal(xa, xb) and torch.equal(ya, yb)
+
+
+@pytest.mark.gpu
+def test_error_paths_and_other_shapes():
+    """Wrong inputs fail loudly with the library's message; a non-default token count / head count still matches the oracle."""
+    from oracle import vis_oracle as V
+    from sequoia_pub_b200.tformer_lin import ViS, FusedAdamW
+    D, G, depth, H, N = 512, 33, 1, 4, 37
+    sd = V.make_state_dict(7, G, input_dim=D, depth=depth, nheads=H, num_clusters=N)
+    m = ViS(num_outputs=G, input_dim=D, depth=depth, nheads=H, dimensions_f=64, dimensions_s=64, dimensions_c=64, num_clusters=N)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().train()
+    x, y = V.make_inputs(8, 3, G, input_dim=D, num_clusters=N)
+    pred = m(x.cuda())
+    torch.nn.functional.mse_loss(pred, y.cuda()).backward()
+    _, want, grads = V.loss_and_grads(sd, x, y)
+    assert _rel(pred, want) < TOL
+    assert max(_rel(p.grad, grads[n]) for n, p in m.named_parameters()) < TOL
+    with pytest.raises(ValueError):
+        m(torch.zeros(2, N + 1, D, device="cuda"))                       # wrong token count
+    with pytest.raises(ValueError):
+        m(torch.zeros(2, N, D, device="cuda", dtype=torch.float64))      # wrong dtype
+    with pytest.raises(NotImplementedError):
+        ViS(num_outputs=4, input_dim=D, depth=1, nheads=2, dimensions_f=32, dimensions_s=64, dimensions_c=64)
+    with pytest.raises(NotImplementedError):
+        FusedAdamW(list(m.parameters()), amsgrad=True)
+    opt = FusedAdamW(list(m.parameters()), lr=1e-3, weight_decay=0.0)
+    opt.step()
+    assert float(next(iter(opt.state.values()))["step"]) == 1.0
+    empty = m.eval()(torch.zeros(0, N, D, device="cuda"))
+    assert tuple(empty.shape) == (0, G)
