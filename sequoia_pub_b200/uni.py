@@ -77,6 +77,7 @@ class VisionTransformer(nn.Module):
         self.depth = depth
         self._packed = None
         self._ws = None
+        self._lanes = None           # [(stream, workspace)] for extract_many
 
     def _tensors(self):
         t = [self.cls_token, self.pos_embed, self.patch_embed.proj.weight, self.patch_embed.proj.bias]
@@ -104,19 +105,51 @@ class VisionTransformer(nn.Module):
         self._packed = (key, pw, pv)
         return pw, pv
 
-    def _run(self, inp, kind, batch, out=None):
+    def _run(self, inp, kind, batch, out=None, workspace=None):
         if self.training:
             raise RuntimeError("inference only: call .eval() (compute_features_hdf5.py:68)")
         _lib.require_device()
         pw, pv = self._prepack()
         L = _lib.lib()
         need = L.sq_vitl16_workspace_bytes(batch)
-        if self._ws is None or self._ws.numel() < need or self._ws.device != inp.device:
-            self._ws = torch.empty(need, dtype=torch.uint8, device=inp.device)
+        if workspace is not None:
+            if workspace.numel() < need:
+                raise ValueError("workspace too small")
+            ws = workspace
+        else:
+            if self._ws is None or self._ws.numel() < need or self._ws.device != inp.device:
+                self._ws = torch.empty(need, dtype=torch.uint8, device=inp.device)
+            ws = self._ws
         if out is None:
             out = torch.empty(batch, 1024, dtype=torch.float32, device=inp.device)
-        _lib.check(L.sq_vitl16_extract(_lib.ptr(inp), kind, batch, self.depth, _lib.ptr(pw), _lib.ptr(pv), _lib.ptr(out), _lib.ptr(self._ws),
-                                       self._ws.numel(), _lib.stream_ptr()))
+        _lib.check(L.sq_vitl16_extract(_lib.ptr(inp), kind, batch, self.depth, _lib.ptr(pw), _lib.ptr(pv), _lib.ptr(out), _lib.ptr(ws),
+                                       ws.numel(), _lib.stream_ptr()))
+        return out
+
+    @torch.no_grad()
+    def extract_many(self, patches, out=None, batch_size=64, lanes=2):
+        """All tiles of a slide resident on the device: uint8 [n,224,224,3] -> float32 [n,1024]; batches alternate between
+        `lanes` CUDA streams with their own workspaces (same scheme as ResNet.extract_many)."""
+        if patches.dim() != 4 or tuple(patches.shape[1:]) != (224, 224, 3) or patches.dtype != torch.uint8 or not patches.is_cuda:
+            raise ValueError("extract_many expects a CUDA uint8 [n,224,224,3] tensor")
+        patches = patches.contiguous()
+        n = patches.shape[0]
+        if out is None:
+            out = torch.empty(n, 1024, dtype=torch.float32, device=patches.device)
+        need = _lib.lib().sq_vitl16_workspace_bytes(min(batch_size, max(n, 1)))
+        if self._lanes is None or len(self._lanes) != lanes or self._lanes[0][1].numel() < need or self._lanes[0][1].device != patches.device:
+            self._lanes = [(torch.cuda.Stream(device=patches.device), torch.empty(need, dtype=torch.uint8, device=patches.device))
+                           for _ in range(lanes)]
+        self._prepack()
+        main = torch.cuda.current_stream(patches.device)
+        for s, _ in self._lanes:
+            s.wait_stream(main)
+        for i, b in enumerate(range(0, n, batch_size)):
+            s, ws = self._lanes[i % lanes]
+            with torch.cuda.stream(s):
+                self._run(patches[b:b + batch_size], 0, min(batch_size, n - b), out[b:b + batch_size], workspace=ws)
+        for s, _ in self._lanes:
+            main.wait_stream(s)
         return out
 
     @torch.no_grad()

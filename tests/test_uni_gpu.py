@@ -63,3 +63,15 @@ def test_throughput_report(capsys):
     ms = s.elapsed_time(e) / 3
     with capsys.disabled():
         print(f"\n[uni timing] batch 64: {ms:.2f} ms -> {64 / ms * 1e3:.0f} patches/s ({123.107e9 * 64 / ms / 1e9:.0f} TFLOP/s algorithmic)")
+
+
+@pytest.mark.gpu
+def test_two_lane_extraction_is_bit_identical():
+    from oracle import uni_oracle as U
+    from sequoia_pub_b200.uni import VisionTransformer
+    m = VisionTransformer(depth=2).eval()
+    m.load_state_dict(U.make_state_dict(2, depth=2))
+    m = m.cuda()
+    tiles = U.make_patches(9, 11).cuda()
+    seq = torch.cat([m.extract_uint8(tiles[b:b + 4]) for b in range(0, 11, 4)])
+    assert torch.equal(m.extract_many(tiles, batch_size=4, lanes=2), seq)
