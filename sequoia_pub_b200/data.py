@@ -1,0 +1,54 @@
+"""Device-resident replacement for the training data path: `SuperTileRNADataset.__getitem__`
+(src/read_data.py:38-56) opens one HDF5 file and gathers ~20 k `rna_*` columns from a pandas row PER SAMPLE, and
+`DataLoader(..., collate_fn=custom_collate_fn)` (src/main.py:120-135, src/utils.py:10-18) stacks them on the host every
+step; once the train step takes milliseconds that is the bottleneck.  Here every slide's `cluster_features` [100, D] and
+RNA vector [G] are loaded ONCE (any loader: the reference Dataset itself works), kept on the device, and batches are
+index gathers on the GPU.
+
+Semantics kept: samples whose features are `None` (unreadable file) are dropped like `custom_collate_fn` does; a batch is
+`(features [B,100,D], rna [B,G], wsi_file_names, tcga_projects)` in the reference's order; `shuffle=True` draws a fresh
+permutation per epoch like `DataLoader(shuffle=True)`; the last, smaller batch is kept (drop_last=False).
+"""
+import torch
+
+
+class DeviceSlideDataset:
+    def __init__(self, samples, device="cuda"):
+        """samples: iterable of (features [100,D] or None, rna [G], wsi_file_name, tcga_project) — e.g. a
+        `SuperTileRNADataset` — read exactly once."""
+        feats, rna, self.names, self.projects = [], [], [], []
+        self.dropped = []
+        for f, r, name, proj in samples:
+            if f is None:                      # custom_collate_fn: remove bad entries
+                self.dropped.append(name)
+                continue
+            feats.append(torch.as_tensor(f, dtype=torch.float32))
+            rna.append(torch.as_tensor(r, dtype=torch.float32))
+            self.names.append(name)
+            self.projects.append(proj)
+        if not feats:
+            raise ValueError("no readable samples")
+        self.device = torch.device(device)
+        self.features = torch.stack(feats).to(self.device)          # [n, 100, D]   (0.8 MB per slide at D = 2048)
+        self.rna = torch.stack(rna).to(self.device)                 # [n, G]
+        self.num_genes = self.rna.shape[1]
+        self.feature_dim = self.features.shape[2]
+
+    def __len__(self):
+        return self.features.shape[0]
+
+    def batches(self, batch_size, shuffle=False, generator=None, rank=0, world=1):
+        """Yields (features, rna, names, projects); with world > 1 every rank gets an equal slice of each global batch
+        (global batches that cannot be split evenly are truncated to a multiple of `world`)."""
+        n = len(self)
+        order = torch.randperm(n, generator=generator) if shuffle else torch.arange(n)
+        for lo in range(0, n, batch_size):
+            idx = order[lo:lo + batch_size]
+            if world > 1:
+                per = idx.numel() // world
+                if per == 0:
+                    continue
+                idx = idx[rank * per:(rank + 1) * per]
+            di = idx.to(self.device)
+            yield (self.features.index_select(0, di), self.rna.index_select(0, di), [self.names[i] for i in idx.tolist()],
+                   [self.projects[i] for i in idx.tolist()])

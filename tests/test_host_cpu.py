@@ -31,3 +31,23 @@ def test_product_modules_refuse_to_run_without_a_gpu():
         KMeans(n_clusters=100, random_state=0).fit(np.zeros((200, 64), np.float32))
     with pytest.raises(RuntimeError):
         metrics.step_metrics(torch.zeros(4, 8), torch.zeros(4, 8))
+
+
+def test_device_slide_dataset_semantics():
+    """f-2: preloaded data path keeps the reference's sample order, drops unreadable samples like custom_collate_fn, and
+    shards global batches evenly across ranks (runs on CPU tensors: it is indexing only)."""
+    import torch
+    from sequoia_pub_b200.data import DeviceSlideDataset
+    g = torch.Generator().manual_seed(0)
+    samples = [(torch.randn(100, 16, generator=g) if i != 3 else None, torch.randn(7, generator=g), f"wsi{i}", "TCGA-X") for i in range(10)]
+    ds = DeviceSlideDataset(samples, device="cpu")
+    assert len(ds) == 9 and ds.dropped == ["wsi3"] and ds.num_genes == 7 and ds.feature_dim == 16
+    got = list(ds.batches(4))
+    assert [b[0].shape[0] for b in got] == [4, 4, 1]
+    assert got[0][2] == ["wsi0", "wsi1", "wsi2", "wsi4"]
+    assert torch.equal(got[0][0][3], samples[4][0]) and torch.equal(got[0][1][3], samples[4][1])
+    e1 = [b[2] for b in ds.batches(4, shuffle=True, generator=torch.Generator().manual_seed(1))]
+    e2 = [b[2] for b in ds.batches(4, shuffle=True, generator=torch.Generator().manual_seed(1))]
+    assert e1 == e2 and sorted(sum(e1, [])) == sorted(ds.names)
+    r0 = list(ds.batches(4, rank=0, world=2)); r1 = list(ds.batches(4, rank=1, world=2))
+    assert [b[0].shape[0] for b in r0] == [2, 2] and r0[0][2] + r1[0][2] == got[0][2]
