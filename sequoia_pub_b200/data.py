@@ -9,7 +9,33 @@ Semantics kept: samples whose features are `None` (unreadable file) are dropped 
 `(features [B,100,D], rna [B,G], wsi_file_names, tcga_projects)` in the reference's order; `shuffle=True` draws a fresh
 permutation per epoch like `DataLoader(shuffle=True)`; the last, smaller batch is kept (drop_last=False).
 """
+import os
+
+import numpy as np
 import torch
+
+from . import hdf5
+
+
+def read_samples(df, features_path, feature_use="cluster_features", prefer_h5py=True):
+    """The samples `SuperTileRNADataset(df, features_path, feature_use)[i]` would return (src/read_data.py:38-56), read in
+    one pass: the `rna_*` columns are gathered ONCE for the whole frame instead of a 20k-column `row[[...]]` selection per
+    item, and every `<features_path>/<tcga_project>/<wsi>/<wsi>.h5` is opened once.  Unreadable files print the exception and
+    the path and yield `features=None` like the reference (:52-55)."""
+    rna_cols = [c for c in df.columns if "rna_" in c]                           # :42
+    rna = np.array(df[rna_cols].to_numpy(dtype=np.float32))
+    for i, (name, proj) in enumerate(zip(df["wsi_file_name"], df["tcga_project"])):
+        path = os.path.join(features_path, proj, name, name + ".h5")            # :40-41
+        try:
+            if "GTEX" not in path:
+                path = path.replace(".svs", "")                                 # :45-46
+            with hdf5.open_file(path, "r", prefer_h5py) as f:
+                feats = torch.as_tensor(f[feature_use][:], dtype=torch.float32)
+        except Exception as e:
+            print(e)
+            print(path)
+            feats = None
+        yield feats, torch.from_numpy(rna[i]), name, proj
 
 
 class DeviceSlideDataset:
@@ -33,6 +59,10 @@ class DeviceSlideDataset:
         self.rna = torch.stack(rna).to(self.device)                 # [n, G]
         self.num_genes = self.rna.shape[1]
         self.feature_dim = self.features.shape[2]
+
+    @classmethod
+    def from_files(cls, df, features_path, feature_use="cluster_features", device="cuda", prefer_h5py=True):
+        return cls(read_samples(df, features_path, feature_use, prefer_h5py), device)
 
     def __len__(self):
         return self.features.shape[0]

@@ -9,9 +9,10 @@
   * `run_slides`     = the outer loops with the reference's per-slide `try/except -> print -> continue` isolation
                         (compute_features_hdf5.py:141-144, kmean_features.py:107-113), sharded over ranks like --start/--end.
 
-HDF5 access uses h5py exactly like the reference (it is the reference's dependency, not ours); h5py is not installed in the
-build image, so the in-memory functions (`extract_tiles`, `reduce_features`) carry the tests and the file functions raise a
-clear ImportError without it.  File layout kept: patch file = one uint8 [256,256,3] dataset per tile named "{x}_{y}"
+HDF5 access goes through `hdf5.open_file`: h5py when it is importable (the reference's own dependency), else the built-in
+codec of `sequoia_pub_b200/hdf5.py` (version-0 superblock, symbol-table root group, contiguous datasets: what h5py emits
+with defaults).  With the built-in codec the tiles of a slide are read straight into one pinned host buffer
+(`File.read_many`, one preadv per tile) instead of 4096 dataset objects + `np.stack`.  File layout kept: patch file = one uint8 [256,256,3] dataset per tile named "{x}_{y}"
 (patch_gen_hdf5.py:119-120); feature file `<feature_path>/<project>/<WSI>/<WSI>.h5` with "resnet_features"/"uni_features"
 [n, D] float32 and "cluster_features" [100, D] float32 (read back by src/read_data.py:47-49).
 """
@@ -20,18 +21,29 @@ import random as _random
 
 import numpy as np
 
+from . import hdf5
 from .dist import shard_slides
 from .extract import SlideExtractor, select_keys
 from .kmeans import KMeans
 
 
-def _h5py():
-    try:
-        import h5py
-        return h5py
-    except ImportError as e:  # pragma: no cover - depends on the deployment image
-        raise ImportError("the HDF5 file functions need h5py (the reference's own dependency); the in-memory functions "
-                          "extract_tiles / reduce_features do not") from e
+def read_tiles(f, keys, pinned=True):
+    """Tiles `keys` of an open patch file as one uint8 [n, H, W, 3] host array (compute_features_hdf5.py:117 `f_read[key][:]`
+    for every key).  Built-in codec: read in place into a (pinned) torch buffer; h5py: per-dataset reads."""
+    if not keys:
+        return np.zeros((0, 256, 256, 3), dtype=np.uint8)
+    shape = tuple(f[keys[0]].shape)
+    if isinstance(f, hdf5.File):
+        import torch
+        buf = torch.empty((len(keys),) + shape, dtype=torch.uint8)
+        if pinned and torch.cuda.is_available():
+            buf = buf.pin_memory()
+        f.read_many(keys, buf)
+        return buf
+    out = np.empty((len(keys),) + shape, dtype=np.uint8)
+    for i, k in enumerate(keys):
+        f[k].read_direct(out[i])
+    return out
 
 
 def extract_tiles(model, tiles, batch_size=64, extractor=None):
@@ -47,21 +59,20 @@ def reduce_features(features, num_clusters=100):
     return KMeans(n_clusters=num_clusters, random_state=0).fit(features).cluster_features_
 
 
-def extract_slide(model, patch_file, feature_file, feat_type="resnet", max_patch_number=4000, rng=_random, batch_size=64):
-    h5py = _h5py()
-    with h5py.File(patch_file, "r") as f:
+def extract_slide(model, patch_file, feature_file, feat_type="resnet", max_patch_number=4000, rng=_random, batch_size=64,
+                  extractor=None, prefer_h5py=True):
+    with hdf5.open_file(patch_file, "r", prefer_h5py) as f:
         keys = select_keys(list(f.keys()), max_patch_number, rng)          # :111-113
-        tiles = np.stack([f[k][:] for k in keys])                          # :117
-    feats = extract_tiles(model, tiles, batch_size)
-    os.makedirs(os.path.dirname(feature_file), exist_ok=True)
-    with h5py.File(feature_file, "w") as f:                                 # :134-136
+        tiles = read_tiles(f, keys)                                        # :117
+    feats = extract_tiles(model, tiles, batch_size, extractor)
+    os.makedirs(os.path.dirname(feature_file) or ".", exist_ok=True)
+    with hdf5.open_file(feature_file, "w", prefer_h5py) as f:               # :134-136
         f.create_dataset(f"{feat_type}_features", data=feats)
     return feats
 
 
-def reduce_slide(feature_file, num_clusters=100, feat_name="resnet_features"):
-    h5py = _h5py()
-    with h5py.File(feature_file, "r+") as f:                                # :75
+def reduce_slide(feature_file, num_clusters=100, feat_name="resnet_features", prefer_h5py=True):
+    with hdf5.open_file(feature_file, "r+", prefer_h5py) as f:              # :75
         if "cluster_features" in f.keys():                                  # :91-94
             return None
         feats = f[feat_name][:]

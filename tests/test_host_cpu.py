@@ -51,3 +51,37 @@ def test_device_slide_dataset_semantics():
     assert e1 == e2 and sorted(sum(e1, [])) == sorted(ds.names)
     r0 = list(ds.batches(4, rank=0, world=2)); r1 = list(ds.batches(4, rank=1, world=2))
     assert [b[0].shape[0] for b in r0] == [2, 2] and r0[0][2] + r1[0][2] == got[0][2]
+
+
+def test_device_dataset_from_feature_files(tmp_path, capsys):
+    """f-1 + f-2: `read_samples` restates SuperTileRNADataset.__getitem__ (src/read_data.py:38-56) over feature files written
+    by the built-in codec: rna_* column gather, '.svs' stripped from TCGA paths, unreadable slides -> None -> dropped."""
+    import numpy as np
+    import pandas as pd
+    import torch
+    from sequoia_pub_b200 import hdf5
+    from sequoia_pub_b200.data import DeviceSlideDataset, read_samples
+    rs = np.random.RandomState(0)
+    names = ["TCGA-A.svs", "TCGA-B", "TCGA-C", "GTEX-D"]
+    df = pd.DataFrame({"wsi_file_name": names, "tcga_project": ["P1", "P1", "P2", "P2"], "patient_id": list("abcd"),
+                       "rna_G1": rs.rand(4), "rna_G2": rs.rand(4), "other": rs.rand(4), "rna_G3": rs.rand(4)})
+    feats = {}
+    for name, proj in zip(names, df.tcga_project):
+        if name == "TCGA-C":
+            continue                                              # no feature file: unreadable sample
+        stem = name.replace(".svs", "")
+        d = tmp_path / proj / stem
+        d.mkdir(parents=True)
+        feats[name] = rs.rand(100, 32).astype(np.float32)
+        with hdf5.File(d / (stem + ".h5"), "w") as f:
+            f.create_dataset("resnet_features", data=rs.rand(130, 32).astype(np.float32))
+            f.create_dataset("cluster_features", data=feats[name])
+    samples = list(read_samples(df, str(tmp_path), prefer_h5py=False))
+    assert [s[2] for s in samples] == names and samples[2][0] is None
+    assert "TCGA-C" in capsys.readouterr().out
+    for (f, r, name, proj), row in zip(samples, df.itertuples()):
+        assert np.allclose(r.numpy(), [row.rna_G1, row.rna_G2, row.rna_G3]) and r.dtype == torch.float32
+        if f is not None:
+            assert np.array_equal(f.numpy(), feats[name])
+    ds = DeviceSlideDataset.from_files(df, str(tmp_path), device="cpu", prefer_h5py=False)
+    assert len(ds) == 3 and ds.dropped == ["TCGA-C"] and ds.feature_dim == 32 and ds.num_genes == 3
