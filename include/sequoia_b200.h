@@ -163,6 +163,35 @@ SQ_API int sq_mse_fwd_bwd(const float* pred, const float* target, int batch, int
 SQ_API int sq_adamw_flat(float* p, const float* g, float* m, float* v, void* p_hi, void* p_lo, long long n, float lr, float beta1,
                          float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream);
 
+/* ------------------------------------------------------------------ ViT softmax-attention aggregator
+ * Replaces ViT.forward (src/vit.py:107-116 and everything it calls: Attention :62-74, FeedForward :47-48, Transformer
+ * :87-91) and its autograd backward for the reference's `--model_type vit` baseline (src/main.py:141-143,161-163:
+ * dim_head = 64, mlp_dim = 2048, to_qkv / to_out without bias).  Same stage contract as sq_vis_*: sq_mse_fwd_bwd and
+ * sq_adamw_flat serve both models. */
+typedef struct sq_vit_config {
+    int dim;           /* D: feature dimension (2048 / 1024); multiple of 64 */
+    int depth;         /* L */
+    int heads;         /* H, dim_head = 64 */
+    int num_clusters;  /* N tokens per slide, <= 128 */
+    int num_outputs;   /* G genes */
+    int mlp_dim;       /* hidden width of the feed-forward block; multiple of 64 */
+} sq_vit_config;
+
+/* Flat fp32 parameter buffer, element offsets in order: pos_emb1D [N,D]; per layer 10 entries {0.norm.weight [D],
+ * 0.norm.bias, 0.to_qkv.weight [3*H*64, D], 0.to_out.weight [D, H*64], 1.net.0.weight [D], 1.net.0.bias,
+ * 1.net.1.weight [mlp, D], 1.net.1.bias, 1.net.3.weight [D, mlp], 1.net.3.bias}; linear_head.0.weight, .0.bias,
+ * .1.weight [G,D], .1.bias. */
+SQ_API int sq_vit_param_table_len(const sq_vit_config* cfg);
+SQ_API int sq_vit_param_layout(const sq_vit_config* cfg, long long* offsets, int n, long long* total_elems);
+SQ_API size_t sq_vit_act_bytes(const sq_vit_config* cfg, int batch);
+SQ_API size_t sq_vit_bwd_bytes(const sq_vit_config* cfg, int batch);
+SQ_API int sq_vit_forward(const sq_vit_config* cfg, const float* params, const void* w_hi, const void* w_lo, const float* x,
+                          int batch, float* pred, void* act, size_t act_bytes, void* stream);
+/* Stages as in sq_vis_backward: `depth` = regression head, l < depth = transformer layer l (stage 0 also pos_emb1D, dx). */
+SQ_API int sq_vit_backward(const sq_vit_config* cfg, const float* params, const void* w_hi, const void* w_lo, const float* dpred,
+                           int batch, void* act, size_t act_bytes, float* grads, float* dx, void* scratch, size_t scratch_bytes,
+                           int stage_hi, int stage_lo, void* stream);
+
 /* ------------------------------------------------------------------ per-step training metrics
  * Replaces sklearn mean_absolute_error + he2rna.compute_correlations of the training loop (src/vit.py:167-168,
  * src/he2rna.py:140-149).  labels, preds: fp32 [batch, num_outputs] (device).  out3 (device): {mean absolute error,

@@ -42,6 +42,12 @@ class VisConfig(C.Structure):
     _fields_ = [("input_dim", c_int), ("depth", c_int), ("nheads", c_int), ("num_clusters", c_int), ("num_outputs", c_int)]
 
 
+class VitConfig(C.Structure):
+    """Mirror of `sq_vit_config` (the first field is `dim` in C; named like VisConfig's so the shared host code reads both)."""
+    _fields_ = [("input_dim", c_int), ("depth", c_int), ("nheads", c_int), ("num_clusters", c_int), ("num_outputs", c_int),
+                ("mlp_dim", c_int)]
+
+
 # name -> (restype, argtypes); kept in one table so tests can check the export list against the header
 SIGNATURES = {
     "sq_version": (c_int, []),
@@ -68,6 +74,14 @@ SIGNATURES = {
     "sq_vis_forward": (c_int, [C.POINTER(VisConfig), c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                c_size_t, c_void_p]),
     "sq_vis_backward": (c_int, [C.POINTER(VisConfig), c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_size_t,
+                                c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p]),
+    "sq_vit_param_table_len": (c_int, [C.POINTER(VitConfig)]),
+    "sq_vit_param_layout": (c_int, [C.POINTER(VitConfig), C.POINTER(c_ll), c_int, C.POINTER(c_ll)]),
+    "sq_vit_act_bytes": (c_size_t, [C.POINTER(VitConfig), c_int]),
+    "sq_vit_bwd_bytes": (c_size_t, [C.POINTER(VitConfig), c_int]),
+    "sq_vit_forward": (c_int, [C.POINTER(VitConfig), c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                               c_size_t, c_void_p]),
+    "sq_vit_backward": (c_int, [C.POINTER(VitConfig), c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_size_t,
                                 c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p]),
     "sq_mse_fwd_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "sq_adamw_flat": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_float, c_float, c_float,

@@ -108,19 +108,17 @@ class _ViSFunction(torch.autograd.Function):
         return (None, dx.view(ctx.x_shape) if dx is not None else None, *grads)
 
 
-class ViS(nn.Module, PyTorchModelHubMixin):
-    def __init__(self, num_outputs, input_dim, depth, nheads, dimensions_f, dimensions_s, dimensions_c, num_clusters=100,
-                 device='cuda:0'):
-        super().__init__()
-        if not (dimensions_f == dimensions_s == dimensions_c == 64):
-            raise NotImplementedError("sequoia_b200 ViS implements dimensions_f = dimensions_s = dimensions_c = 64 "
-                                      "(the values hard-coded by the reference, src/main.py:147,167)")
-        # same construction order as the reference, so the same torch seed gives the same initial weights
-        self.pos_emb1D = nn.Parameter(torch.randn(num_clusters, input_dim))
-        self.transformer = SummaryTransformer(input_dim, depth, nheads, dimensions_f, dimensions_s, dimensions_c)
-        self.to_latent = nn.Identity()
-        self.linear_head = nn.Sequential(nn.LayerNorm(input_dim), nn.Linear(input_dim, num_outputs))
-        self.device = device
+class _FlatAggregator:
+    """Host side shared by the two aggregators (`ViS` here, `ViT` in vit.py): the nn.Parameters are views of ONE flat fp32
+    buffer laid out by the C library, forward/backward are one C call each (stage by stage for the trainer), gradients come
+    back as views of a flat gradient buffer.  Subclasses provide `_config()`, `_slots(cfg)`, the names of their C entry
+    points (`_C`) and the number of layout-table entries per layer (`_PER_LAYER`)."""
+
+    _C = {}
+    _PER_LAYER = 0
+    _NAME = "model"
+
+    def _init_flat_state(self):
         self._flat = None            # fp32 flat parameter buffer the nn.Parameters are views of
         self._flat_token = 0         # bumped on every re-layout
         self._w_hi = self._w_lo = None
@@ -128,6 +126,24 @@ class ViS(nn.Module, PyTorchModelHubMixin):
         self._gbufs = [None, None]   # flat gradient buffers (alternated so accumulation into .grad stays correct)
         self._act_cache = None
         self._scratch = None
+
+    def _layout_table(self, cfg):
+        L = _lib.lib()
+        n = getattr(L, self._C["table_len"])(C.byref(cfg))
+        if n < 0:
+            _lib.check(n)
+        table = (C.c_longlong * n)()
+        total = C.c_longlong()
+        _lib.check(getattr(L, self._C["layout"])(C.byref(cfg), table, n, C.byref(total)))
+        return list(table), total.value
+
+    def _stage_ranges(self):
+        """[begin, end) element ranges of the flat buffer per backward stage: l < depth = layer l (stage 0 also holds
+        pos_emb1D), index depth = regression head."""
+        table, total = self._layout_table(self._cfg)
+        depth, k = self._cfg.depth, self._PER_LAYER
+        starts = [table[1 + k * l] for l in range(depth)] + [table[len(table) - 4], total]
+        return [(0 if l == 0 else starts[l], starts[l + 1]) for l in range(depth)] + [(starts[depth], total)]
 
     # ------------------------------------------------------------------ layout
     def __setattr__(self, name, value):
@@ -140,43 +156,6 @@ class ViS(nn.Module, PyTorchModelHubMixin):
         self.__dict__["_flat"] = None          # .to()/.cuda() re-allocate every parameter
         return out
 
-    def _config(self):
-        head = self.linear_head
-        if not (isinstance(head, nn.Sequential) and len(head) == 2 and isinstance(head[0], nn.LayerNorm)
-                and isinstance(head[1], nn.Linear)):
-            raise RuntimeError("linear_head must be nn.Sequential(nn.LayerNorm(D), nn.Linear(D, num_outputs))")
-        n, d = self.pos_emb1D.shape
-        if head[1].in_features != d or head[0].normalized_shape != (d,):
-            raise RuntimeError("linear_head does not match input_dim")
-        layers = self.transformer.layers
-        return _lib.VisConfig(d, len(layers), len(layers[0][0].mixers), n, head[1].out_features)
-
-    def _slots(self, cfg):
-        """[(parameter, flat element offset)] for every parameter, from the C layout table."""
-        L = _lib.lib()
-        n = L.sq_vis_param_table_len(C.byref(cfg))
-        if n < 0:
-            _lib.check(n)
-        table = (C.c_longlong * n)()
-        total = C.c_longlong()
-        _lib.check(L.sq_vis_param_layout(C.byref(cfg), table, n, C.byref(total)))
-        D = cfg.input_dim
-        slots = [(self.pos_emb1D, table[0])]
-        for l, (attn, ff) in enumerate(self.transformer.layers):
-            lnl_g, lnl_b, lns_g, lns_b, ws, bs, wf, bf, wc, bc, wp, bp, fg, fb, w1, b1, w2, b2 = table[1 + 18 * l: 19 + 18 * l]
-            for h, m in enumerate(attn.mixers):
-                slots += [(m.local_norm.weight, lnl_g + 64 * h), (m.local_norm.bias, lnl_b + 64 * h),
-                          (m.summary_norm.weight, lns_g + 64 * h), (m.summary_norm.bias, lns_b + 64 * h),
-                          (m.s.weight, ws + 64 * D * h), (m.s.bias, bs + 64 * h),
-                          (m.f.weight, wf + 64 * D * h), (m.f.bias, bf + 64 * h),
-                          (m.c.weight, wc + 64 * 128 * h), (m.c.bias, bc + 64 * h)]
-            slots += [(attn.projection.weight, wp), (attn.projection.bias, bp), (ff.net[0].weight, fg), (ff.net[0].bias, fb),
-                      (ff.net[1].weight, w1), (ff.net[1].bias, b1), (ff.net[3].weight, w2), (ff.net[3].bias, b2)]
-        hg, hb, wh, bh = table[n - 4: n]
-        slots += [(self.linear_head[0].weight, hg), (self.linear_head[0].bias, hb), (self.linear_head[1].weight, wh),
-                  (self.linear_head[1].bias, bh)]
-        return slots, total.value
-
     def _ensure_flat(self):
         p0, p1 = self.pos_emb1D, self.linear_head[1].bias
         if self._flat is not None:
@@ -186,13 +165,13 @@ class ViS(nn.Module, PyTorchModelHubMixin):
                 return
         dev = p0.device
         if dev.type != "cuda":
-            raise RuntimeError("sequoia_b200 ViS runs on a B200 only: call .to('cuda') first (no CPU fallback)")
+            raise RuntimeError(f"sequoia_b200 {self._NAME} runs on a B200 only: call .to('cuda') first (no CPU fallback)")
         _lib.require_device()
         cfg = self._config()
         slots, total = self._slots(cfg)
         for p, _ in slots:
             if p.dtype != torch.float32 or p.device != dev:
-                raise RuntimeError("ViS parameters must all be float32 on one CUDA device")
+                raise RuntimeError(f"{self._NAME} parameters must all be float32 on one CUDA device")
         flat = torch.zeros(total, dtype=torch.float32, device=dev)
         sizes, order = [], []
         pos = 0
@@ -255,7 +234,7 @@ class ViS(nn.Module, PyTorchModelHubMixin):
         self._ensure_flat()
         cfg = self._cfg
         if x.device != self._flat.device or x.dtype != torch.float32:
-            raise ValueError("ViS.forward expects a float32 tensor on the model's CUDA device")
+            raise ValueError(f"{self._NAME}.forward expects a float32 tensor on the model's CUDA device")
         B = x.shape[0]
         if B == 0:
             return torch.empty(0, cfg.num_outputs, dtype=torch.float32, device=x.device), None
@@ -264,7 +243,7 @@ class ViS(nn.Module, PyTorchModelHubMixin):
             raise ValueError(f"expected [B, {cfg.num_clusters}, {cfg.input_dim}] cluster features, got {tuple(x.shape)}")
         self._refresh_planes()
         L = _lib.lib()
-        need = L.sq_vis_act_bytes(C.byref(cfg), B)
+        need = getattr(L, self._C["act"])(C.byref(cfg), B)
         if keep:
             act = torch.empty(need, dtype=torch.uint8, device=x.device)
         else:
@@ -273,7 +252,7 @@ class ViS(nn.Module, PyTorchModelHubMixin):
             act = self._act_cache
         pred = torch.empty(B, cfg.num_outputs, dtype=torch.float32, device=x.device)
         if B > 0:
-            _lib.check(L.sq_vis_forward(C.byref(cfg), _lib.ptr(self._flat), _lib.ptr(self._w_hi), _lib.ptr(self._w_lo), _lib.ptr(x), B,
+            _lib.check(getattr(L, self._C["fwd"])(C.byref(cfg), _lib.ptr(self._flat), _lib.ptr(self._w_hi), _lib.ptr(self._w_lo), _lib.ptr(x), B,
                                         _lib.ptr(pred), _lib.ptr(act), act.numel(), _lib.stream_ptr()))
         return pred, act
 
@@ -291,7 +270,7 @@ class ViS(nn.Module, PyTorchModelHubMixin):
         return self._gbufs[i]
 
     def _scratch_for(self, B):
-        need = _lib.lib().sq_vis_bwd_bytes(C.byref(self._cfg), B)
+        need = getattr(_lib.lib(), self._C["bwd_bytes"])(C.byref(self._cfg), B)
         if self._scratch is None or self._scratch.numel() < need:
             self._scratch = torch.empty(need, dtype=torch.uint8, device=self._flat.device)
         return self._scratch
@@ -305,7 +284,7 @@ class ViS(nn.Module, PyTorchModelHubMixin):
         if dpred is not None:
             dpred = dpred.contiguous()
         if B > 0:
-            _lib.check(_lib.lib().sq_vis_backward(C.byref(cfg), _lib.ptr(self._flat), _lib.ptr(self._w_hi), _lib.ptr(self._w_lo),
+            _lib.check(getattr(_lib.lib(), self._C["bwd"])(C.byref(cfg), _lib.ptr(self._flat), _lib.ptr(self._w_hi), _lib.ptr(self._w_lo),
                                                   _lib.ptr(dpred), B, _lib.ptr(act), act.numel(), _lib.ptr(gbuf), _lib.ptr(dx),
                                                   _lib.ptr(scratch), scratch.numel(), cfg.depth if stage_hi is None else stage_hi,
                                                   stage_lo, _lib.stream_ptr()))
@@ -318,6 +297,60 @@ class ViS(nn.Module, PyTorchModelHubMixin):
         if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self._params)):
             return _ViSFunction.apply(self, x, *self._params)
         return self._forward_impl(x, keep=False)[0]
+
+
+class ViS(_FlatAggregator, nn.Module, PyTorchModelHubMixin):
+    _C = dict(table_len="sq_vis_param_table_len", layout="sq_vis_param_layout", act="sq_vis_act_bytes", bwd_bytes="sq_vis_bwd_bytes",
+              fwd="sq_vis_forward", bwd="sq_vis_backward")
+    _PER_LAYER = 18
+    _NAME = "ViS"
+
+    def __init__(self, num_outputs, input_dim, depth, nheads, dimensions_f, dimensions_s, dimensions_c, num_clusters=100,
+                 device='cuda:0'):
+        super().__init__()
+        if not (dimensions_f == dimensions_s == dimensions_c == 64):
+            raise NotImplementedError("sequoia_b200 ViS implements dimensions_f = dimensions_s = dimensions_c = 64 "
+                                      "(the values hard-coded by the reference, src/main.py:147,167)")
+        # same construction order as the reference, so the same torch seed gives the same initial weights
+        self.pos_emb1D = nn.Parameter(torch.randn(num_clusters, input_dim))
+        self.transformer = SummaryTransformer(input_dim, depth, nheads, dimensions_f, dimensions_s, dimensions_c)
+        self.to_latent = nn.Identity()
+        self.linear_head = nn.Sequential(nn.LayerNorm(input_dim), nn.Linear(input_dim, num_outputs))
+        self.device = device
+        self._init_flat_state()
+
+    # ------------------------------------------------------------------ layout
+    def _config(self):
+        head = self.linear_head
+        if not (isinstance(head, nn.Sequential) and len(head) == 2 and isinstance(head[0], nn.LayerNorm)
+                and isinstance(head[1], nn.Linear)):
+            raise RuntimeError("linear_head must be nn.Sequential(nn.LayerNorm(D), nn.Linear(D, num_outputs))")
+        n, d = self.pos_emb1D.shape
+        if head[1].in_features != d or head[0].normalized_shape != (d,):
+            raise RuntimeError("linear_head does not match input_dim")
+        layers = self.transformer.layers
+        return _lib.VisConfig(d, len(layers), len(layers[0][0].mixers), n, head[1].out_features)
+
+    def _slots(self, cfg):
+        """[(parameter, flat element offset)] for every parameter, from the C layout table."""
+        table, total = self._layout_table(cfg)
+        n = len(table)
+        D = cfg.input_dim
+        slots = [(self.pos_emb1D, table[0])]
+        for l, (attn, ff) in enumerate(self.transformer.layers):
+            lnl_g, lnl_b, lns_g, lns_b, ws, bs, wf, bf, wc, bc, wp, bp, fg, fb, w1, b1, w2, b2 = table[1 + 18 * l: 19 + 18 * l]
+            for h, m in enumerate(attn.mixers):
+                slots += [(m.local_norm.weight, lnl_g + 64 * h), (m.local_norm.bias, lnl_b + 64 * h),
+                          (m.summary_norm.weight, lns_g + 64 * h), (m.summary_norm.bias, lns_b + 64 * h),
+                          (m.s.weight, ws + 64 * D * h), (m.s.bias, bs + 64 * h),
+                          (m.f.weight, wf + 64 * D * h), (m.f.bias, bf + 64 * h),
+                          (m.c.weight, wc + 64 * 128 * h), (m.c.bias, bc + 64 * h)]
+            slots += [(attn.projection.weight, wp), (attn.projection.bias, bp), (ff.net[0].weight, fg), (ff.net[0].bias, fb),
+                      (ff.net[1].weight, w1), (ff.net[1].bias, b1), (ff.net[3].weight, w2), (ff.net[3].bias, b2)]
+        hg, hb, wh, bh = table[n - 4: n]
+        slots += [(self.linear_head[0].weight, hg), (self.linear_head[0].bias, hb), (self.linear_head[1].weight, wh),
+                  (self.linear_head[1].bias, bh)]
+        return slots, total
 
 
 class FusedAdamW(torch.optim.Optimizer):

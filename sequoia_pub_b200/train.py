@@ -1,4 +1,4 @@
-"""Fused ViS optimisation step: the body of the reference's training loop (src/vit.py:163-166,175-180 —
+"""Fused optimisation step of an aggregator (`tformer_lin.ViS` or `vit.ViT`): the body of the reference's training loop (src/vit.py:163-166,175-180 —
 `pred = model(x); loss = MSELoss(pred, y); optimizer.zero_grad(); loss.backward(); optimizer.step()` with
 `AdamW(lr, weight_decay=0, amsgrad=False)`, src/main.py:180-183) enqueued as one chain of CUDA kernels with no autograd
 graph: sq_vis_forward -> sq_mse_fwd_bwd -> sq_vis_backward (stage by stage) -> [NCCL all-reduce] -> sq_adamw_flat.
@@ -13,12 +13,11 @@ import ctypes as C
 import torch
 
 from . import _lib
-from .dist import allreduce_stage, stage_ranges
-from .tformer_lin import ViS
+from .dist import allreduce_stage
 
 
 class FusedTrainer:
-    def __init__(self, model: ViS, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, process_group=None, overlap=True):
+    def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, process_group=None, overlap=True):
         self.model = model
         self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
         self.step_count = 0
@@ -42,7 +41,7 @@ class FusedTrainer:
             self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
             self.mse_scratch = torch.empty(1024, dtype=torch.float32, device=dev)
             self._token = m._flat_token
-            self.stage_range = stage_ranges(m._cfg)      # contiguous slices of the flat buffer per backward stage
+            self.stage_range = m._stage_ranges()         # contiguous slices of the flat buffer per backward stage
         return m
 
     def step(self, x, y):

@@ -1,7 +1,7 @@
 """Generates the golden fixtures by running the UNMODIFIED reference classes (imported from /root/reference)
 on weights / inputs produced by the oracle's deterministic generators.  Run in the build container only:
 
-    python tests/golden/gen_golden.py [resnet] [vis] [kmeans]
+    python tests/golden/gen_golden.py [resnet] [vis] [kmeans] [metrics] [vit]
 
 The fixtures travel with the repo; /root/reference does not exist on the GPU box.
 """
@@ -146,6 +146,53 @@ def gen_metrics():
         assert abs(MO.compute_correlations(y, p) - out[f"{tag}_corr"]) < 1e-12
         print("metrics golden", tag, float(out[f"{tag}_corr"]), float(out[f"{tag}_mae"]))
     np.savez_compressed(os.path.join(HERE, "metrics_golden.npz"), **out)
+
+
+def gen_vit():
+    """Reference ViT (src/vit.py:93-116) on the oracle's seeded weights.  `src.vit` imports `src.he2rna` (tkinter, wandb,
+    h5py: absent) only for `compute_correlations`, which the model classes never touch: that module is stubbed.
+    main = the shape src/main.py builds (dim 2048, 16 heads, mlp 2048) at depth 2, 300 genes, batch 2: forward, loss,
+    gradients, 3 AdamW steps; small = dim 256, 4 heads, mlp 512, depth 3, 37 tokens, 129 genes, batch 3."""
+    import types
+    stub = types.ModuleType("src.he2rna")
+    stub.compute_correlations = lambda *a, **k: None
+    sys.modules["src.he2rna"] = stub
+    from oracle import vit_oracle as T
+    from src.vit import ViT  # the reference
+    out = {}
+    for tag, D, H, F_, G, B, depth, N in (("main", 2048, 16, 2048, 300, 2, 2, 100), ("small", 256, 4, 512, 129, 3, 3, 37)):
+        sd = T.make_state_dict(2, G, dim=D, depth=depth, heads=H, mlp_dim=F_, num_clusters=N)
+        ref = ViT(num_outputs=G, dim=D, depth=depth, heads=H, mlp_dim=F_, dim_head=64, num_clusters=N, device="cpu")
+        assert list(ref.state_dict().keys()) == list(sd.keys())
+        ref.load_state_dict(sd, strict=True)
+        opt = torch.optim.AdamW(list(ref.parameters()), lr=1e-3, amsgrad=False, weight_decay=0.)
+        loss_fn = torch.nn.MSELoss()
+        losses = []
+        for step in range(3):
+            x, y = T.make_inputs(20 + step, B, G, input_dim=D, num_clusters=N)
+            pred = ref(x)
+            loss = loss_fn(pred, y)
+            opt.zero_grad()
+            loss.backward()
+            if step == 0:
+                out[f"{tag}_pred0"] = pred.detach().numpy()
+                out[f"{tag}_grad_norms"] = np.array([float(p.grad.double().norm()) for p in ref.parameters()])
+                for k in ("transformer.layers.0.0.norm.weight", "transformer.layers.0.0.to_qkv.weight", "transformer.layers.1.0.to_out.weight",
+                          "transformer.layers.0.1.net.1.bias", "linear_head.1.bias"):
+                    g = dict(ref.named_parameters())[k].grad.numpy()
+                    out[f"{tag}_grad::{k}"] = g[:64].copy()                 # leading rows keep the fixture small
+                with torch.no_grad():
+                    ref64 = ViT(num_outputs=G, dim=D, depth=depth, heads=H, mlp_dim=F_, dim_head=64, num_clusters=N, device="cpu").double()
+                    ref64.load_state_dict(T.to_double(sd))
+                    out[f"{tag}_pred0_fp64"] = ref64(x.double()).numpy()
+            opt.step()
+            losses.append(float(loss))
+        out[f"{tag}_losses"] = np.array(losses)
+        x, _ = T.make_inputs(99, B, G, input_dim=D, num_clusters=N)
+        with torch.no_grad():
+            out[f"{tag}_pred_after3"] = ref(x).numpy()
+    np.savez_compressed(os.path.join(HERE, "vit_golden.npz"), **out)
+    print("vit golden:", {k: v.shape for k, v in out.items()})
 
 
 if __name__ == "__main__":
