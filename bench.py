@@ -32,6 +32,7 @@ sys.path.insert(0, ROOT)
 PATCHES_PER_SLIDE = 4096
 BATCH = 64
 FLOP_PER_PATCH = 10.677e9          # SURVEY §8a R3 (2*MAC, 256 px)
+STEM_FLOP_PER_PATCH = 2.0 * 128 * 128 * 64 * 147
 WORKLOAD = "resnet50_extract: 1 slide = 4096 x 256x256x3 uint8 patches, batch 64 (BASELINE configs[1])"
 METRIC = "patches/sec (feat-extract) & slides/sec (lin-attn train) at 1/2/4/8 B200"
 
@@ -281,6 +282,39 @@ def bench_vis(args, dev, rank, world, timed, pk):
     return out
 
 
+def bench_vit(args, dev, rank, world, timed):
+    """slides/s of the fused train step of the softmax-attention ViT baseline (`--model_type vit`) on the
+    config-3 shape: batch 32 per GPU, 100 x 2048 -> 20530 genes, depth 6, 16 heads, mlp 2048.  Secondary number, device-timed."""
+    import torch
+    from oracle import vis_oracle as V
+    from sequoia_pub_b200.train import FusedTrainer
+    from sequoia_pub_b200.vit import ViT
+    torch.manual_seed(0)
+    model = ViT(num_outputs=VIS_G, dim=VIS_D, depth=VIS_DEPTH, heads=VIS_H, mlp_dim=2048, dim_head=64, num_clusters=VIS_N,
+                device=str(dev)).to(dev).train()
+    x, y = V.make_inputs(200 + rank, VIS_B, VIS_G)
+    xs = [x.to(dev), x.flip(0).contiguous().to(dev)]
+    ys = [y.to(dev), y.flip(0).contiguous().to(dev)]
+    tr = FusedTrainer(model, lr=1e-3, weight_decay=0.0, process_group=None)
+    state = {"i": 0}
+
+    def step_dev():
+        i = state["i"] = state["i"] + 1
+        tr.step(xs[i & 1], ys[i & 1])
+
+    for _ in range(args.warmup):
+        step_dev()
+    steps = max(args.steps, 5)
+    ms = timed(step_dev, steps) / steps
+    out = {"value": world * VIS_B / (ms * 1e-3), "unit": "slides/s", "ms_per_step": ms, "steps": steps,
+           "dtype": "bf16x3 GEMMs + fp32 softmax attention", "final_loss": float(tr.loss.item()),
+           "config": {"workload": "ViT (softmax attention) train step: batch 32 slides per GPU, 100x2048 -> 20530 genes, depth 6, 16 heads, mlp 2048, AdamW",
+                      "global_batch": VIS_B * world}}
+    del tr, model
+    torch.cuda.empty_cache()
+    return out
+
+
 UNI_BATCH, UNI_PATCHES = 64, 1024
 UNI_FLOP_PER_PATCH = 123.107e9     # SURVEY §8a U1
 UNI_WORKLOAD = "UNI ViT-L/16 extraction: 1024 synthetic 224x224x3 uint8 patches per rank per step, batch 64 (BASELINE configs[3] shape, slide-sharded)"
@@ -386,7 +420,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=256, help="patches timed on the CPU baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--only", default="", help="comma list of {vis,kmeans,uni}: run only these extra legs (debugging)")
+    ap.add_argument("--only", default="", help="comma list of {vis,kmeans,uni,vit}: run only these extra legs (debugging)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -448,7 +482,8 @@ def main():
     slide_host = torch.empty(slide_dev.shape, dtype=torch.uint8).pin_memory()
     slide_host.copy_(slide_dev)
     feats = torch.empty(PATCHES_PER_SLIDE, 2048, dtype=torch.float32, device=dev)
-    launches_per_step = (PATCHES_PER_SLIDE // BATCH) * (L.sq_resnet50_num_convs() + 3)
+    fused_stem = os.environ.get("SQ_STEM_FUSED", "1") != "0"     # one kernel for preprocessing + conv1 + max-pool (csrc/resnet.cu)
+    launches_per_step = (PATCHES_PER_SLIDE // BATCH) * (L.sq_resnet50_num_convs() + (1 if fused_stem else 3))
 
     def step_device():
         # batch 64 per extractor launch (BASELINE configs[1]); consecutive batches alternate between two CUDA streams
@@ -479,7 +514,9 @@ def main():
         step_serial()
         ser_ms = timed_local(step_serial, 2) / 2
         tms, n, fl = gemm_timing(L, _lib, step_serial)
-        alg_flops = FLOP_PER_PATCH * PATCHES_PER_SLIDE          # algorithmic work of one step
+        # algorithmic work of the launches that are timed: with the fused stem, conv1 (2*128*128*64*147 FLOP/patch) runs in
+        # stem_fused_kernel, not in gemm_tc_kernel, and is left out of the numerator
+        alg_flops = (FLOP_PER_PATCH - (STEM_FLOP_PER_PATCH if fused_stem else 0.0)) * PATCHES_PER_SLIDE
         achieved = alg_flops / (tms * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (implicit-GEMM conv, bf16 -> fp32 TMEM)",
                 "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
@@ -500,6 +537,7 @@ def main():
     vis = bench_vis(args, dev, rank, world, timed, pk) if (not only or "vis" in only) else None
     kmn = bench_kmeans(args, dev, rank, world, pk) if (not only or "kmeans" in only) else None
     uni = bench_uni(args, dev, rank, world, timed, pk) if (not only or "uni" in only) else None
+    vit = bench_vit(args, dev, rank, world, timed) if (not only or "vit" in only) else None
 
     if rank != 0:
         if world > 1:
@@ -527,7 +565,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "patches/s", "h2d_bytes_per_step": ex_h2d // e2e_steps,
                     "d2h_bytes_per_step": ex_d2h // e2e_steps, "ms_per_step": e2e_ms},
             "gpu_launches": launches_per_step * args.steps,
-            "roofline": roof, "cpu_baseline": cpu, "vis_train": vis, "kmeans": kmn, "uni_extract": uni}
+            "roofline": roof, "cpu_baseline": cpu, "vis_train": vis, "kmeans": kmn, "uni_extract": uni, "vit_train": vit}
     emit(line)
     if world > 1:
         dist.destroy_process_group()

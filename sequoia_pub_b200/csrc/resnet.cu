@@ -8,6 +8,7 @@
 // into that im2col kernel (R4), max-pool and the 7x7 top-left average pool (fact 4) are small bandwidth kernels.
 #include "gemm.cuh"
 #include "../../include/sequoia_b200.h"
+#include <stdlib.h>
 
 namespace sq {
 
@@ -147,6 +148,181 @@ __global__ void maxpool3x3s2_kernel(const bf16* __restrict__ in, bf16* __restric
     }
 }
 
+// ---------------------------------------------------------------------------------------------------- fused stem
+// conv1 7x7/2 (+ folded BN shift, ReLU) + 3x3/2 max-pool in ONE kernel, straight from the uint8 tile (R4 fused too):
+// no im2col buffer (403 MB written + read per batch of 64) and no full-resolution stem map (134 MB written + read).
+// A CTA owns an 8x8 tile of the POOLED map = 17x17 conv outputs = 39x39 input pixels, staged in shared memory as
+// normalised bf16 [row][x*3 + c].  For a fixed filter row r the 21 (s, c) taps of a conv pixel are contiguous there
+// (offset 6*ox), exactly the K layout of the packed stem weights (K index = r*24 + s*3 + c, 3 zero weights per filter
+// row), so the im2col matrix is never materialised: mma.sync A fragments are 32-bit loads from the staged tile, B
+// fragments come from the weight slab with ldmatrix.  M = 289 conv pixels (19 m16 tiles over 10 warps), N = 64,
+// K = 176 (11 k16 steps; taps 168..175 multiply zero weights).  The conv tile goes to shared memory as bf16 after shift +
+// ReLU, then the 3x3/2 max-pool writes whole 128-byte channel rows.  ~20 GFLOP per batch: legacy mma.sync is enough
+// here, the kernel is bound by staging and the pool, not by the tensor pipe.
+constexpr int ST_THREADS = 320;
+constexpr int ST_IROW = 120, ST_IROWS = 40;     // staged input: 39 rows (+1 over-read row) x (39*3 = 117 -> 120) bf16
+constexpr int ST_WLD = 184;                     // weight slab [64][176] row stride: 368 B, conflict-free ldmatrix
+constexpr int ST_CLD = 72;                      // conv tile [289][64] row stride: 144 B, conflict-free fragment stores
+constexpr int ST_KSTEPS = 11;
+constexpr int ST_CPIX = 17 * 17;
+constexpr int ST_WORDS = 31;                    // aligned 32-bit words that cover the 117 (+3) bytes of a staged uint8 row
+constexpr size_t ST_SMEM = (size_t)(ST_IROWS * ST_IROW + 64 * ST_WLD + ST_CPIX * ST_CLD + 3 * 256) * 2;
+
+__device__ __forceinline__ void st_ldsm_x4(uint32_t (&r)[4], const void* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void st_mma(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// kind 0: uint8 NHWC; 1: fp32 NCHW normalised; 2: uint8 NHWC with a 4-byte aligned base and W % 4 == 0 (word loads + LUT)
+__global__ void __launch_bounds__(ST_THREADS, 2) stem_fused_kernel(const void* __restrict__ in, int kind, int batch, int H, int W,
+                                                                   const bf16* __restrict__ wpk, const float* __restrict__ shift,
+                                                                   bf16* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char st_smem[];
+    bf16* s_in = reinterpret_cast<bf16*>(st_smem);
+    bf16* s_w = s_in + ST_IROWS * ST_IROW;
+    bf16* s_c = s_w + 64 * ST_WLD;
+    bf16* s_lut = s_c + ST_CPIX * ST_CLD;                         // normalised value of every (channel, byte): bit-identical to the formula
+    for (int i = threadIdx.x; i < 3 * 256; i += ST_THREADS) {
+        const int c = i >> 8;
+        const float mu = c == 0 ? 0.485f : (c == 1 ? 0.456f : 0.406f), sd = c == 0 ? 0.229f : (c == 1 ? 0.224f : 0.225f);
+        s_lut[i] = __float2bfloat16_rn((static_cast<float>(i & 255) / 255.0f - mu) / sd);
+    }
+    for (int i = threadIdx.x; i < ST_IROW; i += ST_THREADS) s_in[39 * ST_IROW + i] = __float2bfloat16_rn(0.f);   // over-read row
+    const int Hc = H / 2, Wc = W / 2, Hp = H / 4, Wp = W / 4, tiles_x = Wp / 8, tiles_y = Hp / 8;
+    const int ntiles = batch * tiles_y * tiles_x;
+    for (int i = threadIdx.x; i < 64 * (ST_KSTEPS * 2); i += ST_THREADS) {          // [64][192] packed -> [64][176] slab
+        const int n = i / (ST_KSTEPS * 2), q = i - n * (ST_KSTEPS * 2);
+        *reinterpret_cast<uint4*>(s_w + n * ST_WLD + q * 8) = *reinterpret_cast<const uint4*>(wpk + n * STEM_K + q * 8);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    float sh[8][2];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) { sh[nt][0] = shift[nt * 8 + 2 * t]; sh[nt][1] = shift[nt * 8 + 2 * t + 1]; }
+    const uint32_t* in32 = reinterpret_cast<const uint32_t*>(s_in);
+
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int tx = tile % tiles_x; const int rest = tile / tiles_x; const int ty = rest % tiles_y; const int img = rest / tiles_y;
+        const int cy0 = 16 * ty - 1, cx0 = 16 * tx - 1;          // conv-map origin of the 17x17 tile
+        const int iy0 = 2 * cy0 - 3, ix0 = 2 * cx0 - 3;          // input origin of the 39x39 tile
+        __syncthreads();                                         // the previous tile's readers of s_in / s_c are done
+        if (kind == 2) {
+            const int row_bytes = W * 3, xb0 = ix0 * 3;          // byte offset of tile column 0 inside an image row (may be < 0)
+            const int a0 = (xb0 >> 2) << 2, mis = xb0 - a0;      // word-aligned start; rows start on word boundaries (W % 4 == 0)
+            const uint8_t* img_base = reinterpret_cast<const uint8_t*>(in) + (long long)img * H * row_bytes;
+            for (int i = threadIdx.x; i < 39 * ST_WORDS; i += ST_THREADS) {
+                const int r = i / ST_WORDS, wi = i - r * ST_WORDS;
+                const int ih = iy0 + r, wb = a0 + 4 * wi;
+                const bool ok = ih >= 0 && ih < H && wb >= 0 && wb < row_bytes;     // a word is entirely inside or outside the row
+                uint32_t word = 0u;
+                if (ok) word = *reinterpret_cast<const uint32_t*>(img_base + (long long)ih * row_bytes + wb);
+                const int c0 = ok ? wb % 3 : 0;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const int xc = 4 * wi + b - mis;
+                    if (xc >= 0 && xc < ST_IROW) {
+                        int c = c0 + b; c = c >= 3 ? c - 3 : c; c = c >= 3 ? c - 3 : c;
+                        s_in[r * ST_IROW + xc] = ok ? s_lut[(c << 8) + ((word >> (8 * b)) & 255u)] : __float2bfloat16_rn(0.f);
+                    }
+                }
+            }
+        } else
+        for (int i = threadIdx.x; i < ST_IROWS * ST_IROW; i += ST_THREADS) {
+            const int r = i / ST_IROW; const int xc = i - r * ST_IROW; const int x = xc / 3; const int c = xc - x * 3;
+            const int ih = iy0 + r, iw = ix0 + x;
+            float v = 0.f;
+            if (r < 39 && x < 39 && ih >= 0 && ih < H && iw >= 0 && iw < W) {
+                if (kind == 0) {
+                    const uint8_t u = reinterpret_cast<const uint8_t*>(in)[(((long long)img * H + ih) * W + iw) * 3 + c];
+                    const float mu = c == 0 ? 0.485f : (c == 1 ? 0.456f : 0.406f), sd = c == 0 ? 0.229f : (c == 1 ? 0.224f : 0.225f);
+                    v = (static_cast<float>(u) / 255.0f - mu) / sd;
+                } else {
+                    v = reinterpret_cast<const float*>(in)[(((long long)img * 3 + c) * H + ih) * W + iw];
+                }
+            }
+            s_in[i] = __float2bfloat16_rn(v);
+        }
+        __syncthreads();
+        for (int mt = warp; mt < (ST_CPIX + 15) / 16; mt += ST_THREADS / 32) {
+            const int p0 = mt * 16 + g, p1 = p0 + 8;
+            const int q0 = p0 < ST_CPIX ? p0 : ST_CPIX - 1, q1 = p1 < ST_CPIX ? p1 : ST_CPIX - 1;
+            const int oy0 = q0 / 17, ox0 = q0 - oy0 * 17, oy1 = q1 / 17, ox1 = q1 - oy1 * 17;
+            const int b0 = oy0 * 2 * (ST_IROW / 2) + ox0 * 3 + t, b1 = oy1 * 2 * (ST_IROW / 2) + ox1 * 3 + t;     // 32-bit word offsets
+            float acc[8][4];
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
+#pragma unroll
+            for (int ks = 0; ks < ST_KSTEPS; ++ks) {
+                const int kA = ks * 16, kB = ks * 16 + 8;        // each 8-wide half lies inside one 24-wide filter-row segment
+                const int offA = (kA / 24) * (ST_IROW / 2) + (kA % 24) / 2, offB = (kB / 24) * (ST_IROW / 2) + (kB % 24) / 2;
+                uint32_t a[4];
+                a[0] = in32[b0 + offA]; a[1] = in32[b1 + offA]; a[2] = in32[b0 + offB]; a[3] = in32[b1 + offB];
+#pragma unroll
+                for (int jn = 0; jn < 4; ++jn) {
+                    uint32_t b[4];   // matrices: (n-tile 2jn, k-half 0), (2jn, 1), (2jn+1, 0), (2jn+1, 1)
+                    st_ldsm_x4(b, s_w + ((jn * 2 + (lane >> 4)) * 8 + (lane & 7)) * ST_WLD + ks * 16 + ((lane >> 3) & 1) * 8);
+                    st_mma(acc[2 * jn], a, b[0], b[1]);
+                    st_mma(acc[2 * jn + 1], a, b[2], b[3]);
+                }
+            }
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int p = half ? p1 : p0;
+                if (p < ST_CPIX) {
+                    const int oy = half ? oy1 : oy0, ox = half ? ox1 : ox0;
+                    const int cy = cy0 + oy, cx = cx0 + ox;
+                    const bool valid = cy >= 0 && cy < Hc && cx >= 0 && cx < Wc;      // outside the conv map: excluded from the max (ReLU output >= 0)
+#pragma unroll
+                    for (int nt = 0; nt < 8; ++nt) {
+                        const float v0 = valid ? fmaxf(acc[nt][2 * half] + sh[nt][0], 0.f) : 0.f;
+                        const float v1 = valid ? fmaxf(acc[nt][2 * half + 1] + sh[nt][1], 0.f) : 0.f;
+                        *reinterpret_cast<__nv_bfloat162*>(s_c + p * ST_CLD + nt * 8 + 2 * t) = __floats2bfloat162_rn(v0, v1);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < 64 * 8; i += ST_THREADS) {
+            const int c8 = i & 7, pp = i >> 3, ply = pp >> 3, plx = pp & 7;
+            uint4 m = *reinterpret_cast<const uint4*>(s_c + ((2 * ply) * 17 + 2 * plx) * ST_CLD + c8 * 8);
+            __nv_bfloat162* mh = reinterpret_cast<__nv_bfloat162*>(&m);
+#pragma unroll
+            for (int rs = 1; rs < 9; ++rs) {
+                const uint4 v = *reinterpret_cast<const uint4*>(s_c + ((2 * ply + rs / 3) * 17 + 2 * plx + rs % 3) * ST_CLD + c8 * 8);
+                const __nv_bfloat162* vh = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) mh[j] = __hmax2(mh[j], vh[j]);
+            }
+            *reinterpret_cast<uint4*>(out + ((((long long)img * Hp + 8 * ty + ply) * Wp + 8 * tx + plx) * 64 + c8 * 8)) = m;
+        }
+    }
+}
+
+static int stem_fused_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SQ_STEM_FUSED"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v;
+}
+
+static int launch_stem_fused(const void* input, int kind, int batch, int H, int W, const bf16* wpk, const float* shift, bf16* out, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(stem_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM) != cudaSuccess) {
+            set_error("stem: cannot raise the dynamic shared memory limit"); (void)cudaGetLastError(); return -1;
+        }
+        attr_set = true;
+    }
+    const int ntiles = batch * (H / 32) * (W / 32);
+    int grid = 2 * num_sms(); if (grid > ntiles) grid = ntiles;
+    if (kind == 0 && (reinterpret_cast<uintptr_t>(input) & 3) == 0 && W % 4 == 0) kind = 2;
+    stem_fused_kernel<<<grid, ST_THREADS, ST_SMEM, st>>>(input, kind, batch, H, W, wpk, shift, out);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) { set_error("stem_fused: %s", cudaGetErrorString(err)); return -1; }
+    return 0;
+}
+
 // AvgPool2d(7) on an HfxWf map with Hf,Wf in [7,13]: mean of the top-left 7x7 window (src/resnet.py:110,166; fact 4)
 __global__ void avgpool7_kernel(const float* __restrict__ in, float* __restrict__ out, int batch, int Hf, int Wf, int C) {
     const long long n = (long long)batch * C;
@@ -255,8 +431,13 @@ int sq_resnet50_extract(const void* input, int input_kind, int batch, int H, int
     bf16* small_[2] = {(bf16*)(ws + L.small[0]), (bf16*)(ws + L.small[1])};
     float* fmap = (float*)(ws + L.fmap);
 
-    // ---- stem: im2col (+ fused preprocessing) -> GEMM(+shift+ReLU) -> maxpool
+    // ---- stem: one fused kernel (preprocessing + conv1 + BN shift + ReLU + max-pool); SQ_STEM_FUSED=0 selects the older
+    //      im2col -> tcgen05 GEMM -> max-pool chain (kept for A/B measurements)
     const int Ho = H / 2, Wo = W / 2;
+    int h = Ho / 2, w = Wo / 2;
+    if (stem_fused_enabled()) {
+        if (launch_stem_fused(input, input_kind, batch, H, W, wp + p.conv[0].w_off, shifts + p.conv[0].s_off, big[0], st)) return -1;
+    } else {
     stem_im2col_kernel<<<batch * Ho * (Wo / 32), 256, 0, st>>>(input, input_kind, H, W, Ho, Wo, col);
     {
         GemmArgs g; memset(&g, 0, sizeof(g));
@@ -265,10 +446,10 @@ int sq_resnet50_extract(const void* input, int input_kind, int batch, int H, int
         g.e.bias = shifts + p.conv[0].s_off; g.e.out_hi = stem; g.e.ld_bf = 64; g.e.act = ACT_RELU; g.e.alpha = 1.0f; g.e.rowbias_div = 1;
         if (gemm_launch(g, st)) return -1;
     }
-    int h = Ho / 2, w = Wo / 2;
     {
         const long long n = (long long)batch * h * w * 8;
         maxpool3x3s2_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(stem, big[0], batch, Ho, Wo, 64);
+    }
     }
     // ---- 16 bottlenecks
     const int blocks[4] = {3, 4, 6, 3};

@@ -144,18 +144,21 @@ __device__ __forceinline__ void at_softmax(const float* Qs, const float* Ks, flo
     }
 }
 
-// acc[m] = sum_t P(row, t) X[t][c..c+3] for the rows row = r + 16 m this thread owns (r = tid/16, c = 4 (tid%16)).
+// acc[m] = sum_t P(row, t) X[t][c..c+3] for the rows row = r + AT_RG m this thread owns (r = tid/16, c = 4 (tid%16)).
 // TRANS = false: P(row, t) = Ps[row][t];  TRANS = true: P(row, t) = Ps[t][row].
+constexpr int AT_THREADS = 512;                 // 16 warps per (slide, head)
+constexpr int AT_RG = AT_THREADS / 16;          // row groups
+constexpr int AT_NM = AT_MAXN / AT_RG;          // rows per thread
 template <bool TRANS>
-__device__ __forceinline__ void at_mix(const float* Ps, int pld, const float* Xs, int N, float4 (&acc)[8]) {
+__device__ __forceinline__ void at_mix(const float* Ps, int pld, const float* Xs, int N, float4 (&acc)[AT_NM]) {
     const int r = threadIdx.x >> 4, c = (threadIdx.x & 15) * 4;
 #pragma unroll
-    for (int m = 0; m < 8; ++m) acc[m] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int m = 0; m < AT_NM; ++m) acc[m] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int t = 0; t < N; ++t) {
         const float4 x = *reinterpret_cast<const float4*>(Xs + t * AT_LD + c);
 #pragma unroll
-        for (int m = 0; m < 8; ++m) {
-            const int row = r + 16 * m;
+        for (int m = 0; m < AT_NM; ++m) {
+            const int row = r + AT_RG * m;
             if (row < N) {
                 const float p = TRANS ? Ps[t * pld + row] : Ps[row * pld + t];
                 acc[m].x = fmaf(p, x.x, acc[m].x); acc[m].y = fmaf(p, x.y, acc[m].y);
@@ -165,37 +168,53 @@ __device__ __forceinline__ void at_mix(const float* Ps, int pld, const float* Xs
     }
 }
 
-__device__ __forceinline__ void at_store_planes(const float4 (&acc)[8], bf16* hi, bf16* lo, size_t row0, long long ld, int col0, int N) {
+__device__ __forceinline__ void at_store_planes(const float4 (&acc)[AT_NM], bf16* hi, bf16* lo, size_t row0, long long ld, int col0, int N) {
     const int r = threadIdx.x >> 4, c = (threadIdx.x & 15) * 4;
 #pragma unroll
-    for (int m = 0; m < 8; ++m) {
-        const int row = r + 16 * m;
+    for (int m = 0; m < AT_NM; ++m) {
+        const int row = r + AT_RG * m;
         if (row < N) store_planes4(hi, lo, (row0 + row) * ld + col0 + c, acc[m]);
     }
 }
 
 // qkv fp32 [B*N, 3I] (q | k | v column blocks, head h at columns h*64, 'b n (h d) -> b h n d', src/vit.py:65-66)
-// -> out planes [B*N, I] ('b h n d -> b n (h d)', :73).  grid (H, B), 256 threads.
-__global__ void __launch_bounds__(256) vit_attn_fwd_kernel(const float* __restrict__ qkv, int N, int I, float scale, bf16* __restrict__ oh,
-                                                           bf16* __restrict__ ol) {
+// -> out planes [B*N, I] ('b h n d -> b n (h d)', :73).  grid (H, B).  Shared memory holds q, ONE k/v buffer and the
+// probabilities (95 KB at N = 100: two CTAs per SM); v is prefetched into registers while the scores are computed and
+// replaces k afterwards.
+__global__ void __launch_bounds__(AT_THREADS, 2) vit_attn_fwd_kernel(const float* __restrict__ qkv, int N, int I, float scale, bf16* __restrict__ oh,
+                                                                  bf16* __restrict__ ol) {
     extern __shared__ __align__(16) float at_smem[];
     const int h = blockIdx.x, b = blockIdx.y, pld = N + 1;
-    float* Qs = at_smem; float* Ks = Qs + N * AT_LD; float* Vs = Ks + N * AT_LD; float* Ps = Vs + N * AT_LD;
+    float* Qs = at_smem; float* Ks = Qs + N * AT_LD; float* Ps = Ks + N * AT_LD;
     const size_t row0 = (size_t)b * N;
     const float* base = qkv + row0 * 3 * I + h * 64;
-    at_load(Qs, base, 3LL * I, N); at_load(Ks, base + I, 3LL * I, N); at_load(Vs, base + 2 * I, 3LL * I, N);
+    at_load(Qs, base, 3LL * I, N); at_load(Ks, base + I, 3LL * I, N);
+    constexpr int VPT = (AT_MAXN * 16 + AT_THREADS - 1) / AT_THREADS;      // float4 of v per thread
+    float4 vreg[VPT];
+#pragma unroll
+    for (int k = 0; k < VPT; ++k) {
+        const int i = threadIdx.x + k * AT_THREADS;
+        vreg[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < N * 16) vreg[k] = *reinterpret_cast<const float4*>(base + 2 * I + (size_t)(i >> 4) * 3 * I + (i & 15) * 4);
+    }
     __syncthreads();
     at_softmax(Qs, Ks, Ps, N, pld, scale);
     __syncthreads();
-    float4 acc[8];
-    at_mix<false>(Ps, pld, Vs, N, acc);
+#pragma unroll
+    for (int k = 0; k < VPT; ++k) {
+        const int i = threadIdx.x + k * AT_THREADS;
+        if (i < N * 16) *reinterpret_cast<float4*>(Ks + (i >> 4) * AT_LD + (i & 15) * 4) = vreg[k];
+    }
+    __syncthreads();
+    float4 acc[AT_NM];
+    at_mix<false>(Ps, pld, Ks, N, acc);
     at_store_planes(acc, oh, ol, row0, I, h * 64, N);
 }
 
 // Backward of the above: dqkv planes [B*N, 3I] from qkv (probabilities are recomputed) and dout fp32 [B*N, I].
 //   dV = P^T dO;  dP = dO V^T;  dS = P o (dP - rowsum(P o dP)) * scale;  dQ = dS K;  dK = dS^T Q.
-__global__ void __launch_bounds__(256) vit_attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ dout, int N, int I, float scale,
-                                                           bf16* __restrict__ gh, bf16* __restrict__ gl) {
+__global__ void __launch_bounds__(AT_THREADS) vit_attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ dout, int N, int I, float scale,
+                                                                  bf16* __restrict__ gh, bf16* __restrict__ gl) {
     extern __shared__ __align__(16) float at_smem[];
     const int h = blockIdx.x, b = blockIdx.y, pld = N + 1;
     float* Qs = at_smem; float* Ks = Qs + N * AT_LD; float* Vs = Ks + N * AT_LD; float* Gs = Vs + N * AT_LD; float* Ps = Gs + N * AT_LD;
@@ -206,7 +225,7 @@ __global__ void __launch_bounds__(256) vit_attn_bwd_kernel(const float* __restri
     __syncthreads();
     at_softmax(Qs, Ks, Ps, N, pld, scale);
     __syncthreads();
-    float4 acc[8];
+    float4 acc[AT_NM];
     at_mix<true>(Ps, pld, Gs, N, acc);                                   // dV[j] = sum_i P[i][j] dO[i]
     at_store_planes(acc, gh, gl, row0, 3LL * I, 2 * I + h * 64, N);
     __syncthreads();
@@ -247,12 +266,12 @@ static size_t at_smem_bytes(int N, int operands) { return ((size_t)operands * N 
 static int launch_attn_fwd(const float* qkv, int B, int N, int H, bf16* oh, bf16* ol, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        if (cudaFuncSetAttribute(vit_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)at_smem_bytes(AT_MAXN, 3)) != cudaSuccess) {
+        if (cudaFuncSetAttribute(vit_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)at_smem_bytes(AT_MAXN, 2)) != cudaSuccess) {
             set_error("vit attention: cannot raise the dynamic shared memory limit"); (void)cudaGetLastError(); return -1;
         }
         attr_set = true;
     }
-    vit_attn_fwd_kernel<<<dim3(H, B), 256, at_smem_bytes(N, 3), st>>>(qkv, N, H * 64, 0.125f, oh, ol);
+    vit_attn_fwd_kernel<<<dim3(H, B), AT_THREADS, at_smem_bytes(N, 2), st>>>(qkv, N, H * 64, 0.125f, oh, ol);
     return check_launch("vit attention fwd");
 }
 
@@ -264,7 +283,7 @@ static int launch_attn_bwd(const float* qkv, const float* dout, int B, int N, in
         }
         attr_set = true;
     }
-    vit_attn_bwd_kernel<<<dim3(H, B), 256, at_smem_bytes(N, 4), st>>>(qkv, dout, N, H * 64, 0.125f, gh, gl);
+    vit_attn_bwd_kernel<<<dim3(H, B), AT_THREADS, at_smem_bytes(N, 4), st>>>(qkv, dout, N, H * 64, 0.125f, gh, gl);
     return check_launch("vit attention bwd");
 }
 

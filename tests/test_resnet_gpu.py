@@ -58,6 +58,11 @@ def test_extract_batch_sizes_and_determinism():
     for bs in (1, 2, 5):                                  # ragged batches (odd counts hit the 2-image 8x8 tiles)
         parts = torch.cat([m.extract_uint8(patches[i:i + bs]) for i in range(0, 9, bs)])
         assert torch.equal(parts, full)
+    # a tile buffer that does not start on a 4-byte boundary takes the byte-wise staging path of the fused stem: same bits
+    raw = torch.empty(patches.numel() + 1, dtype=torch.uint8, device="cuda")
+    odd = raw[1:].view(patches.shape)
+    odd.copy_(patches)
+    assert odd.data_ptr() % 4 == 1 and torch.equal(m.extract_uint8(odd), full)
     with torch.no_grad():
         ref = O.forward_extract(sd, O.preprocess(patches.cpu()))
     assert _rel(full.cpu(), ref) < FEATURE_TOL
