@@ -1,4 +1,5 @@
-"""2-GPU data-parallel ViS step (NCCL): two ranks with half the batch each must follow the single-GPU trajectory."""
+"""2-GPU data-parallel train step (NCCL) of both aggregators (ViS, and the ViT baseline of SURVEY §8 f-4): two ranks with half
+the batch each must follow the single-GPU trajectory."""
 import os
 import sys
 
@@ -8,20 +9,38 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, ret):
+def _case(kind):
+    """(oracle module, state dict, model factory, G, B, D)."""
+    if kind == "vis":
+        from oracle import vis_oracle as V
+        D, G, B, depth = 1024, 257, 4, 2
+        sd = V.make_state_dict(1, G, input_dim=D, depth=depth)
+
+        def make():
+            from sequoia_pub_b200.tformer_lin import ViS
+            return ViS(num_outputs=G, input_dim=D, depth=depth, nheads=16, dimensions_f=64, dimensions_s=64, dimensions_c=64)
+        return V, sd, make, G, B, D
+    from oracle import vit_oracle as T
+    D, G, B, depth = 512, 129, 4, 2
+    sd = T.make_state_dict(4, G, dim=D, depth=depth, heads=8, mlp_dim=1024)
+
+    def make():
+        from sequoia_pub_b200.vit import ViT
+        return ViT(num_outputs=G, dim=D, depth=depth, heads=8, mlp_dim=1024, dim_head=64)
+    return T, sd, make, G, B, D
+
+
+def _worker(rank, world, port, ret, kind):
     import torch.distributed as dist
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
-        from oracle import vis_oracle as V
         from sequoia_pub_b200.dist import split_batch
-        from sequoia_pub_b200.tformer_lin import ViS
         from sequoia_pub_b200.train import FusedTrainer
-        D, G, B, depth = 1024, 257, 4, 2
-        sd = V.make_state_dict(1, G, input_dim=D, depth=depth)
-        m = ViS(num_outputs=G, input_dim=D, depth=depth, nheads=16, dimensions_f=64, dimensions_s=64, dimensions_c=64)
+        V, sd, make, G, B, D = _case(kind)
+        m = make()
         m.load_state_dict(sd)
         m = m.cuda().train()
         tr = FusedTrainer(m, lr=1e-3)
@@ -38,23 +57,22 @@ def _worker(rank, world, port, ret):
 
 
 @pytest.mark.gpu
-def test_dp2_matches_single_gpu_and_oracle():
+@pytest.mark.parametrize("kind", ["vis", "vit"])
+def test_dp2_matches_single_gpu_and_oracle(kind):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
-    from oracle import vis_oracle as V
-    port = 29600 + os.getpid() % 2000
+    port = 29600 + os.getpid() % 2000 + (7 if kind == "vit" else 0)
     with mp.Manager() as mgr:
         ret = mgr.dict()
-        mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
+        mp.spawn(_worker, args=(2, port, ret, kind), nprocs=2, join=True)
         p0, p1 = ret[0], ret[1]
     assert torch.equal(p0, p1)                                   # replicas stay bit-identical
-    D, G, B, depth = 1024, 257, 4, 2
-    sd = V.make_state_dict(1, G, input_dim=D, depth=depth)
+    V, sd, _, G, B, D = _case(kind)
     V.train_steps(sd, [V.make_inputs(20 + s, B, G, input_dim=D) for s in range(3)])
     x, _ = V.make_inputs(99, B, G, input_dim=D)
     with torch.no_grad():
         want = V.forward(sd, x)
     err = ((p0.double() - want.double()).norm() / want.double().norm()).item()
-    print(f"\n[dp2] predictions after 3 DP steps vs full-batch oracle: L2-rel {err:.3e}")
+    print(f"\n[dp2 {kind}] predictions after 3 DP steps vs full-batch oracle: L2-rel {err:.3e}")
     assert err < 1e-3
