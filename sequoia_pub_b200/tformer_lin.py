@@ -294,6 +294,11 @@ class _FlatAggregator:
 
     def forward(self, x):
         self._ensure_flat()
+        n = self._cfg.num_clusters
+        if x.dim() >= 2 and n > 1 and x.numel() == x.shape[0] * x.shape[-1]:
+            # one token per slide: `x + pos_emb1D` broadcasts it over the N positions in the reference (tformer_lin.py:100,
+            # vit.py:109) — which is what spatial_vis/visualize.py:80 relies on when it passes an unbatched [100, D] tensor
+            x = x.reshape(x.shape[0], 1, x.shape[-1]).expand(x.shape[0], n, x.shape[-1])
         if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self._params)):
             return _ViSFunction.apply(self, x, *self._params)
         return self._forward_impl(x, keep=False)[0]

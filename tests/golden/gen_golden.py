@@ -1,7 +1,7 @@
 """Generates the golden fixtures by running the UNMODIFIED reference classes (imported from /root/reference)
 on weights / inputs produced by the oracle's deterministic generators.  Run in the build container only:
 
-    python tests/golden/gen_golden.py [resnet] [vis] [kmeans] [metrics] [vit]
+    python tests/golden/gen_golden.py [resnet] [vis] [kmeans] [metrics] [vit] [spatial]
 
 The fixtures travel with the repo; /root/reference does not exist on the GPU box.
 """
@@ -193,6 +193,76 @@ def gen_vit():
             out[f"{tag}_pred_after3"] = ref(x).numpy()
     np.savez_compressed(os.path.join(HERE, "vit_golden.npz"), **out)
     print("vit golden:", {k: v.shape for k, v in out.items()})
+
+
+def spatial_case():
+    """Synthetic tissue grid shared by the generator and tests/test_spatial_cpu.py: 23 x 19 tile grid with holes."""
+    import pandas as pd
+    rs = np.random.RandomState(7)
+    ps = 256
+    pts = [(c, r) for c in range(23) for r in range(19) if rs.rand() < 0.8 and not (8 <= c < 12 and r < 6)]
+    df = pd.DataFrame([(c * ps + 1024, r * ps + 512) for c, r in pts], columns=["xcoord", "ycoord"])
+    df["xcoord_tf"] = ((df["xcoord"] - min(df["xcoord"])) / ps).astype(int)          # visualize.py:213-214
+    df["ycoord_tf"] = ((df["ycoord"] - min(df["ycoord"])) / ps).astype(int)
+    return df, ps
+
+
+def spatial_tile_feature(col, row, dim):
+    g = torch.Generator().manual_seed(int(col) * 7919 + int(row))
+    return torch.relu(torch.randn(dim, generator=g)) * 0.5
+
+
+def gen_spatial():
+    """The reference's own `sliding_window_method` (spatial_vis/visualize.py:35-102, extracted with ast: the module imports
+    openslide and timm) driven by stub `slide` / `transforms_` / feature model and the reference ViS / ViT classes on CPU."""
+    import ast
+    import types
+    from einops import rearrange
+    stub = types.ModuleType("src.he2rna")
+    stub.compute_correlations = lambda *a, **k: None
+    sys.modules["src.he2rna"] = stub
+    from oracle import vis_oracle as V
+    from oracle import vit_oracle as T
+    from src.tformer_lin import ViS
+    from src.vit import ViT
+    src = open("/root/reference/spatial_vis/visualize.py").read()
+    fn = [n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "sliding_window_method"][0]
+    D = 64
+
+    class Patch:
+        def __init__(self, col, row):
+            self.col, self.row = col, row
+
+        def convert(self, mode):
+            return self
+
+    class Slide:
+        def read_region(self, loc, level, size):
+            return Patch(*loc)
+
+    class Feat:
+        def forward_extract(self, x):
+            return x
+
+    ns = {"np": np, "torch": torch, "tqdm": lambda it: it, "rearrange": rearrange, "slide": Slide(),
+          "transforms_": lambda p: spatial_tile_feature(p.col, p.row, D)}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "visualize.py", "exec"), ns)
+    df, ps = spatial_case()
+    vis = ViS(num_outputs=9, input_dim=D, depth=1, nheads=2, dimensions_f=64, dimensions_s=64, dimensions_c=64, device="cpu")
+    vis.load_state_dict(V.make_state_dict(11, 9, input_dim=D, depth=1, nheads=2))
+    vit = ViT(num_outputs=9, dim=D, depth=1, heads=2, mlp_dim=128, dim_head=64, device="cpu")
+    vit.load_state_dict(T.make_state_dict(12, 9, dim=D, depth=1, heads=2, mlp_dim=128))
+    genes = [0, 3, 8]
+    out = {}
+    for name, model in (("vis", vis.eval()), ("vit", vit.eval())):
+        for stride in (1, 4, 10):
+            preds = ns["sliding_window_method"](df=df, patch_size_resized=ps, feat_model=Feat(), model=model, inds_gene_of_interest=genes,
+                                                stride=stride, feat_model_type="resnet", feat_dim=D, model_type=name, device="cpu")
+            ks = list(preds[genes[0]].keys())
+            out[f"{name}_s{stride}_keys"] = np.array(ks, dtype=np.int64)
+            out[f"{name}_s{stride}_vals"] = np.array([[preds[g][k] for g in genes] for k in ks], dtype=np.float32)
+            print("spatial golden", name, stride, len(ks))
+    np.savez_compressed(os.path.join(HERE, "spatial_golden.npz"), **out)
 
 
 if __name__ == "__main__":

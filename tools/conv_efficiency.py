@@ -30,5 +30,5 @@ for (st, b, n, (cin, cout, k, Hi, Ho)), l in zip(order, lines):
     floor = max(mb / PEAK_GBS * 1e3, gf / PEAK_TF * 1e3)
     tot += t
     ideal_tot += floor
-    print(f"L{st}.b{b}.{n:3s} {cin:5d} {cout:5d} {k}  {Hi:3d}->{Ho:3d} {M:8d} {gf:6.1f} {t:8.1f} {gf / t * 1e3:5.0f} {mb:6.1f} {floor:9.1f} {t / floor:8.1f}  {l[-1][-10:]}")
+    print(f"L{st}.b{b}.{n:3s} {cin:5d} {cout:5d} {k}  {Hi:3d}->{Ho:3d} {M:8d} {gf:6.1f} {t:8.1f} {gf / t * 1e3:5.0f} {mb:6.1f} {floor:9.1f} {t / floor:8.1f}  {' '.join(l[6:])[-22:]}")
 print(f"sum of measured {tot:.0f} us, sum of floors {ideal_tot:.0f} us, ratio {tot / ideal_tot:.2f}")
