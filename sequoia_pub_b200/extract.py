@@ -28,24 +28,27 @@ def select_keys(keys, max_patch_number=4000, rng=_random):
 
 class SlideExtractor:
     """Runs `model.extract_uint8` over all tiles of a slide.  H2D copies (pinned staging, copy stream) overlap compute, and
-    consecutive batches alternate between two compute lanes (stream + extractor workspace + device tile buffer each), so the
-    persistent convolution kernels of one batch fill the SMs the other leaves idle in partial waves and launch gaps."""
+    consecutive batches alternate between two compute lanes (stream + extractor workspace each), so the persistent
+    convolution kernels of one batch fill the SMs the other leaves idle in partial waves and launch gaps.  There are twice as
+    many device tile buffers as lanes: the tiles of a lane's NEXT batch are already on the device when its current batch
+    finishes (with one buffer per lane every batch would wait for its own H2D copy, ~8 % of the lane's time)."""
 
     LANES = 2
+    NBUF = 4
 
     def __init__(self, model, batch_size=64, tile_hw=(256, 256), device=None):
         self.model = model
         self.bs = batch_size
         self.device = torch.device(device if device is not None else "cuda")
         h, w = tile_hw
-        n = self.LANES
         self.copy_stream = torch.cuda.Stream(device=self.device)
-        self.lanes = [torch.cuda.Stream(device=self.device) for _ in range(n)]
+        self.lanes = [torch.cuda.Stream(device=self.device) for _ in range(self.LANES)]
+        n = self.NBUF
         self.dev_buf = [torch.empty(batch_size, h, w, 3, dtype=torch.uint8, device=self.device) for _ in range(n)]
-        self.pin_buf = [torch.empty(batch_size, h, w, 3, dtype=torch.uint8).pin_memory() for _ in range(n)]
+        self.pin_buf = [torch.empty(batch_size, h, w, 3, dtype=torch.uint8, pin_memory=True) for _ in range(n)]
         self.copied = [torch.cuda.Event() for _ in range(n)]
         self.consumed = [torch.cuda.Event() for _ in range(n)]
-        self.workspaces = [None] * n
+        self.workspaces = [None] * self.LANES
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
@@ -72,31 +75,31 @@ class SlideExtractor:
         for s in self.lanes:
             s.wait_stream(main)
         nb = (n + self.bs - 1) // self.bs
-        L = self.LANES
+        L, NB = self.LANES, self.NBUF
         for b in range(nb):
             lo, hi = b * self.bs, min(n, (b + 1) * self.bs)
-            slot = b % L
+            slot, li = b % NB, b % L
             with torch.cuda.stream(self.copy_stream):
-                if b >= L:
-                    self.copy_stream.wait_event(self.consumed[slot])    # device buffer free again
+                if b >= NB:
+                    self.copy_stream.wait_event(self.consumed[slot])    # device buffer free again (batch b - NBUF is done)
                 src = tiles[lo:hi]
                 if not pinned:
-                    if b >= L:
+                    if b >= NB:
                         self.copied[slot].synchronize()                 # staging buffer free again
                     self.pin_buf[slot][: hi - lo].copy_(src)
                     src = self.pin_buf[slot][: hi - lo]
                 self.dev_buf[slot][: hi - lo].copy_(src, non_blocking=True)
                 self.copied[slot].record(self.copy_stream)
-            lane = self.lanes[slot]
+            lane = self.lanes[li]
             with torch.cuda.stream(lane):
                 lane.wait_event(self.copied[slot])
                 buf = self.dev_buf[slot][: hi - lo]
-                self.model._run(buf, 0, hi - lo, buf.shape[1], buf.shape[2], out[lo:hi], workspace=self._workspace(slot, buf.shape[1], buf.shape[2]))
+                self.model._run(buf, 0, hi - lo, buf.shape[1], buf.shape[2], out[lo:hi], workspace=self._workspace(li, buf.shape[1], buf.shape[2]))
                 self.consumed[slot].record(lane)
             self.h2d_bytes += (hi - lo) * tiles[0].numel()
         for s in self.lanes:
             main.wait_stream(s)
-        host = torch.empty(out.shape, dtype=torch.float32).pin_memory()
+        host = torch.empty(out.shape, dtype=torch.float32, pin_memory=True)   # straight from the pinned allocator: no pageable copy
         host.copy_(out, non_blocking=True)
         main.synchronize()
         self.d2h_bytes += host.numel() * 4

@@ -35,9 +35,7 @@ def read_tiles(f, keys, pinned=True):
     shape = tuple(f[keys[0]].shape)
     if isinstance(f, hdf5.File):
         import torch
-        buf = torch.empty((len(keys),) + shape, dtype=torch.uint8)
-        if pinned and torch.cuda.is_available():
-            buf = buf.pin_memory()
+        buf = torch.empty((len(keys),) + shape, dtype=torch.uint8, pin_memory=bool(pinned and torch.cuda.is_available()))
         f.read_many(keys, buf)
         return buf
     out = np.empty((len(keys),) + shape, dtype=np.uint8)
