@@ -521,10 +521,11 @@ def main():
         roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (implicit-GEMM conv, bf16 -> fp32 TMEM)",
                 "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
                 "peak_source": pk["source"] + " bf16 sustained", "traffic": ncu_traffic("resnet"),
-                "traffic_note": "dram read+write bytes per launch, mean over the 53 launches of one batch (ncu, profiles/r01_traffic.json)",
+                "traffic_note": "dram read+write bytes per launch, mean over the gemm_tc_kernel launches of one batch (ncu, profiles/r01_traffic.json; captured before the stem left this kernel: 53 launches)",
                 "launches": n, "avg_launch_us": tms * 1e3 / max(n, 1),
                 "kernel_share_of_step": tms / ser_ms, "serialized_step_ms": ser_ms,
-                "timing_note": "kernel durations and share measured on one stream (no inter-batch overlap)",
+                "timing_note": "kernel durations and share measured on one stream (no inter-batch overlap); the per-launch event brackets serialise launches that "
+                               "overlap through programmatic dependent launch in the untimed step, so the share can read slightly above 1 and `achieved` is conservative",
                 "issued_mma_tflops": fl / (tms * 1e-3) / 1e12}
         if roof["traffic"]:
             # secondary bound: DRAM bytes the same launches moved (ncu) over their live duration
