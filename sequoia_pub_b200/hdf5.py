@@ -363,8 +363,9 @@ class File:
         self._cache[name] = ds
         return ds
 
-    def read_many(self, names, out):
-        """Reads the datasets `names` (all of shape out.shape[1:], dtype out.dtype) into out[i], one preadv each."""
+    def read_many(self, names, out, threads=None):
+        """Reads the datasets `names` (all of shape out.shape[1:], dtype out.dtype) into out[i], one preadv each, spread over
+        `threads` worker threads (preadv releases the GIL; default min(8, cpu count), 1 = in the calling thread)."""
         self._check_open()
         if len(names) > out.shape[0]:
             raise ValueError("output buffer too small")
@@ -376,12 +377,29 @@ class File:
         view = memoryview(arr).cast("B")
         item_shape = tuple(arr.shape[1:])
         item = int(np.prod(item_shape, dtype=np.int64)) * arr.dtype.itemsize
-        for i, name in enumerate(names):
+        addrs = []
+        for name in names:
             ds = self[name]
             if ds.shape != item_shape or ds.dtype != arr.dtype:
                 raise ValueError(f"dataset {name} is {ds.dtype}{ds.shape}, expected {arr.dtype}{item_shape}")
-            if item:
-                self._pread_into(view[i * item:(i + 1) * item], ds._addr)
+            addrs.append(ds._addr)
+        if not item:
+            return out
+
+        def work(lo, hi):
+            for i in range(lo, hi):
+                self._pread_into(view[i * item:(i + 1) * item], addrs[i])
+
+        nthr = min(8, os.cpu_count() or 1) if threads is None else max(1, int(threads))
+        nthr = min(nthr, len(names))
+        if nthr == 1:
+            work(0, len(names))
+        else:
+            from concurrent.futures import ThreadPoolExecutor
+            step = (len(names) + nthr - 1) // nthr
+            with ThreadPoolExecutor(nthr) as pool:
+                for fut in [pool.submit(work, lo, min(lo + step, len(names))) for lo in range(0, len(names), step)]:
+                    fut.result()
         return out
 
     # -- writing the group structures ------------------------------------------------------------------------------
