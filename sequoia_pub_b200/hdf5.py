@@ -233,8 +233,8 @@ class File:
         names = self._pread(hsize, hdata)
         self._walk(btree, names)
 
-    def _messages(self, addr):
-        """Yields (type, flags, body) over a version-1 object header, following continuation blocks."""
+    def _messages(self, addr, positions=False):
+        """Yields (type, flags, body[, address of the body]) over a version-1 object header, following continuation blocks."""
         h = self._pread(16, addr)
         if h[0] != 1:
             raise HDF5Error(f"object header version {h[0]} is not supported (file written with libver='latest'?)")
@@ -252,12 +252,15 @@ class File:
                 seen += 1
                 if mtype == 0x10:
                     blocks.append(struct.unpack_from("<QQ", body))
+                elif positions:
+                    yield mtype, flags, body, a + p - msize
                 else:
                     yield mtype, flags, body
 
     def _find_symbol_table(self, addr):
-        for mtype, _, body in self._messages(addr):
+        for mtype, _, body, at in self._messages(addr, positions=True):
             if mtype == 0x11:
+                self._symtab_at = at                 # where "r+" re-links the group (the root header itself stays in place)
                 return struct.unpack_from("<QQ", body)
         raise HDF5Error("root group has no symbol table message (new-style groups are not supported)")
 
@@ -450,17 +453,20 @@ class File:
                 break
             level_nodes, level = upper, level + 1
         # root object header (symbol table message) and superblock
-        root = self._append(_object_header([_message(0x11, struct.pack("<QQ", btree_addr, heap_addr))], min_size=40))
-        self._root_header = root
         if self.mode == "w":
+            root = self._append(_object_header([_message(0x11, struct.pack("<QQ", btree_addr, heap_addr))], min_size=40))
+            self._root_header = root
             sb = _SIG + struct.pack("<BBBBBBBBHHI", 0, 0, 0, 0, 0, 8, 8, 0, _LEAF_K, _INTERNAL_K, 0)
             sb += struct.pack("<QQQQ", 0, _UNDEF, self._eof, _UNDEF)
             sb += struct.pack("<QQII", 0, root, 1, 0) + struct.pack("<QQ", btree_addr, heap_addr)
             os.pwrite(self._fd, sb, 0)
         else:
-            # the old heap / B-tree / root header stay behind as unreferenced file space, which the format allows
+            # re-link the existing root group: its symbol table message and the superblock's cached copy point at the new
+            # B-tree / heap (other messages of the root header are untouched); the old heap and B-tree stay behind as
+            # unreferenced file space, which the format allows
+            os.pwrite(self._fd, struct.pack("<QQ", btree_addr, heap_addr), self._base + self._symtab_at)
             os.pwrite(self._fd, struct.pack("<Q", self._eof), self._sb_at + self._eof_at)
-            os.pwrite(self._fd, struct.pack("<QQII", 0, root, 1, 0) + struct.pack("<QQ", btree_addr, heap_addr),
+            os.pwrite(self._fd, struct.pack("<QQII", 0, self._root_header, 1, 0) + struct.pack("<QQ", btree_addr, heap_addr),
                       self._sb_at + self._root_entry_at)
         self._dirty = False
 

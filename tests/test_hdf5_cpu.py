@@ -201,8 +201,12 @@ def test_feature_file_append_in_place(tmp_path):
 def test_append_to_the_library_file_and_error_paths(tmp_path):
     p = tmp_path / "lib.h5"
     p.write_bytes(open(GOLDEN, "rb").read())
+    root_before = struct.unpack_from("<Q", open(GOLDEN, "rb").read(), 512 + 64)[0]
     with hdf5.File(p, "r+") as f:
         f.create_dataset("cluster_features", data=np.arange(12, dtype=np.float32).reshape(3, 4))
+    entries, eof, base, size = check_structure(p)                # still a consistent file, user block and base address kept
+    assert base == 512 and base + eof == size and sorted(entries) == ["cluster_features", "testdouble"]
+    assert struct.unpack_from("<Q", p.read_bytes(), 512 + 64)[0] == root_before      # the library's root header is re-linked in place
     with hdf5.File(p, "r") as f:
         assert f.keys() == ["cluster_features", "testdouble"]
         assert np.array_equal(f["testdouble"][:].ravel(), np.linspace(0, 2 * np.pi, 9))
