@@ -38,6 +38,24 @@ def read_samples(df, features_path, feature_use="cluster_features", prefer_h5py=
         yield feats, torch.from_numpy(rna[i]), name, proj
 
 
+def filter_no_features(df, feature_path, feature_name, prefer_h5py=True):
+    """Rows of `df` whose feature file exists and holds a `feature_name` dataset — src/utils.py:20-40 restated over the HDF5
+    shim (a directory without a readable `<wsi>.h5`, or a file without the dataset, removes the slide)."""
+    remove, present = [], []
+    for proj in np.unique(df["tcga_project"]):
+        wsis = os.listdir(os.path.join(feature_path, proj))
+        for wsi in wsis:
+            try:
+                with hdf5.open_file(os.path.join(feature_path, proj, wsi, wsi + ".h5"), "r", prefer_h5py) as f:
+                    if feature_name not in list(f.keys()):
+                        remove.append(wsi)
+            except Exception:
+                remove.append(wsi)
+        present += wsis
+    remove += df[~df["wsi_file_name"].isin(present)]["wsi_file_name"].values.tolist()
+    return df[~df["wsi_file_name"].isin(remove)].reset_index(drop=True)
+
+
 class DeviceSlideDataset:
     def __init__(self, samples, device="cuda"):
         """samples: iterable of (features [100,D] or None, rna [G], wsi_file_name, tcga_project) — e.g. a

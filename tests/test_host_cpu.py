@@ -85,3 +85,12 @@ def test_device_dataset_from_feature_files(tmp_path, capsys):
             assert np.array_equal(f.numpy(), feats[name])
     ds = DeviceSlideDataset.from_files(df, str(tmp_path), device="cpu", prefer_h5py=False)
     assert len(ds) == 3 and ds.dropped == ["TCGA-C"] and ds.feature_dim == 32 and ds.num_genes == 3
+    # src/utils.py:20-40: slides without a feature directory, without a readable file or without the dataset are filtered out
+    from sequoia_pub_b200.data import filter_no_features
+    (tmp_path / "P2" / "TCGA-E").mkdir()
+    (tmp_path / "P2" / "TCGA-E" / "TCGA-E.h5").write_bytes(b"garbage")
+    df2 = pd.concat([df, pd.DataFrame({"wsi_file_name": ["TCGA-E"], "tcga_project": ["P2"]})], ignore_index=True)
+    df2["wsi_file_name"] = df2["wsi_file_name"].str.replace(".svs", "")
+    kept = filter_no_features(df2, str(tmp_path), "cluster_features", prefer_h5py=False)
+    assert kept["wsi_file_name"].tolist() == ["TCGA-A", "TCGA-B", "GTEX-D"] and kept.index.tolist() == [0, 1, 2]
+    assert filter_no_features(df2, str(tmp_path), "uni_features", prefer_h5py=False).empty
