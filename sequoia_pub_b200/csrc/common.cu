@@ -76,7 +76,7 @@ int launch_gemm_dispatch(int bn, int cls, int fuse3, const CUtensorMap* maps, co
 #define SQ_ALL_BN(CLS) SQ_CASE(64, CLS) SQ_CASE(128, CLS) SQ_CASE(256, CLS)
 #define SQ_FUSED(CLS) SQ_CASE3(128, CLS) SQ_CASE3(192, CLS) SQ_CASE3(256, CLS)
     SQ_FUSED(EPI_F32) SQ_FUSED(EPI_GELU) SQ_FUSED(EPI_DGELU) SQ_FUSED(EPI_LN64)
-    SQ_ALL_BN(EPI_CONV) SQ_ALL_BN(EPI_F32) SQ_ALL_BN(EPI_GELU) SQ_ALL_BN(EPI_DGELU) SQ_ALL_BN(EPI_LN64) SQ_ALL_BN(EPI_GENERIC)
+    SQ_ALL_BN(EPI_CONV) SQ_ALL_BN(EPI_CONV_PF) SQ_ALL_BN(EPI_F32) SQ_ALL_BN(EPI_GELU) SQ_ALL_BN(EPI_DGELU) SQ_ALL_BN(EPI_LN64) SQ_ALL_BN(EPI_GENERIC)
 #undef SQ_FUSED
 #undef SQ_ALL_BN
 #undef SQ_CASE3

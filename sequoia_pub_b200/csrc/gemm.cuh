@@ -78,12 +78,13 @@ enum EpiClass {
     EPI_GELU = 3,      // bias, row bias, save_pre, exact GELU -> planes / fp32                         (W1, combine)
     EPI_DGELU = 4,     // multiply by GELU'(aux) -> planes / fp32                                       (dgrad through a GELU)
     EPI_LN64 = 5,      // bias, save_pre, per-head LayerNorm(64) + GELU -> planes / fp32                (local branch)
-    EPI_NUM_CLASSES = 6
+    EPI_CONV_PF = 6,   // EPI_CONV with 32-column chunks and the residual tile prefetched one chunk ahead (opt-in, SQ_CONV_EPI_PF=1)
+    EPI_NUM_CLASSES = 7
 };
 __host__ __device__ constexpr bool epi_has(int cls, int opt) {
     // opt: 0 alpha, 1 bias, 2 rowbias, 3 res_f32, 4 res_bf, 5 save_pre, 6 relu, 7 gelu, 8 dgelu, 9 ln64, 10 out_f32, 11 out_bf, 12 out_lo
     return cls == EPI_GENERIC ? true
-         : cls == EPI_CONV ? (opt == 1 || opt == 4 || opt == 6 || opt == 7 || opt == 10 || opt == 11)
+         : (cls == EPI_CONV || cls == EPI_CONV_PF) ? (opt == 1 || opt == 4 || opt == 6 || opt == 7 || opt == 10 || opt == 11)
          : cls == EPI_F32 ? (opt == 0 || opt == 1 || opt == 2 || opt == 3 || opt == 10 || opt == 11 || opt == 12)
          : cls == EPI_GELU ? (opt == 1 || opt == 2 || opt == 5 || opt == 7 || opt == 10 || opt == 11 || opt == 12)
          : cls == EPI_DGELU ? (opt == 0 || opt == 8 || opt == 10 || opt == 11 || opt == 12)
@@ -106,7 +107,7 @@ __device__ __forceinline__ void epilogue_apply(float* v, long long row, int col0
     if constexpr (!epi_has(CLS, 11)) e.out_hi = nullptr;
     if constexpr (!epi_has(CLS, 12)) e.out_lo = nullptr;
     if constexpr (CLS != EPI_GENERIC) {
-        if constexpr (CLS == EPI_CONV) e.act = (e.act == ACT_RELU || e.act == ACT_GELU) ? e.act : ACT_NONE;
+        if constexpr (CLS == EPI_CONV || CLS == EPI_CONV_PF) e.act = (e.act == ACT_RELU || e.act == ACT_GELU) ? e.act : ACT_NONE;
         else if constexpr (CLS == EPI_F32) e.act = ACT_NONE;
         else if constexpr (CLS == EPI_GELU) e.act = ACT_GELU;
         else if constexpr (CLS == EPI_DGELU) e.act = ACT_MUL_DGELU;
@@ -330,6 +331,91 @@ __device__ __forceinline__ void epilogue_conv_staged(float* v, long long row_bas
     }
 }
 
+// ---- EPI_CONV_PF (opt-in, NOT yet validated on hardware: written at the end of round 1 after the GPU budget was spent).
+// The EPI_CONV kernels sit at the 168-register cap with spills (64 accumulator values + 8 residual vectors per lane), which is
+// why the residual loads cannot be hoisted there.  This variant walks the tile in 32-column chunks (32 values + 4 residual
+// vectors per lane), so the residual of chunk c+1 is requested before chunk c is processed and the residual of a tile's first
+// chunk before the warp waits for the accumulator — the K <= 512 1x1 expansions are bound by exactly that latency
+// (profiles/r01_resnet_per_conv_efficiency.txt).  Staging: 32 rows x 64 B per warp, 16-byte chunk s of row r stored at
+// chunk (s ^ ((r >> 1) & 3)): conflict-free for the row-per-lane and for the 8-rows-x-4-segments access patterns.
+constexpr int GEMM_PF_STG_BYTES = 32 * 64;
+__device__ __forceinline__ int pf_stg_off(int r, int s) { return r * 64 + ((s ^ ((r >> 1) & 3)) << 4); }
+
+__device__ __forceinline__ void conv_pf_load_res(uint4 (&rr)[4], const EpiParams& e, long long row_base, int lane, int M, int col0) {
+    const int r_sub = lane >> 2, seg = lane & 3;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const long long r = row_base + i * 8 + r_sub;
+        rr[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (r < M) rr[i] = *reinterpret_cast<const uint4*>(e.res_bf + r * e.ld_res + col0 + seg * 8);
+    }
+}
+
+// one 32-row x 32-column chunk: v = accumulator values of this lane's row, rr = the residual chunk in the coalesced pattern
+__device__ __forceinline__ void conv_pf_chunk(float (&v)[32], const uint4 (&rr)[4], bool has_res, long long row_base, int lane, int M,
+                                              int col0, const EpiParams& e, uint8_t* stg) {
+    const int r_sub = lane >> 2, seg = lane & 3;
+    if (e.bias) {
+        const float4* b4 = reinterpret_cast<const float4*>(e.bias + col0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float4 b = __ldg(b4 + i);
+            v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+        }
+    }
+    if (has_res) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(stg + pf_stg_off(i * 8 + r_sub, seg)) = rr[i];
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint4 t = *reinterpret_cast<const uint4*>(stg + pf_stg_off(lane, j));
+            const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                v[8 * j + 2 * k] += __uint_as_float(w[k] << 16);
+                v[8 * j + 2 * k + 1] += __uint_as_float(w[k] & 0xffff0000u);
+            }
+        }
+        __syncwarp();
+    }
+    if (e.act == ACT_RELU) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
+    } else if (e.act == ACT_GELU) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = gelu_f(v[i]);
+    }
+    if (e.out_hi) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint4 pk;
+            __nv_bfloat162 t;
+            t = __floats2bfloat162_rn(v[8 * j], v[8 * j + 1]); pk.x = *reinterpret_cast<uint32_t*>(&t);
+            t = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]); pk.y = *reinterpret_cast<uint32_t*>(&t);
+            t = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]); pk.z = *reinterpret_cast<uint32_t*>(&t);
+            t = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]); pk.w = *reinterpret_cast<uint32_t*>(&t);
+            *reinterpret_cast<uint4*>(stg + pf_stg_off(lane, j)) = pk;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const long long r = row_base + i * 8 + r_sub;
+            const uint4 t = *reinterpret_cast<const uint4*>(stg + pf_stg_off(i * 8 + r_sub, seg));
+            if (r < M) *reinterpret_cast<uint4*>(e.out_hi + r * e.ld_bf + col0 + seg * 8) = t;
+        }
+        __syncwarp();
+    }
+    if (e.out_f32) {
+        const long long r = row_base + lane;
+        if (r < M) {
+            float4* o4 = reinterpret_cast<float4*>(e.out_f32 + r * e.ld_f32 + col0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        }
+    }
+}
+
 constexpr int GEMM_THREADS = 384;      // warps 0-3: TMA producer, MMA issuer, TMEM allocator, idle; warps 4-11: epilogue
 constexpr int GEMM_EPI_WARPS = 8;      // two warps per TMEM lane quadrant, each draining half of the tile's columns
 constexpr int GEMM_BM = 128;
@@ -342,7 +428,8 @@ constexpr int GEMM_A_BYTES = GEMM_BM * GEMM_BK * 2;  // 16 KB
 template <int BN, int CLS = 0, int FUSE3 = 0> struct GemmCfg {
     static constexpr int B_BYTES = BN * GEMM_BK * 2;
     static constexpr int STAGE_BYTES = (FUSE3 ? 2 : 1) * (GEMM_A_BYTES + B_BYTES);
-    static constexpr int STAGING = (CLS == EPI_CONV) ? GEMM_EPI_WARPS * GEMM_STG_BYTES : 0;     // per-warp epilogue transposition buffers
+    static constexpr int STAGING = (CLS == EPI_CONV) ? GEMM_EPI_WARPS * GEMM_STG_BYTES
+                                 : (CLS == EPI_CONV_PF) ? GEMM_EPI_WARPS * GEMM_PF_STG_BYTES : 0;     // per-warp epilogue transposition buffers
     static constexpr int STAGES = FUSE3 ? (BN >= 192 ? 2 : (BN == 128 ? 3 : 4))
                                         : (BN == 256) ? (STAGING ? 3 : 4) : (BN == 128 ? (STAGING ? 5 : 6) : (STAGING ? 6 : 8));
     static_assert(STAGES * STAGE_BYTES + 1024 + 256 + STAGING <= 232448, "shared memory budget");
@@ -594,6 +681,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             const int mn = t - split * tiles_mn;
             const int mt = mn / p.num_n, nt = mn - mt * p.num_n;
             const int as = iter & 1; const uint32_t aphase = (iter >> 1) & 1;
+            [[maybe_unused]] uint4 pf_rr[4];
+            [[maybe_unused]] bool pf_staged = false;
+            if constexpr (CLS == EPI_CONV_PF) {
+                // the residual of the tile's first chunk does not depend on the MMAs: request it before waiting for them
+                const int pn0 = nt * BN;
+                pf_staged = !p.diag64 && !p.streamk && p.split_k <= 1 && pn0 + cend <= p.N && ((p.e.ld_bf | p.e.ld_f32 | p.e.ld_res) & 7) == 0 &&
+                            ((reinterpret_cast<uintptr_t>(p.e.bias) | reinterpret_cast<uintptr_t>(p.e.out_f32) |
+                              reinterpret_cast<uintptr_t>(p.e.out_hi) | reinterpret_cast<uintptr_t>(p.e.res_bf)) & 15) == 0;
+                if (pf_staged && p.e.res_bf) conv_pf_load_res(pf_rr, p.e, (long long)mt * GEMM_BM + q * 32, lane, p.M, pn0 + cbeg);
+            }
             const long long w3 = clock64();
             mbar_wait(&tmem_full[as], aphase);
             ew += clock64() - w3;
@@ -686,6 +783,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                             tmem_ld_wait();
                             if (nprev) streamk_add<32>(v, p.partial, nprev, BN, c, r_in);
                             epilogue_conv_staged<32>(v, row_base, lane, p.M, n0 + c, p.e, stg);
+                        }
+                    }
+                } else {
+                    for (int c = cbeg; c < cend && n0 + c < p.N; c += 32) {
+                        float v[32];
+                        tmem_ld32(tacc + c, v);
+                        tmem_ld_wait();
+                        if (nprev) streamk_add<32>(v, p.partial, nprev, BN, c, r_in);
+                        if (row_ok) epilogue_apply<32, CLS>(v, row, c0 + c, ncols, p.e);
+                    }
+                }
+            } else if constexpr (CLS == EPI_CONV_PF) {
+                uint8_t* stg = smem + STAGES * Cfg::STAGE_BYTES + 256 + (warp - 4) * GEMM_PF_STG_BYTES;
+                const long long row_base = (long long)mt * GEMM_BM + q * 32;
+                if (pf_staged) {
+                    const bool has_res = p.e.res_bf != nullptr;
+#pragma unroll
+                    for (int ci = 0; ci < BN / 64; ++ci) {
+                        const int c = cbeg + ci * 32;
+                        float v[32];
+                        uint4 rr_next[4];
+                        tmem_ld32(tacc + c, v);
+                        if (has_res && ci + 1 < BN / 64) conv_pf_load_res(rr_next, p.e, row_base, lane, p.M, n0 + c + 32);   // one chunk ahead
+                        tmem_ld_wait();
+                        conv_pf_chunk(v, pf_rr, has_res, row_base, lane, p.M, n0 + c, p.e, stg);
+                        if (ci + 1 < BN / 64) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) pf_rr[i] = rr_next[i];
                         }
                     }
                 } else {
@@ -972,7 +1097,9 @@ inline int gemm_launch(const GemmArgs& g, cudaStream_t st) {
         kp.kb_per_split = (total_kb + split - 1) / split;
         split = (total_kb + kp.kb_per_split - 1) / kp.kb_per_split;
         cls = epi_class_of(kp.e, split > 1, g.conv.enabled != 0 || g.epi_conv_pref != 0);
-        if (fuse3 && (cls == EPI_GENERIC || cls == EPI_CONV)) { fuse3 = 0; continue; }
+        static const int conv_pf = getenv("SQ_CONV_EPI_PF") ? atoi(getenv("SQ_CONV_EPI_PF")) : 0;   // opt-in until measured on hardware
+        if (conv_pf && cls == EPI_CONV) cls = EPI_CONV_PF;
+        if (fuse3 && (cls == EPI_GENERIC || cls == EPI_CONV || cls == EPI_CONV_PF)) { fuse3 = 0; continue; }
         break;
     }
     kp.split_k = split;
