@@ -94,3 +94,36 @@ def test_device_dataset_from_feature_files(tmp_path, capsys):
     kept = filter_no_features(df2, str(tmp_path), "cluster_features", prefer_h5py=False)
     assert kept["wsi_file_name"].tolist() == ["TCGA-A", "TCGA-B", "GTEX-D"] and kept.index.tolist() == [0, 1, 2]
     assert filter_no_features(df2, str(tmp_path), "uni_features", prefer_h5py=False).empty
+
+
+def test_read_tiles_builtin_codec_and_h5py_like_objects(tmp_path):
+    """pipeline.read_tiles = `f_read[key][:]` for every key (compute_features_hdf5.py:117): in-place bulk read with the built-in
+    codec, per-dataset `read_direct` with anything h5py-shaped; key order (including a random.sample order) is preserved."""
+    import numpy as np
+    import torch
+    from sequoia_pub_b200 import hdf5, pipeline
+    rs = np.random.RandomState(1)
+    tiles = {f"{x}_{y}": rs.randint(0, 256, (16, 16, 3)).astype(np.uint8) for x in range(0, 1280, 256) for y in range(0, 768, 256)}
+    p = tmp_path / "s.hdf5"
+    with hdf5.File(p, "w") as f:
+        for k, v in tiles.items():
+            f.create_dataset(k, data=v)
+    with hdf5.File(p) as f:
+        keys = list(f.keys())[::-1]
+        got = pipeline.read_tiles(f, keys, pinned=False)
+        assert isinstance(got, torch.Tensor) and got.dtype == torch.uint8 and tuple(got.shape) == (len(keys), 16, 16, 3)
+        assert all(np.array_equal(got[i].numpy(), tiles[k]) for i, k in enumerate(keys))
+        assert pipeline.read_tiles(f, []).shape == (0, 256, 256, 3)
+
+    class FakeDataset:
+        def __init__(self, a):
+            self.a, self.shape = a, a.shape
+
+        def read_direct(self, out):
+            out[...] = self.a
+
+    class FakeFile(dict):
+        pass
+    ff = FakeFile({k: FakeDataset(v) for k, v in tiles.items()})
+    got2 = pipeline.read_tiles(ff, keys)
+    assert isinstance(got2, np.ndarray) and np.array_equal(got2, got.numpy())
