@@ -1,0 +1,360 @@
+// bf16 -> bf16 convolution / GEMM kernel of the feature extractors (ResNet-50 bottleneck convolutions, src/resnet.py:73-93):
+//
+//   out[M, N] = act( A[M, K] * W[N, K]^T + shift[N] (+ residual[M, N]) )        bf16 operands, fp32 accumulation in TMEM
+//
+// Same warp-specialised tcgen05 skeleton as gemm.cuh, re-designed around the two things the round-1 profile showed to be
+// the limits of these launches (profiles/r01_resnet_per_conv_efficiency.txt):
+//
+//  * CTA PAIRS (`cta_group::2`, cluster of two CTAs on one TPC): one tcgen05.mma covers a 256 x BN tile, each CTA stages
+//    its own 128 rows of A and only HALF of the weight tile, so the L2 -> shared-memory operand traffic per FLOP drops by a
+//    third and the pipeline gets deeper stages for the same shared memory.  Only the leader CTA issues MMAs; both CTAs'
+//    TMA loads complete on the leader's "full" barrier; tcgen05.commit multicasts "stage free" / "accumulator ready" to both.
+//  * TMA EPILOGUE: every epilogue warp owns a ring of D sub-tiles (32 rows x 64 channels, 4 KB, 128B-swizzled).  The residual
+//    sub-tile of item j+D-1 is requested by TMA while item j is processed (the K <= 512 expansions were bound by the latency of
+//    register loads of the residual), shift + residual + ReLU happen IN PLACE in that sub-tile, and the result leaves through
+//    `cp.async.bulk.tensor` stores (UTMASTG) - no per-lane global loads / stores at all.
+//
+// A is either a plain [M, K] matrix (1x1 stride-1 convolutions) or an NHWC tensor walked as one 4-D TMA box per filter tap.
+#pragma once
+#include "gemm.cuh"
+
+namespace sq {
+
+struct CgParams {
+    int M, N;
+    int num_n;           // BN-wide column tiles
+    int total_tiles;     // (pairs of) 128-row tiles x column tiles
+    int nk;              // 64-wide k-blocks
+    int conv, cblocks, S, stride, pad, tiles_per_img, BH, BIMG;
+    const float* bias;   // [N] folded BatchNorm shift
+    int relu, has_res;
+};
+
+template <int BN, int CG, int D> struct CgCfg {
+    static constexpr int B_ROWS = BN / CG;                        // rows of the weight tile this CTA stages
+    static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
+    static constexpr int B_BYTES = B_ROWS * GEMM_BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int NCHUNK = BN / 64;                        // 64-column epilogue items per tile
+    static constexpr int CPH = NCHUNK >= 2 ? NCHUNK / 2 : 1;      // items per tile of one epilogue warp
+    static constexpr int NWORK = NCHUNK >= 2 ? 8 : 4;             // epilogue warps with work (2 per TMEM lane quadrant when BN >= 128)
+    static constexpr int SUB_BYTES = 32 * 128;
+    static constexpr int RING_BYTES = NWORK * D * SUB_BYTES;
+    static constexpr int BAR_BYTES = 1024;
+    static constexpr int BUDGET = 232448 - 1024 - BAR_BYTES - RING_BYTES;
+    static constexpr int STAGES = BUDGET / STAGE_BYTES > 8 ? 8 : BUDGET / STAGE_BYTES;
+    static_assert(STAGES >= 2, "shared memory budget");
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + RING_BYTES + BAR_BYTES + 1024;
+    static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
+};
+
+template <int BN, int CG, int D>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+convgemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                const __grid_constant__ CUtensorMap mapR, const __grid_constant__ CUtensorMap mapO, const CgParams p) {
+    using Cfg = CgCfg<BN, CG, D>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* ring = smem + STAGES * Cfg::STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + Cfg::RING_BYTES);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + STAGES;
+    uint64_t* tmem_full = bars + 2 * STAGES;
+    uint64_t* tmem_empty = bars + 2 * STAGES + 2;
+    uint64_t* res_full = bars + 2 * STAGES + 4;                   // [NWORK][D]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_full + Cfg::NWORK * D);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+    const int cluster_id = blockIdx.x / CG, num_clusters = gridDim.x / CG;
+
+    asm volatile("griddepcontrol.launch_dependents;");
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&mapA); tma_prefetch_desc(&mapB); tma_prefetch_desc(&mapR); tma_prefetch_desc(&mapO);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], CG * Cfg::NWORK); }
+        for (int i = 0; i < Cfg::NWORK * D; ++i) mbar_init(&res_full[i], 1);
+        mbar_fence_init();
+    }
+    if (warp == 2) { if constexpr (CG == 2) tmem_alloc_pair(tmem_ptr, Cfg::TMEM_COLS); else tmem_alloc(tmem_ptr, Cfg::TMEM_COLS); }
+    __syncwarp();
+    tc_fence_before();
+    if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();      // the peer's barriers are initialised too
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+
+    const int my_tiles = cluster_id < p.total_tiles ? (p.total_tiles - cluster_id + num_clusters - 1) / num_clusters : 0;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            // ===================== TMA producer (both CTAs of a pair; completion on the leader's barrier) =====================
+            int stage = 0; uint32_t phase = 0;
+            for (int ti = 0; ti < my_tiles; ++ti) {
+                const int t = cluster_id + ti * num_clusters;
+                const int pm = t / p.num_n, nt = t - pm * p.num_n;
+                const int mt = pm * CG + (int)rank;
+                const int m0 = mt * GEMM_BM, nb0 = nt * BN + (int)rank * Cfg::B_ROWS;
+                int img = 0, hin0 = 0;
+                if (p.conv) {
+                    if (p.BIMG == 1) { img = mt / p.tiles_per_img; hin0 = (mt - img * p.tiles_per_img) * p.BH * p.stride - p.pad; }
+                    else { img = mt * p.BIMG; hin0 = -p.pad; }
+                }
+                int tap_r = 0, tap_s = 0, cb = 0;
+                for (int kb = 0; kb < p.nk; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+                    uint8_t* sb = sa + Cfg::A_BYTES;
+                    if constexpr (CG == 2) {
+                        if (rank == 0) mbar_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
+                        const uint32_t bar = mapa_u32(&full[stage], 0);
+                        if (p.conv) tma_load_4d_pair(&mapA, bar, sa, cb * GEMM_BK, tap_s - p.pad, hin0 + tap_r, img);
+                        else tma_load_2d_pair(&mapA, bar, sa, kb * GEMM_BK, m0);
+                        tma_load_2d_pair(&mapB, bar, sb, kb * GEMM_BK, nb0);
+                    } else {
+                        mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+                        if (p.conv) tma_load_4d(&mapA, &full[stage], sa, cb * GEMM_BK, tap_s - p.pad, hin0 + tap_r, img);
+                        else tma_load_2d(&mapA, &full[stage], sa, kb * GEMM_BK, m0);
+                        tma_load_2d(&mapB, &full[stage], sb, kb * GEMM_BK, nb0);
+                    }
+                    if (p.conv && ++cb == p.cblocks) { cb = 0; if (++tap_s == p.S) { tap_s = 0; ++tap_r; } }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (rank == 0) {
+            // ===================== MMA issuer (leader CTA) =====================
+            const uint32_t idesc = make_idesc_bf16(BN, 0, 0, GEMM_BM * CG);
+            int stage = 0; uint32_t phase = 0;
+            for (int ti = 0; ti < my_tiles; ++ti) {
+                const int as = ti & 1; const uint32_t aphase = (ti >> 1) & 1;
+                mbar_wait(&tmem_empty[as], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t tacc = tmem_base + as * BN;
+                for (int kb = 0; kb < p.nk; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t a_base = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                        const uint32_t b_base = a_base + Cfg::A_BYTES;
+#pragma unroll
+                        for (int k = 0; k < GEMM_BK / 16; ++k) {
+                            const uint64_t da = make_smem_desc(a_base + k * 32, 1024, 0);
+                            const uint64_t db = make_smem_desc(b_base + k * 32, 1024, 0);
+                            if constexpr (CG == 2) umma_bf16_pair(tacc, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                            else umma_bf16(tacc, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                        }
+                        if constexpr (CG == 2) { umma_commit_pair(&empty[stage]); if (kb == p.nk - 1) umma_commit_pair(&tmem_full[as]); }
+                        else { umma_commit(&empty[stage]); if (kb == p.nk - 1) umma_commit(&tmem_full[as]); }
+                    }
+                    __syncwarp();
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp >= 4 && warp - 4 < Cfg::NWORK) {
+        // ===================== epilogue: TMEM -> (+ shift, + residual, ReLU) in the warp's ring -> TMA store =====================
+        const int ew = warp - 4, q = warp & 3, half = ew >> 2;
+        uint8_t* myring = ring + ew * D * Cfg::SUB_BYTES;
+        uint64_t* myfull = res_full + ew * D;
+        const bool has_res = p.has_res != 0;
+        const int n_items = my_tiles * Cfg::CPH;
+        auto item_coords = [&](int j, int& row0, int& col0) {
+            const int ti = j / Cfg::CPH, c = half * Cfg::CPH + (j - ti * Cfg::CPH);
+            const int t = cluster_id + ti * num_clusters;
+            const int pm = t / p.num_n, nt = t - pm * p.num_n;
+            row0 = (pm * CG + (int)rank) * GEMM_BM + q * 32;
+            col0 = nt * BN + c * 64;
+        };
+        auto request_res = [&](int j) {          // lane 0: residual sub-tile of item j into its ring slot
+            int row0, col0; item_coords(j, row0, col0);
+            const int s = j % D;
+            mbar_expect_tx(&myfull[s], Cfg::SUB_BYTES);
+            tma_load_2d(&mapR, &myfull[s], myring + s * Cfg::SUB_BYTES, col0, row0);
+        };
+        if (has_res && lane == 0)
+            for (int j = 0; j < D - 1 && j < n_items; ++j) request_res(j);
+        const uint32_t tmem_empty_leader = (CG == 2) ? mapa_u32(tmem_empty, 0) : 0u;
+        int j = 0;
+        for (int ti = 0; ti < my_tiles; ++ti) {
+            const int as = ti & 1; const uint32_t aphase = (ti >> 1) & 1;
+            mbar_wait(&tmem_full[as], aphase);
+            tc_fence_after();
+            const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+#pragma unroll 1
+            for (int cc = 0; cc < Cfg::CPH; ++cc, ++j) {
+                const int c = half * Cfg::CPH + cc, slot = j % D;
+                uint8_t* sl = myring + slot * Cfg::SUB_BYTES;
+                int row0, col0; item_coords(j, row0, col0);
+                float v[64];
+                tmem_ld32(tacc + c * 64, v);
+                tmem_ld32(tacc + c * 64 + 32, v + 32);
+                if (has_res) {
+                    mbar_wait(&myfull[slot], (uint32_t)((j / D) & 1));
+                } else {
+                    if (lane == 0) bulk_wait_group_read<D - 1>();       // the store that last used this slot has read it
+                    __syncwarp();
+                }
+                tmem_ld_wait();
+                const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float4 b = __ldg(b4 + i);
+                    v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+                }
+                uint8_t* rowp = sl + lane * 128;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    uint4* cell = reinterpret_cast<uint4*>(rowp + ((k ^ (lane & 7)) << 4));      // 128B swizzle: chunk ^ (row % 8)
+                    float* f = v + 8 * k;
+                    if (has_res) {
+                        const uint4 t = *cell;
+                        const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            f[2 * u] += __uint_as_float(w[u] << 16);
+                            f[2 * u + 1] += __uint_as_float(w[u] & 0xffff0000u);
+                        }
+                    }
+                    if (p.relu) {
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) f[u] = fmaxf(f[u], 0.0f);
+                    }
+                    uint4 pk; __nv_bfloat162 h2;
+                    h2 = __floats2bfloat162_rn(f[0], f[1]); pk.x = *reinterpret_cast<uint32_t*>(&h2);
+                    h2 = __floats2bfloat162_rn(f[2], f[3]); pk.y = *reinterpret_cast<uint32_t*>(&h2);
+                    h2 = __floats2bfloat162_rn(f[4], f[5]); pk.z = *reinterpret_cast<uint32_t*>(&h2);
+                    h2 = __floats2bfloat162_rn(f[6], f[7]); pk.w = *reinterpret_cast<uint32_t*>(&h2);
+                    *cell = pk;
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_2d(&mapO, sl, col0, row0);
+                    bulk_commit_group();
+                    if (has_res && j + D - 1 < n_items) {
+                        if (j >= 1) bulk_wait_group_read<1>();          // the store of item j-1 has read slot (j-1) % D
+                        request_res(j + D - 1);
+                    }
+                }
+                __syncwarp();
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { if constexpr (CG == 2) mbar_arrive_cluster(tmem_empty_leader + as * 8); else mbar_arrive(&tmem_empty[as]); }
+        }
+        if (lane == 0) bulk_wait_group_read<0>();
+    }
+    __syncwarp();                 // the single-lane roles rejoin their warps before the aligned barrier
+    tc_fence_before();
+    if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+    if (warp == 2) { if constexpr (CG == 2) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS); else tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+struct ConvGemmArgs {
+    int M, N, K;                 // K = R*S*Cin
+    const bf16* A; long long lda;
+    const bf16* W;               // [N][K]
+    const float* bias;
+    const bf16* res;             // [M][N] or null
+    bf16* out;                   // [M][N]
+    int relu;
+    ConvGeom conv;
+    int block_n;                 // 0 = auto
+    int cta_group;               // 0 = auto
+};
+
+template <int BN, int CG, int D>
+int convgemm_launch_inst(const CUtensorMap* maps, const CgParams& kp, int grid, cudaStream_t st) {
+    using Cfg = CgCfg<BN, CG, D>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t err = cudaFuncSetAttribute(convgemm_kernel<BN, CG, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        if (err != cudaSuccess) { set_error("convgemm: cudaFuncSetAttribute: %s", cudaGetErrorString(err)); return -1; }
+        configured = true;
+    }
+    static const int pdl = getenv("SQ_PDL") ? atoi(getenv("SQ_PDL")) : 1;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (CG == 2) { attr[na].id = cudaLaunchAttributeClusterDimension; attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1; ++na; }
+    if (pdl) { attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[na].val.programmaticStreamSerializationAllowed = 1; ++na; }
+    cfg.attrs = attr; cfg.numAttrs = na;
+    cudaError_t err = cudaLaunchKernelEx(&cfg, convgemm_kernel<BN, CG, D>, maps[0], maps[1], maps[2], maps[3], kp);
+    if (err == cudaSuccess) err = cudaGetLastError();
+    if (err != cudaSuccess) { set_error("convgemm launch: %s", cudaGetErrorString(err)); return -1; }
+    return 0;
+}
+
+int convgemm_dispatch(int bn, int cg, const CUtensorMap* maps, const CgParams& kp, int grid, cudaStream_t st);   // resnet.cu
+
+// true when the launch fits this kernel (N a multiple of 64, channels a multiple of 64, tile geometry of the 4-D boxes)
+inline bool convgemm_supported(const ConvGemmArgs& g) {
+    if (g.N % 64 != 0 || g.K % 64 != 0 || !g.out || !g.bias) return false;
+    if ((reinterpret_cast<uintptr_t>(g.out) | reinterpret_cast<uintptr_t>(g.res) | reinterpret_cast<uintptr_t>(g.A) | reinterpret_cast<uintptr_t>(g.W)) & 15) return false;
+    return true;
+}
+
+inline int convgemm_launch(const ConvGemmArgs& g, cudaStream_t st) {
+    CgParams kp;
+    memset(&kp, 0, sizeof(kp));
+    int bn = g.block_n;
+    if (bn == 0) bn = g.N >= 256 ? 256 : (g.N >= 128 ? 128 : 64);
+    static const int env_cg = getenv("SQ_CONV_CG") ? atoi(getenv("SQ_CONV_CG")) : 0;
+    int cg = g.cta_group ? g.cta_group : (env_cg ? env_cg : 2);
+    if (cg == 1 && bn == 256) bn = 128;                     // a single CTA has no room for 256-wide stages beside the ring
+    if (g.N % bn != 0) bn = 64;
+    kp.M = g.M; kp.N = g.N;
+    const int num_m = (g.M + GEMM_BM - 1) / GEMM_BM;
+    kp.num_n = g.N / bn;
+    kp.total_tiles = ((num_m + cg - 1) / cg) * kp.num_n;
+    kp.bias = g.bias; kp.relu = g.relu; kp.has_res = g.res != nullptr;
+
+    CUtensorMap maps[4];
+    if (g.conv.enabled) {
+        const ConvGeom& c = g.conv;
+        if (c.C % 64 != 0) { set_error("conv: C=%d must be a multiple of 64", c.C); return -1; }
+        int BW = c.Wo, BH, BIMG = 1;
+        if (BW > 128 || 128 % BW != 0) { set_error("conv: Wo=%d must divide 128", c.Wo); return -1; }
+        BH = 128 / BW;
+        if (BH > c.Ho) { BIMG = BH / c.Ho; BH = c.Ho; if (BIMG * BH * BW != 128) { set_error("conv: tile does not fit Ho=%d Wo=%d", c.Ho, c.Wo); return -1; } }
+        if (c.Ho % BH != 0) { set_error("conv: Ho=%d not a multiple of %d", c.Ho, BH); return -1; }
+        kp.conv = 1; kp.cblocks = c.C / 64; kp.S = c.S; kp.stride = c.stride; kp.pad = c.pad;
+        kp.tiles_per_img = c.Ho / BH; kp.BH = BH; kp.BIMG = BIMG;
+        kp.nk = c.R * c.S * kp.cblocks;
+        if (g.M != c.batch * c.Ho * c.Wo) { set_error("conv: M mismatch"); return -1; }
+        cuuint64_t dims[4] = {(cuuint64_t)c.C, (cuuint64_t)c.W, (cuuint64_t)c.H, (cuuint64_t)c.batch};
+        cuuint64_t strides[3] = {(cuuint64_t)c.C * 2, (cuuint64_t)c.W * c.C * 2, (cuuint64_t)c.H * c.W * c.C * 2};
+        cuuint32_t box[4] = {64, (cuuint32_t)(BW * c.stride), (cuuint32_t)(BH * c.stride), (cuuint32_t)BIMG};
+        cuuint32_t estr[4] = {1, (cuuint32_t)c.stride, (cuuint32_t)c.stride, 1};
+        if (encode_map(&maps[0], g.A, 4, dims, strides, box, estr)) return -1;
+    } else {
+        kp.nk = g.K / GEMM_BK;
+        if (make_operand_map(&maps[0], g.A, 0, g.lda, g.M, g.K, GEMM_BM)) return -1;
+    }
+    if (make_operand_map(&maps[1], g.W, 0, (long long)kp.nk * 64, g.N, kp.nk * 64, bn / cg)) return -1;
+    // residual / output sub-tiles: 64 channels x 32 rows
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)g.N, (cuuint64_t)g.M}, strides[1] = {(cuuint64_t)g.N * 2};
+        cuuint32_t box[2] = {64, 32}, estr[2] = {1, 1};
+        if (encode_map(&maps[3], g.out, 2, dims, strides, box, estr)) return -1;
+        if (g.res) { if (encode_map(&maps[2], g.res, 2, dims, strides, box, estr)) return -1; }
+        else maps[2] = maps[3];
+    }
+    const int clusters_max = num_sms() / cg;
+    const int clusters = kp.total_tiles < clusters_max ? kp.total_tiles : clusters_max;
+    gemm_timing_begin(st, 2.0 * g.M * g.N * (double)kp.nk * 64);
+    const int rc = convgemm_dispatch(bn, cg, maps, kp, clusters * cg, st);
+    gemm_timing_end(st);
+    return rc;
+}
+
+}  // namespace sq

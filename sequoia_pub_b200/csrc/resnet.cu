@@ -6,7 +6,7 @@
 // kernel (gemm.cuh) whose epilogue applies shift + residual + ReLU.  The 7x7/2 stem goes through an im2col
 // buffer (K = 147 padded to 192) so it also runs on the tensor cores; uint8 -> /255 -> normalise is fused
 // into that im2col kernel (R4), max-pool and the 7x7 top-left average pool (fact 4) are small bandwidth kernels.
-#include "gemm.cuh"
+#include "convgemm.cuh"
 #include "../../include/sequoia_b200.h"
 #include <stdlib.h>
 
@@ -354,9 +354,32 @@ static ResNetWs ws_layout(int batch, int H, int W) {
     return w;
 }
 
+// one instantiation per (tile width, CTA group); ring depth 3
+int convgemm_dispatch(int bn, int cg, const CUtensorMap* maps, const CgParams& kp, int grid, cudaStream_t st) {
+#define SQ_CG_CASE(BN, CG) if (bn == BN && cg == CG) return convgemm_launch_inst<BN, CG, 3>(maps, kp, grid, st);
+    SQ_CG_CASE(64, 2) SQ_CG_CASE(128, 2) SQ_CG_CASE(256, 2) SQ_CG_CASE(64, 1) SQ_CG_CASE(128, 1)
+#undef SQ_CG_CASE
+    set_error("convgemm: no kernel for block_n %d cta_group %d", bn, cg);
+    return -1;
+}
+
+static int convgemm_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SQ_CONVGEMM"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v;
+}
+
 static int run_conv(const ConvSpec& c, const bf16* wbase, const float* sbase, const bf16* in, int batch, int H, int W, bf16* out_bf,
                     float* out_f32, const bf16* res, bool relu, cudaStream_t st, int* Ho_out, int* Wo_out) {
     const int Ho = (H + 2 * c.pad - c.k) / c.stride + 1, Wo = (W + 2 * c.pad - c.k) / c.stride + 1;
+    if (convgemm_enabled() && out_bf && !out_f32) {
+        ConvGemmArgs a; memset(&a, 0, sizeof(a));
+        a.M = batch * Ho * Wo; a.N = c.cout; a.K = c.k * c.k * c.cin;
+        a.A = in; a.lda = c.cin; a.W = wbase + c.w_off; a.bias = sbase + c.s_off; a.res = res; a.out = out_bf; a.relu = relu ? 1 : 0;
+        a.conv.enabled = (c.k == 1 && c.stride == 1) ? 0 : 1; a.conv.batch = batch; a.conv.H = H; a.conv.W = W; a.conv.C = c.cin; a.conv.Ho = Ho; a.conv.Wo = Wo;
+        a.conv.R = c.k; a.conv.S = c.k; a.conv.stride = c.stride; a.conv.pad = c.pad;
+        if (convgemm_supported(a)) { *Ho_out = Ho; *Wo_out = Wo; return convgemm_launch(a, st); }
+    }
     GemmArgs g; memset(&g, 0, sizeof(g));
     g.M = batch * Ho * Wo; g.N = c.cout; g.K = c.k * c.k * c.cin;
     g.A.hi = in; g.A.ld = c.cin;
