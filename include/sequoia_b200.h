@@ -120,6 +120,18 @@ SQ_API int sq_resnet50_extract(const void* input, int input_kind, int batch, int
                                const float* shifts, float* features, void* workspace, size_t workspace_bytes,
                                void* stream);
 
+/* One bottleneck convolution on the CTA-pair tcgen05 kernel (csrc/convgemm.cuh):
+ *   out = act(conv(in, weight) + shift [+ residual]),  NHWC bf16 in / out, weight [Cout][R][S][Cin] bf16 (BatchNorm scale folded),
+ *   shift fp32 [Cout], residual bf16 [batch*Ho*Wo, Cout] or NULL.  Cin and Cout multiples of 64.
+ * Building block of sq_resnet50_extract, exposed for tests (src/resnet.py:73-93: conv -> bn -> (+= residual) -> relu).
+ * block_n: 0 = auto, 64 / 128 / 256; cta_group: 0 = auto (2), 1, 2. */
+typedef struct sq_conv_desc {
+    int batch, H, W, Cin, Cout, R, S, stride, pad;
+    const void* in; const void* weight; const float* shift; const void* residual; void* out;
+    int relu, block_n, cta_group;
+} sq_conv_desc;
+SQ_API int sq_conv_bf16(const sq_conv_desc* desc, void* stream);
+
 /* ------------------------------------------------------------------ ViS aggregator (SummaryMixing transformer)
  * Replaces ViS.forward (src/tformer_lin.py:97-106 and everything it calls, :18-26,39-48,60-61,73-77), the autograd
  * backward behind loss.backward() (src/vit.py:179), nn.MSELoss (src/vit.py:129,166) and the AdamW step

@@ -76,16 +76,23 @@ def _gemv_block(a, kind):
     return _fold_hadd4(acc)
 
 
+def gemv_row_kind(row, nrows):
+    """Which sgemv_t micro-kernel sums row `row` of an (nrows, n) matrix: rows are taken four at a time by the 4-column
+    kernel (kind 0), then a remaining pair by the 2-column kernel (kind 1), then a remaining single row by the 1-column
+    kernel, whose summation order equals kind 0 (two 4-lane accumulators over 8-element groups, lo + hi, two hadds)."""
+    rem = nrows % 4
+    if row < nrows - rem:
+        return 0
+    r = row - (nrows - rem)
+    return 1 if (rem & 2) and r < 2 else 0
+
+
 def blas_order_gemv_row(a, row, nrows=6):
-    """Row `row` of (nrows, n) @ ones(n, 1) through cblas_sgemv: rows are processed four at a time by the 4-column
-    kernel, a remaining pair by the 2-column kernel (nrows = 6 -> rows 0-3 kind 0, rows 4-5 kind 1); the n % 4 tail is
-    summed left to right and added last."""
+    """Row `row` of (nrows, n) @ ones(n, 1) through cblas_sgemv (nrows >= 2; nrows = 6 -> rows 0-3 kind 0, rows 4-5
+    kind 1; nrows = 7 -> rows 0-3 kind 0, 4-5 kind 1, 6 kind 0); the n % 4 tail is summed left to right and added last."""
     a = np.asarray(a, dtype=f32)
     n = a.shape[0]
-    rem = nrows % 4
-    kind = 0 if row < nrows - rem else 1
-    if rem not in (0, 2):
-        raise NotImplementedError("only nrows % 4 in (0, 2) is restated")
+    kind = gemv_row_kind(row, nrows)
     m1 = n - (n & 3)
     y = f32(0)
     for b0 in range(0, m1, GEMV_NB):
@@ -160,8 +167,9 @@ def lloyd(X, centers, tol, max_iter=300):
                 new[l] += xc[i]
                 weight[l] += 1
         if (weight == 0).any():
-            raise RuntimeError("empty cluster: _relocate_empty_clusters_dense is not restated")
-        new *= (f32(1.0) / weight)[:, None]
+            relocate_empty_clusters(X, centers, new, weight, labels)
+        nz = weight > 0                                        # _average_centers: empty (un-relocated) clusters keep 0
+        new[nz] *= (f32(1.0) / weight[nz])[:, None]
         shift = np.sqrt(((new - centers) ** 2).sum(axis=1))
         centers = new
         if np.array_equal(labels, labels_old):
@@ -175,6 +183,54 @@ def lloyd(X, centers, tol, max_iter=300):
         d = csq[None, :] - f32(2.0) * (X @ centers.T)
         labels = np.argmin(d, axis=1).astype(np.int32)
     return labels, it + 1
+
+
+def pairwise_sum_f32(a):
+    """numpy's float32 pairwise summation of a contiguous 1-D array (loops_utils.h.src, PW_BLOCKSIZE 128, 8 accumulators):
+    the order `ndarray.sum(axis=1)` uses for every row of a C-contiguous matrix.  Restated for the CUDA kernel that has to
+    reproduce the relocation distances; asserted equal to numpy in tests/test_oracle_cpu.py."""
+    a = np.asarray(a, dtype=f32)
+    n = a.shape[0]
+    if n < 8:
+        res = f32(0)
+        for x in a:
+            res = f32(res + x)
+        return res
+    if n <= 128:
+        r = a[:8].copy()
+        m = n - (n % 8)
+        for i in range(8, m, 8):
+            r = (r + a[i:i + 8]).astype(f32)
+        res = f32(f32(f32(r[0] + r[1]) + f32(r[2] + r[3])) + f32(f32(r[4] + r[5]) + f32(r[6] + r[7])))
+        for x in a[m:]:
+            res = f32(res + x)
+        return res
+    n2 = n // 2
+    n2 -= n2 % 8
+    return f32(pairwise_sum_f32(a[:n2]) + pairwise_sum_f32(a[n2:]))
+
+
+def relocate_empty_clusters(X, centers_old, centers_new, weight, labels):
+    """_relocate_empty_clusters_dense (_k_means_common.pyx L167-211, sample_weight = 1): every empty cluster takes the
+    sample farthest from its own (old) centre, which is removed from the cluster it was assigned to.  `centers_new` holds
+    the per-cluster SUMS here (the averaging follows), labels are left as they are.
+    The candidates are `np.argpartition(distances, -n_empty)[:-n_empty-1:-1]`; numpy's introselect leaves the order inside
+    the partition unspecified, numpy 2.x on x86-64 returns them in descending distance (checked here against numpy on 720
+    random cases) and that is the order restated: empty cluster i (ascending id) takes the i-th farthest sample."""
+    empty = np.where(weight == 0)[0]
+    n_empty = empty.shape[0]
+    if n_empty == 0:
+        return
+    distances = ((X - centers_old[labels]) ** 2).sum(axis=1)
+    if np.max(distances) == 0:
+        return
+    far = np.argsort(-distances, kind="stable")[:n_empty]
+    for new_id, far_idx in zip(empty, far):
+        old_id = labels[far_idx]
+        centers_new[old_id] -= X[far_idx]
+        centers_new[new_id] = X[far_idx]
+        weight[new_id] = 1
+        weight[old_id] -= 1
 
 
 def fit_labels(features, k=100, seed=0, pot_mode="blas"):

@@ -64,3 +64,20 @@ def gemm(M, N, K, a_hi, b_hi, a_lo=None, b_lo=None, a_mn=False, b_mn=False, lda=
                                                                                b_map_mn, b_map_k, diag64)
     _lib.check(_lib.lib().sq_gemm_bf16(C.byref(d), _lib.stream_ptr()))
     return workspace
+
+
+def conv_bf16(x, w, shift, residual=None, relu=True, stride=1, pad=0, block_n=0, cta_group=0, out=None):
+    """x: bf16 NHWC [B,H,W,Cin]; w: bf16 [Cout,R,S,Cin]; shift: fp32 [Cout]; residual: bf16 [B,Ho,Wo,Cout] -> bf16 [B,Ho,Wo,Cout]
+    through `sq_conv_bf16` (the CTA-pair tcgen05 kernel with the TMA epilogue)."""
+    B, H, W, Cin = x.shape
+    Cout, R, S, _ = w.shape
+    Ho, Wo = (H + 2 * pad - R) // stride + 1, (W + 2 * pad - S) // stride + 1
+    if out is None:
+        out = torch.empty(B, Ho, Wo, Cout, dtype=torch.bfloat16, device=x.device)
+    d = _lib.ConvDesc()
+    d.batch, d.H, d.W, d.Cin, d.Cout, d.R, d.S, d.stride, d.pad = B, H, W, Cin, Cout, R, S, stride, pad
+    d.inp, d.weight, d.shift, d.out = x.data_ptr(), w.data_ptr(), shift.data_ptr(), out.data_ptr()
+    d.residual = residual.data_ptr() if residual is not None else None
+    d.relu, d.block_n, d.cta_group = int(relu), block_n, cta_group
+    _lib.check(_lib.lib().sq_conv_bf16(C.byref(d), _lib.stream_ptr()))
+    return out

@@ -37,6 +37,14 @@ class GemmDesc(C.Structure):
     ]
 
 
+class ConvDesc(C.Structure):
+    """Mirror of `sq_conv_desc`."""
+    _fields_ = [("batch", c_int), ("H", c_int), ("W", c_int), ("Cin", c_int), ("Cout", c_int), ("R", c_int), ("S", c_int),
+                ("stride", c_int), ("pad", c_int),
+                ("inp", c_void_p), ("weight", c_void_p), ("shift", c_void_p), ("residual", c_void_p), ("out", c_void_p),
+                ("relu", c_int), ("block_n", c_int), ("cta_group", c_int)]
+
+
 class VisConfig(C.Structure):
     """Mirror of `sq_vis_config`."""
     _fields_ = [("input_dim", c_int), ("depth", c_int), ("nheads", c_int), ("num_clusters", c_int), ("num_outputs", c_int)]
@@ -59,6 +67,7 @@ SIGNATURES = {
     "sq_side_stream_enable": (c_int, [c_int]),
     "sq_split_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_ll, c_int, c_ll, c_ll, c_void_p]),
     "sq_gemm_bf16": (c_int, [C.POINTER(GemmDesc), c_void_p]),
+    "sq_conv_bf16": (c_int, [C.POINTER(ConvDesc), c_void_p]),
     "sq_resnet50_num_convs": (c_int, []),
     "sq_resnet50_conv_info": (c_int, [c_int] + [C.POINTER(c_int)] * 5),
     "sq_resnet50_packed_weight_elems": (c_ll, []),

@@ -28,6 +28,7 @@ struct CgParams {
     int conv, cblocks, S, stride, pad, tiles_per_img, BH, BIMG;
     const float* bias;   // [N] folded BatchNorm shift
     int relu, has_res;
+    unsigned long long* prof;   // optional per-CTA cycle counters (sq_gemm_profile): [cta][16]
 };
 
 template <int BN, int CG, int D> struct CgCfg {
@@ -40,11 +41,13 @@ template <int BN, int CG, int D> struct CgCfg {
     static constexpr int NWORK = NCHUNK >= 2 ? 8 : 4;             // epilogue warps with work (2 per TMEM lane quadrant when BN >= 128)
     static constexpr int SUB_BYTES = 32 * 128;
     static constexpr int RING_BYTES = NWORK * D * SUB_BYTES;
-    static constexpr int BAR_BYTES = 1024;
-    static constexpr int BUDGET = 232448 - 1024 - BAR_BYTES - RING_BYTES;
+    static constexpr int BAR_BYTES = 512;
+    static constexpr int BIAS_BYTES = 2 * BN * 4;                 // shift table, double-buffered like the accumulator
+    static constexpr int BUDGET = 232448 - BAR_BYTES - BIAS_BYTES - RING_BYTES;
     static constexpr int STAGES = BUDGET / STAGE_BYTES > 8 ? 8 : BUDGET / STAGE_BYTES;
     static_assert(STAGES >= 2, "shared memory budget");
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + RING_BYTES + BAR_BYTES + 1024;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + RING_BYTES + BIAS_BYTES + BAR_BYTES;
+    static_assert((2 * STAGES + 4 + NWORK * D) * 8 + 4 <= BAR_BYTES, "barrier area");
     static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
 };
 
@@ -54,10 +57,10 @@ convgemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 const __grid_constant__ CUtensorMap mapR, const __grid_constant__ CUtensorMap mapO, const CgParams p) {
     using Cfg = CgCfg<BN, CG, D>;
     constexpr int STAGES = Cfg::STAGES;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    extern __shared__ __align__(1024) uint8_t smem[];              // 128B-swizzled tiles need 1024-byte alignment (checked below)
     uint8_t* ring = smem + STAGES * Cfg::STAGE_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + Cfg::RING_BYTES);
+    float* bias_smem = reinterpret_cast<float*>(ring + Cfg::RING_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + Cfg::RING_BYTES + Cfg::BIAS_BYTES);
     uint64_t* full = bars;
     uint64_t* empty = bars + STAGES;
     uint64_t* tmem_full = bars + 2 * STAGES;
@@ -72,6 +75,7 @@ convgemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 
     asm volatile("griddepcontrol.launch_dependents;");
     if (warp == 0 && lane == 0) {
+        if (smem_u32(smem) & 1023u) { printf("sequoia_b200: dynamic shared memory is not 1024-byte aligned\n"); __trap(); }
         tma_prefetch_desc(&mapA); tma_prefetch_desc(&mapB); tma_prefetch_desc(&mapR); tma_prefetch_desc(&mapO);
     }
     if (warp == 1 && lane == 0) {
@@ -94,6 +98,7 @@ convgemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         if (elect_one()) {
             // ===================== TMA producer (both CTAs of a pair; completion on the leader's barrier) =====================
             int stage = 0; uint32_t phase = 0;
+            long long pw = 0; const long long pt0 = clock64();
             for (int ti = 0; ti < my_tiles; ++ti) {
                 const int t = cluster_id + ti * num_clusters;
                 const int pm = t / p.num_n, nt = t - pm * p.num_n;
@@ -106,7 +111,8 @@ convgemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 }
                 int tap_r = 0, tap_s = 0, cb = 0;
                 for (int kb = 0; kb < p.nk; ++kb) {
-                    mbar_wait(&empty[stage], phase ^ 1);
+                    if (p.prof) { const long long w0 = clock64(); mbar_wait(&empty[stage], phase ^ 1); pw += clock64() - w0; }
+                    else mbar_wait(&empty[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
                     uint8_t* sb = sa + Cfg::A_BYTES;
                     if constexpr (CG == 2) {
@@ -125,19 +131,21 @@ convgemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
+            if (p.prof) { p.prof[blockIdx.x * 16 + 0] = pw; p.prof[blockIdx.x * 16 + 1] = clock64() - pt0; }
         }
     } else if (warp == 1) {
         if (rank == 0) {
             // ===================== MMA issuer (leader CTA) =====================
             const uint32_t idesc = make_idesc_bf16(BN, 0, 0, GEMM_BM * CG);
             int stage = 0; uint32_t phase = 0;
+            long long mw_full = 0, mw_tmem = 0; const long long mt0 = clock64();
             for (int ti = 0; ti < my_tiles; ++ti) {
                 const int as = ti & 1; const uint32_t aphase = (ti >> 1) & 1;
-                mbar_wait(&tmem_empty[as], aphase ^ 1);
+                { const long long w1 = clock64(); mbar_wait(&tmem_empty[as], aphase ^ 1); mw_tmem += clock64() - w1; }
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + as * BN;
                 for (int kb = 0; kb < p.nk; ++kb) {
-                    mbar_wait(&full[stage], phase);
+                    { const long long w2 = clock64(); mbar_wait(&full[stage], phase); mw_full += clock64() - w2; }
                     tc_fence_after();
                     if (elect_one()) {
                         const uint32_t a_base = smem_u32(smem + stage * Cfg::STAGE_BYTES);
@@ -156,99 +164,119 @@ convgemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
+            if (p.prof && lane == 0) { p.prof[blockIdx.x * 16 + 2] = mw_full; p.prof[blockIdx.x * 16 + 3] = mw_tmem; p.prof[blockIdx.x * 16 + 4] = clock64() - mt0; }
         }
     } else if (warp >= 4 && warp - 4 < Cfg::NWORK) {
         // ===================== epilogue: TMEM -> (+ shift, + residual, ReLU) in the warp's ring -> TMA store =====================
+        // Two epilogue warps share a scheduler, so latency is hidden by instruction-level parallelism inside an item: all
+        // residual reads of the item are issued together, the shift comes from a shared-memory table (broadcast reads), the
+        // packed results are written together, and tile / item coordinates are tracked incrementally (no divisions per item).
         const int ew = warp - 4, q = warp & 3, half = ew >> 2;
         uint8_t* myring = ring + ew * D * Cfg::SUB_BYTES;
         uint64_t* myfull = res_full + ew * D;
         const bool has_res = p.has_res != 0;
+        const float relu_lo = p.relu ? 0.0f : -INFINITY;
         const int n_items = my_tiles * Cfg::CPH;
-        auto item_coords = [&](int j, int& row0, int& col0) {
-            const int ti = j / Cfg::CPH, c = half * Cfg::CPH + (j - ti * Cfg::CPH);
-            const int t = cluster_id + ti * num_clusters;
-            const int pm = t / p.num_n, nt = t - pm * p.num_n;
-            row0 = (pm * CG + (int)rank) * GEMM_BM + q * 32;
-            col0 = nt * BN + c * 64;
-        };
-        auto request_res = [&](int j) {          // lane 0: residual sub-tile of item j into its ring slot
-            int row0, col0; item_coords(j, row0, col0);
-            const int s = j % D;
-            mbar_expect_tx(&myfull[s], Cfg::SUB_BYTES);
-            tma_load_2d(&mapR, &myfull[s], myring + s * Cfg::SUB_BYTES, col0, row0);
+        const uint32_t rowoff = (uint32_t)lane * 128u, swz = (uint32_t)(lane & 7);
+        // residual prefetch cursor (lane 0): item pf_j = (tile pf_ti, chunk pf_cc), ring slot pf_slot
+        int pf_j = 0, pf_cc = 0, pf_slot = 0, pf_pm = 0, pf_nt = 0, pf_t = cluster_id;
+        if (my_tiles > 0) { pf_pm = pf_t / p.num_n; pf_nt = pf_t - pf_pm * p.num_n; }
+        auto request_next = [&]() {
+            const int row0 = (pf_pm * CG + (int)rank) * GEMM_BM + q * 32, col0 = pf_nt * BN + (half * Cfg::CPH + pf_cc) * 64;
+            mbar_expect_tx(&myfull[pf_slot], Cfg::SUB_BYTES);
+            tma_load_2d(&mapR, &myfull[pf_slot], myring + pf_slot * Cfg::SUB_BYTES, col0, row0);
+            ++pf_j; if (++pf_slot == D) pf_slot = 0;
+            if (++pf_cc == Cfg::CPH) { pf_cc = 0; pf_t += num_clusters; pf_pm = pf_t / p.num_n; pf_nt = pf_t - pf_pm * p.num_n; }
         };
         if (has_res && lane == 0)
-            for (int j = 0; j < D - 1 && j < n_items; ++j) request_res(j);
+            for (int i = 0; i < D - 1 && i < n_items; ++i) request_next();
         const uint32_t tmem_empty_leader = (CG == 2) ? mapa_u32(tmem_empty, 0) : 0u;
-        int j = 0;
+        int j = 0, slot = 0; uint32_t sphase = 0;
+        long long ew_acc = 0, ew_res = 0, ew_grp = 0; const long long et0 = clock64();
+        const bool prof_on = p.prof != nullptr;
         for (int ti = 0; ti < my_tiles; ++ti) {
+            const int t = cluster_id + ti * num_clusters;
+            const int pm = t / p.num_n, nt = t - pm * p.num_n;
+            const int row0 = (pm * CG + (int)rank) * GEMM_BM + q * 32;
             const int as = ti & 1; const uint32_t aphase = (ti >> 1) & 1;
-            mbar_wait(&tmem_full[as], aphase);
+            // this warp's CPH*64 shift values of the tile: requested before the accumulator wait, published after it (all warps
+            // of the half write the same values; the buffer of tile ti was last read for tile ti-2, which every warp of the
+            // pair had finished before this tile's MMAs could start)
+            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (lane < Cfg::CPH * 16) bv = __ldg(reinterpret_cast<const float4*>(p.bias + nt * BN + half * Cfg::CPH * 64) + lane);
+            if (prof_on) { const long long w3 = clock64(); mbar_wait(&tmem_full[as], aphase); ew_acc += clock64() - w3; }
+            else mbar_wait(&tmem_full[as], aphase);
             tc_fence_after();
+            float4* bias4 = reinterpret_cast<float4*>(bias_smem) + (as * BN + half * Cfg::CPH * 64) / 4;
+            if (lane < Cfg::CPH * 16) bias4[lane] = bv;
+            __syncwarp();
             const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
 #pragma unroll 1
             for (int cc = 0; cc < Cfg::CPH; ++cc, ++j) {
-                const int c = half * Cfg::CPH + cc, slot = j % D;
+                const int c = half * Cfg::CPH + cc;
                 uint8_t* sl = myring + slot * Cfg::SUB_BYTES;
-                int row0, col0; item_coords(j, row0, col0);
+                uint8_t* rowp = sl + rowoff;
                 float v[64];
                 tmem_ld32(tacc + c * 64, v);
                 tmem_ld32(tacc + c * 64 + 32, v + 32);
+                uint4 r[8];
+                const long long w4 = prof_on ? clock64() : 0;
                 if (has_res) {
-                    mbar_wait(&myfull[slot], (uint32_t)((j / D) & 1));
+                    mbar_wait(&myfull[slot], sphase);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) r[k] = *reinterpret_cast<const uint4*>(rowp + ((k ^ swz) << 4));     // 128B swizzle: chunk ^ (row % 8)
                 } else {
                     if (lane == 0) bulk_wait_group_read<D - 1>();       // the store that last used this slot has read it
                     __syncwarp();
                 }
+                if (prof_on) ew_res += clock64() - w4;
                 tmem_ld_wait();
-                const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const float4 b = __ldg(b4 + i);
-                    v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
-                }
-                uint8_t* rowp = sl + lane * 128;
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
-                    uint4* cell = reinterpret_cast<uint4*>(rowp + ((k ^ (lane & 7)) << 4));      // 128B swizzle: chunk ^ (row % 8)
                     float* f = v + 8 * k;
+                    const float4 b0 = bias4[cc * 16 + 2 * k], b1 = bias4[cc * 16 + 2 * k + 1];
+                    f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w; f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
                     if (has_res) {
-                        const uint4 t = *cell;
-                        const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+                        const uint32_t w[4] = {r[k].x, r[k].y, r[k].z, r[k].w};
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
                             f[2 * u] += __uint_as_float(w[u] << 16);
                             f[2 * u + 1] += __uint_as_float(w[u] & 0xffff0000u);
                         }
                     }
-                    if (p.relu) {
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) f[u] = fmaxf(f[u], 0.0f);
-                    }
-                    uint4 pk; __nv_bfloat162 h2;
-                    h2 = __floats2bfloat162_rn(f[0], f[1]); pk.x = *reinterpret_cast<uint32_t*>(&h2);
-                    h2 = __floats2bfloat162_rn(f[2], f[3]); pk.y = *reinterpret_cast<uint32_t*>(&h2);
-                    h2 = __floats2bfloat162_rn(f[4], f[5]); pk.z = *reinterpret_cast<uint32_t*>(&h2);
-                    h2 = __floats2bfloat162_rn(f[6], f[7]); pk.w = *reinterpret_cast<uint32_t*>(&h2);
-                    *cell = pk;
+                    __nv_bfloat162 h2;
+                    h2 = __floats2bfloat162_rn(fmaxf(f[0], relu_lo), fmaxf(f[1], relu_lo)); r[k].x = *reinterpret_cast<uint32_t*>(&h2);
+                    h2 = __floats2bfloat162_rn(fmaxf(f[2], relu_lo), fmaxf(f[3], relu_lo)); r[k].y = *reinterpret_cast<uint32_t*>(&h2);
+                    h2 = __floats2bfloat162_rn(fmaxf(f[4], relu_lo), fmaxf(f[5], relu_lo)); r[k].z = *reinterpret_cast<uint32_t*>(&h2);
+                    h2 = __floats2bfloat162_rn(fmaxf(f[6], relu_lo), fmaxf(f[7], relu_lo)); r[k].w = *reinterpret_cast<uint32_t*>(&h2);
                 }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) *reinterpret_cast<uint4*>(rowp + ((k ^ swz) << 4)) = r[k];
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) {
-                    tma_store_2d(&mapO, sl, col0, row0);
+                    tma_store_2d(&mapO, sl, nt * BN + c * 64, row0);
                     bulk_commit_group();
-                    if (has_res && j + D - 1 < n_items) {
-                        if (j >= 1) bulk_wait_group_read<1>();          // the store of item j-1 has read slot (j-1) % D
-                        request_res(j + D - 1);
+                    if (has_res && pf_j < n_items) {
+                        const long long w5 = prof_on ? clock64() : 0;
+                        if (j >= 1) bulk_wait_group_read<1>();          // the store of item j-1 has read the slot being refilled
+                        if (prof_on) ew_grp += clock64() - w5;
+                        request_next();
                     }
                 }
                 __syncwarp();
+                if (++slot == D) { slot = 0; sphase ^= 1; }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) { if constexpr (CG == 2) mbar_arrive_cluster(tmem_empty_leader + as * 8); else mbar_arrive(&tmem_empty[as]); }
         }
         if (lane == 0) bulk_wait_group_read<0>();
+        // counters of epilogue warp 0 (lane 0): accumulator wait, residual / slot wait, store-read wait, total
+        if (prof_on && lane == 0 && ew == 0) {
+            unsigned long long* o = p.prof + blockIdx.x * 16 + 5;
+            o[0] = ew_acc; o[1] = ew_res; o[2] = ew_grp; o[3] = clock64() - et0;
+        }
     }
     __syncwarp();                 // the single-lane roles rejoin their warps before the aligned barrier
     tc_fence_before();
@@ -317,6 +345,7 @@ inline int convgemm_launch(const ConvGemmArgs& g, cudaStream_t st) {
     kp.num_n = g.N / bn;
     kp.total_tiles = ((num_m + cg - 1) / cg) * kp.num_n;
     kp.bias = g.bias; kp.relu = g.relu; kp.has_res = g.res != nullptr;
+    kp.prof = gemm_prof_buffer();
 
     CUtensorMap maps[4];
     if (g.conv.enabled) {

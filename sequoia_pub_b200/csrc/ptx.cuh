@@ -158,7 +158,7 @@ __device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
     return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA loads of a CTA pair: destination in this CTA, completion bytes on the mbarrier at cluster address `bar` (the leader's)
 __device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* m, uint32_t bar, void* dst, int c0, int c1) {

@@ -434,6 +434,20 @@ int sq_resnet50_prepack(const void* const* tensors, void* packed_w, float* shift
     return 0;
 }
 
+int sq_conv_bf16(const sq_conv_desc* d, void* stream) {
+    if (!d || !d->in || !d->weight || !d->shift || !d->out) { set_error("conv: null pointer"); return -1; }
+    if (d->batch <= 0 || d->Cin % 64 || d->Cout % 64 || d->R != d->S || d->stride < 1) { set_error("conv: unsupported geometry"); return -1; }
+    const int Ho = (d->H + 2 * d->pad - d->R) / d->stride + 1, Wo = (d->W + 2 * d->pad - d->S) / d->stride + 1;
+    ConvGemmArgs a; memset(&a, 0, sizeof(a));
+    a.M = d->batch * Ho * Wo; a.N = d->Cout; a.K = d->R * d->S * d->Cin;
+    a.A = (const bf16*)d->in; a.lda = d->Cin; a.W = (const bf16*)d->weight; a.bias = d->shift; a.res = (const bf16*)d->residual; a.out = (bf16*)d->out;
+    a.relu = d->relu; a.block_n = d->block_n; a.cta_group = d->cta_group;
+    a.conv.enabled = (d->R == 1 && d->stride == 1 && d->pad == 0) ? 0 : 1; a.conv.batch = d->batch; a.conv.H = d->H; a.conv.W = d->W; a.conv.C = d->Cin;
+    a.conv.Ho = Ho; a.conv.Wo = Wo; a.conv.R = d->R; a.conv.S = d->S; a.conv.stride = d->stride; a.conv.pad = d->pad;
+    if (!convgemm_supported(a)) { set_error("conv: operands must be 16-byte aligned, channels multiples of 64"); return -1; }
+    return convgemm_launch(a, (cudaStream_t)stream);
+}
+
 size_t sq_resnet50_workspace_bytes(int batch, int H, int W) { return ws_layout(batch, H, W).total; }
 
 int sq_resnet50_extract(const void* input, int input_kind, int batch, int H, int W, const void* packed_w, const float* shifts,
