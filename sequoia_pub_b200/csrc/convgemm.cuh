@@ -26,14 +26,27 @@ struct CgParams {
     int total_tiles;     // (pairs of) 128-row tiles x column tiles
     int nk;              // 64-wide k-blocks
     int conv, cblocks, S, stride, pad, tiles_per_img, BH, BIMG;
+    int tiles_x, Ho, halo_bo;   // halo mode: 8-pixel-wide tiles per output row, output height, descriptor base-offset mode
     const float* bias;   // [N] folded BatchNorm shift
     int relu, has_res;
+    float* pool_out;     // non-null: instead of storing the tile, add mean over the top-left 7x7 of each 8x8 image map into pool_out[img][N] (src/resnet.py:110,166)
+    int batch;
+    int l2pf;            // prefetch residual sub-tiles into L2 two tiles ahead
     unsigned long long* prof;   // optional per-CTA cycle counters (sq_gemm_profile): [cta][16]
 };
 
-template <int BN, int CG, int D> struct CgCfg {
+// HALO = 1 (3x3, stride 1, pad 1): the CTA's 128 output pixels are a 16 x 8 patch; its 18 x 10 input halo is staged ONCE per
+// 64-channel block (one 4-D TMA box, 23 KB) and the nine taps are issued from shifted views of it: tap (r, s) reads pixel
+// rows (oy + r, ox + s), i.e. a K-major operand whose 8-row groups (one output row = 8 consecutive halo pixels) are 10
+// pixels = 1280 bytes apart (the descriptor's stride-byte-offset) and which starts (r * 10 + s) * 128 bytes into the halo.
+// The stage ring then only carries weight tiles.  L2 -> shared-memory traffic for A drops from 9x to 1.4x the input.
+constexpr int HALO_TH = 16, HALO_TW = 8, HALO_PITCH = HALO_TW + 2;
+constexpr int HALO_BYTES_RAW = (HALO_TH + 2) * HALO_PITCH * 128;
+constexpr int HALO_BYTES = (HALO_BYTES_RAW + 1023) / 1024 * 1024;
+template <int BN, int CG, int D, int HALO = 0> struct CgCfg {
     static constexpr int B_ROWS = BN / CG;                        // rows of the weight tile this CTA stages
-    static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
+    static constexpr int A_BYTES = HALO ? 0 : GEMM_BM * GEMM_BK * 2;
+    static constexpr int HS = HALO ? 3 : 0;                       // halo slots
     static constexpr int B_BYTES = B_ROWS * GEMM_BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int NCHUNK = BN / 64;                        // 64-column epilogue items per tile
@@ -43,22 +56,23 @@ template <int BN, int CG, int D> struct CgCfg {
     static constexpr int RING_BYTES = NWORK * D * SUB_BYTES;
     static constexpr int BAR_BYTES = 512;
     static constexpr int BIAS_BYTES = 2 * BN * 4;                 // shift table, double-buffered like the accumulator
-    static constexpr int BUDGET = 232448 - BAR_BYTES - BIAS_BYTES - RING_BYTES;
+    static constexpr int BUDGET = 232448 - BAR_BYTES - BIAS_BYTES - RING_BYTES - HS * HALO_BYTES;
     static constexpr int STAGES = BUDGET / STAGE_BYTES > 8 ? 8 : BUDGET / STAGE_BYTES;
     static_assert(STAGES >= 2, "shared memory budget");
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + RING_BYTES + BIAS_BYTES + BAR_BYTES;
-    static_assert((2 * STAGES + 4 + NWORK * D) * 8 + 4 <= BAR_BYTES, "barrier area");
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + HS * HALO_BYTES + RING_BYTES + BIAS_BYTES + BAR_BYTES;
+    static_assert((2 * STAGES + 4 + NWORK * D + 2 * HS) * 8 + 4 <= BAR_BYTES, "barrier area");
     static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
 };
 
-template <int BN, int CG, int D>
+template <int BN, int CG, int D, int HALO>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 convgemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                 const __grid_constant__ CUtensorMap mapR, const __grid_constant__ CUtensorMap mapO, const CgParams p) {
-    using Cfg = CgCfg<BN, CG, D>;
+    using Cfg = CgCfg<BN, CG, D, HALO>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ __align__(1024) uint8_t smem[];              // 128B-swizzled tiles need 1024-byte alignment (checked below)
-    uint8_t* ring = smem + STAGES * Cfg::STAGE_BYTES;
+    uint8_t* halo = smem + STAGES * Cfg::STAGE_BYTES;
+    uint8_t* ring = halo + Cfg::HS * HALO_BYTES;
     float* bias_smem = reinterpret_cast<float*>(ring + Cfg::RING_BYTES);
     uint64_t* bars = reinterpret_cast<uint64_t*>(ring + Cfg::RING_BYTES + Cfg::BIAS_BYTES);
     uint64_t* full = bars;
@@ -66,7 +80,9 @@ convgemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     uint64_t* tmem_full = bars + 2 * STAGES;
     uint64_t* tmem_empty = bars + 2 * STAGES + 2;
     uint64_t* res_full = bars + 2 * STAGES + 4;                   // [NWORK][D]
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_full + Cfg::NWORK * D);
+    uint64_t* full_h = res_full + Cfg::NWORK * D;                 // [HS] halo slot filled / drained
+    uint64_t* empty_h = full_h + Cfg::HS;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(empty_h + Cfg::HS);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -82,6 +98,7 @@ convgemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], CG * Cfg::NWORK); }
         for (int i = 0; i < Cfg::NWORK * D; ++i) mbar_init(&res_full[i], 1);
+        for (int i = 0; i < Cfg::HS; ++i) { mbar_init(&full_h[i], 1); mbar_init(&empty_h[i], 1); }
         mbar_fence_init();
     }
     if (warp == 2) { if constexpr (CG == 2) tmem_alloc_pair(tmem_ptr, Cfg::TMEM_COLS); else tmem_alloc(tmem_ptr, Cfg::TMEM_COLS); }
@@ -98,6 +115,7 @@ convgemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         if (elect_one()) {
             // ===================== TMA producer (both CTAs of a pair; completion on the leader's barrier) =====================
             int stage = 0; uint32_t phase = 0;
+            [[maybe_unused]] int hslot = 0; [[maybe_unused]] uint32_t hphase = 0;
             long long pw = 0; const long long pt0 = clock64();
             for (int ti = 0; ti < my_tiles; ++ti) {
                 const int t = cluster_id + ti * num_clusters;
@@ -109,6 +127,37 @@ convgemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                     if (p.BIMG == 1) { img = mt / p.tiles_per_img; hin0 = (mt - img * p.tiles_per_img) * p.BH * p.stride - p.pad; }
                     else { img = mt * p.BIMG; hin0 = -p.pad; }
                 }
+                if constexpr (HALO) {
+                    // tile = 16 x 8 output pixels of one image; per channel block: its halo once, then the nine weight tiles
+                    const int img_h = mt / p.tiles_per_img, rem = mt - img_h * p.tiles_per_img;
+                    const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+                    for (int cbh = 0; cbh < p.cblocks; ++cbh) {
+                        mbar_wait(&empty_h[hslot], hphase ^ 1);
+                        uint8_t* sh = halo + hslot * HALO_BYTES;
+                        if constexpr (CG == 2) {
+                            if (rank == 0) mbar_expect_tx(&full_h[hslot], 2 * HALO_BYTES_RAW);
+                            tma_load_4d_pair(&mapA, mapa_u32(&full_h[hslot], 0), sh, cbh * GEMM_BK, tx * HALO_TW - 1, ty * HALO_TH - 1, img_h);
+                        } else {
+                            mbar_expect_tx(&full_h[hslot], HALO_BYTES_RAW);
+                            tma_load_4d(&mapA, &full_h[hslot], sh, cbh * GEMM_BK, tx * HALO_TW - 1, ty * HALO_TH - 1, img_h);
+                        }
+                        if (++hslot == Cfg::HS) { hslot = 0; hphase ^= 1; }
+                        for (int tap = 0; tap < 9; ++tap) {
+                            if (p.prof) { const long long w0 = clock64(); mbar_wait(&empty[stage], phase ^ 1); pw += clock64() - w0; }
+                            else mbar_wait(&empty[stage], phase ^ 1);
+                            uint8_t* sb = smem + stage * Cfg::STAGE_BYTES;
+                            const int kcol = (tap * p.cblocks + cbh) * GEMM_BK;
+                            if constexpr (CG == 2) {
+                                if (rank == 0) mbar_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
+                                tma_load_2d_pair(&mapB, mapa_u32(&full[stage], 0), sb, kcol, nb0);
+                            } else {
+                                mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+                                tma_load_2d(&mapB, &full[stage], sb, kcol, nb0);
+                            }
+                            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        }
+                    }
+                } else {
                 int tap_r = 0, tap_s = 0, cb = 0;
                 for (int kb = 0; kb < p.nk; ++kb) {
                     if (p.prof) { const long long w0 = clock64(); mbar_wait(&empty[stage], phase ^ 1); pw += clock64() - w0; }
@@ -130,6 +179,7 @@ convgemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                     if (p.conv && ++cb == p.cblocks) { cb = 0; if (++tap_s == p.S) { tap_s = 0; ++tap_r; } }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
+                }
             }
             if (p.prof) { p.prof[blockIdx.x * 16 + 0] = pw; p.prof[blockIdx.x * 16 + 1] = clock64() - pt0; }
         }
@@ -138,12 +188,49 @@ convgemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             // ===================== MMA issuer (leader CTA) =====================
             const uint32_t idesc = make_idesc_bf16(BN, 0, 0, GEMM_BM * CG);
             int stage = 0; uint32_t phase = 0;
+            [[maybe_unused]] int hslot = 0; [[maybe_unused]] uint32_t hphase = 0;
             long long mw_full = 0, mw_tmem = 0; const long long mt0 = clock64();
             for (int ti = 0; ti < my_tiles; ++ti) {
                 const int as = ti & 1; const uint32_t aphase = (ti >> 1) & 1;
                 { const long long w1 = clock64(); mbar_wait(&tmem_empty[as], aphase ^ 1); mw_tmem += clock64() - w1; }
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + as * BN;
+                if constexpr (HALO) {
+                    for (int cbh = 0; cbh < p.cblocks; ++cbh) {
+                        { const long long w2 = clock64(); mbar_wait(&full_h[hslot], hphase); mw_full += clock64() - w2; }
+                        const uint32_t h_base = smem_u32(halo + hslot * HALO_BYTES);
+                        for (int tap = 0; tap < 9; ++tap) {
+                            { const long long w2 = clock64(); mbar_wait(&full[stage], phase); mw_full += clock64() - w2; }
+                            tc_fence_after();
+                            if (elect_one()) {
+                                const int tr = tap / 3, ts = tap - tr * 3;
+                                const uint32_t a_base = h_base + (uint32_t)(tr * HALO_PITCH + ts) * 128u;
+                                const uint32_t b_base = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                                const uint32_t bo = p.halo_bo ? ((a_base >> 7) & 7u) : 0u;
+#pragma unroll
+                                for (int k = 0; k < GEMM_BK / 16; ++k) {
+                                    const uint64_t da = make_smem_desc(a_base + k * 32, HALO_PITCH * 128, 0, bo);
+                                    const uint64_t db = make_smem_desc(b_base + k * 32, 1024, 0);
+                                    const uint32_t acc = (cbh > 0 || tap > 0 || k > 0) ? 1u : 0u;
+                                    if constexpr (CG == 2) umma_bf16_pair(tacc, da, db, idesc, acc); else umma_bf16(tacc, da, db, idesc, acc);
+                                }
+                                const bool last = cbh == p.cblocks - 1 && tap == 8;
+                                if constexpr (CG == 2) {
+                                    umma_commit_pair(&empty[stage]);
+                                    if (tap == 8) umma_commit_pair(&empty_h[hslot]);
+                                    if (last) umma_commit_pair(&tmem_full[as]);
+                                } else {
+                                    umma_commit(&empty[stage]);
+                                    if (tap == 8) umma_commit(&empty_h[hslot]);
+                                    if (last) umma_commit(&tmem_full[as]);
+                                }
+                            }
+                            __syncwarp();
+                            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        }
+                        if (++hslot == Cfg::HS) { hslot = 0; hphase ^= 1; }
+                    }
+                } else {
                 for (int kb = 0; kb < p.nk; ++kb) {
                     { const long long w2 = clock64(); mbar_wait(&full[stage], phase); mw_full += clock64() - w2; }
                     tc_fence_after();
@@ -162,6 +249,7 @@ convgemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                     }
                     __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
                 }
             }
             if (p.prof && lane == 0) { p.prof[blockIdx.x * 16 + 2] = mw_full; p.prof[blockIdx.x * 16 + 3] = mw_tmem; p.prof[blockIdx.x * 16 + 4] = clock64() - mt0; }
@@ -198,10 +286,22 @@ convgemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             const int t = cluster_id + ti * num_clusters;
             const int pm = t / p.num_n, nt = t - pm * p.num_n;
             const int row0 = (pm * CG + (int)rank) * GEMM_BM + q * 32;
+            [[maybe_unused]] int h_ox0 = 0, h_row0 = 0;
+            if constexpr (HALO) {
+                const int mt = pm * CG + (int)rank, img_h = mt / p.tiles_per_img, rem = mt - img_h * p.tiles_per_img;
+                const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+                h_ox0 = tx * HALO_TW; h_row0 = img_h * p.Ho + ty * HALO_TH + q * 4;
+            }
             const int as = ti & 1; const uint32_t aphase = (ti >> 1) & 1;
             // this warp's CPH*64 shift values of the tile: requested before the accumulator wait, published after it (all warps
             // of the half write the same values; the buffer of tile ti was last read for tile ti-2, which every warp of the
             // pair had finished before this tile's MMAs could start)
+            if (has_res && p.l2pf && lane == 0 && ti + 2 < my_tiles) {          // residual sub-tiles of the tile after next: HBM -> L2 now
+                const int t2 = t + 2 * num_clusters, pm2 = t2 / p.num_n, nt2 = t2 - pm2 * p.num_n;
+#pragma unroll
+                for (int cc2 = 0; cc2 < Cfg::CPH; ++cc2)
+                    tma_prefetch_l2_2d(&mapR, nt2 * BN + (half * Cfg::CPH + cc2) * 64, (pm2 * CG + (int)rank) * GEMM_BM + q * 32);
+            }
             float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
             if (lane < Cfg::CPH * 16) bv = __ldg(reinterpret_cast<const float4*>(p.bias + nt * BN + half * Cfg::CPH * 64) + lane);
             if (prof_on) { const long long w3 = clock64(); mbar_wait(&tmem_full[as], aphase); ew_acc += clock64() - w3; }
@@ -244,18 +344,52 @@ convgemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                             f[2 * u + 1] += __uint_as_float(w[u] & 0xffff0000u);
                         }
                     }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) f[u] = fmaxf(f[u], relu_lo);
+                }
+                if (p.pool_out) {
+                    // fused AvgPool2d(7) of the final 8x8 map: a 128-row tile is two images, this warp's 32 rows are image rows
+                    // 4*(q&1) .. +3; masked recursive-halving reduction over the lanes leaves columns 2*lane, 2*lane+1 here; the two
+                    // half-image partial means are combined with atomicAdd onto a zeroed output (two addends: order-independent)
+                    const bool inside = ((q & 1) * 4 + (lane >> 3) < 7) && ((lane & 7) < 7);
+#pragma unroll
+                    for (int i = 0; i < 64; ++i) v[i] = inside ? v[i] : 0.0f;
+#pragma unroll
+                    for (int step = 0; step < 5; ++step) {
+                        const int width = 32 >> step, mask = 16 >> step;
+                        const bool upper = (lane & mask) != 0;
+#pragma unroll
+                        for (int i = 0; i < width; ++i) {
+                            const float send = upper ? v[i] : v[i + width];
+                            const float keep = upper ? v[i + width] : v[i];
+                            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
+                        }
+                    }
+                    const int img = (pm * CG + (int)rank) * 2 + (q >> 1);
+                    if (img < p.batch) {
+                        float* o = p.pool_out + (size_t)img * p.N + nt * BN + c * 64 + 2 * lane;
+                        atomicAdd(o, v[0] * (1.0f / 49.0f));
+                        atomicAdd(o + 1, v[1] * (1.0f / 49.0f));
+                    }
+                    if (lane == 0 && has_res && pf_j < n_items) request_next();
+                    __syncwarp();
+                } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float* f = v + 8 * k;
                     __nv_bfloat162 h2;
-                    h2 = __floats2bfloat162_rn(fmaxf(f[0], relu_lo), fmaxf(f[1], relu_lo)); r[k].x = *reinterpret_cast<uint32_t*>(&h2);
-                    h2 = __floats2bfloat162_rn(fmaxf(f[2], relu_lo), fmaxf(f[3], relu_lo)); r[k].y = *reinterpret_cast<uint32_t*>(&h2);
-                    h2 = __floats2bfloat162_rn(fmaxf(f[4], relu_lo), fmaxf(f[5], relu_lo)); r[k].z = *reinterpret_cast<uint32_t*>(&h2);
-                    h2 = __floats2bfloat162_rn(fmaxf(f[6], relu_lo), fmaxf(f[7], relu_lo)); r[k].w = *reinterpret_cast<uint32_t*>(&h2);
+                    h2 = __floats2bfloat162_rn(f[0], f[1]); r[k].x = *reinterpret_cast<uint32_t*>(&h2);
+                    h2 = __floats2bfloat162_rn(f[2], f[3]); r[k].y = *reinterpret_cast<uint32_t*>(&h2);
+                    h2 = __floats2bfloat162_rn(f[4], f[5]); r[k].z = *reinterpret_cast<uint32_t*>(&h2);
+                    h2 = __floats2bfloat162_rn(f[6], f[7]); r[k].w = *reinterpret_cast<uint32_t*>(&h2);
                 }
 #pragma unroll
                 for (int k = 0; k < 8; ++k) *reinterpret_cast<uint4*>(rowp + ((k ^ swz) << 4)) = r[k];
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) {
-                    tma_store_2d(&mapO, sl, nt * BN + c * 64, row0);
+                    if constexpr (HALO) tma_store_3d(&mapO, sl, nt * BN + c * 64, h_ox0, h_row0);     // 4 output rows x 8 pixels
+                    else tma_store_2d(&mapO, sl, nt * BN + c * 64, row0);
                     bulk_commit_group();
                     if (has_res && pf_j < n_items) {
                         const long long w5 = prof_on ? clock64() : 0;
@@ -265,6 +399,7 @@ convgemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                     }
                 }
                 __syncwarp();
+                }
                 if (++slot == D) { slot = 0; sphase ^= 1; }
             }
             tc_fence_before();
@@ -296,14 +431,15 @@ struct ConvGemmArgs {
     ConvGeom conv;
     int block_n;                 // 0 = auto
     int cta_group;               // 0 = auto
+    float* pool_out; int pool_batch;   // fused 7x7 average pool of an 8x8 final map (out may then be null)
 };
 
-template <int BN, int CG, int D>
+template <int BN, int CG, int D, int HALO>
 int convgemm_launch_inst(const CUtensorMap* maps, const CgParams& kp, int grid, cudaStream_t st) {
-    using Cfg = CgCfg<BN, CG, D>;
+    using Cfg = CgCfg<BN, CG, D, HALO>;
     static bool configured = false;
     if (!configured) {
-        cudaError_t err = cudaFuncSetAttribute(convgemm_kernel<BN, CG, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        cudaError_t err = cudaFuncSetAttribute(convgemm_kernel<BN, CG, D, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
         if (err != cudaSuccess) { set_error("convgemm: cudaFuncSetAttribute: %s", cudaGetErrorString(err)); return -1; }
         configured = true;
     }
@@ -316,17 +452,17 @@ int convgemm_launch_inst(const CUtensorMap* maps, const CgParams& kp, int grid, 
     if (CG == 2) { attr[na].id = cudaLaunchAttributeClusterDimension; attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1; ++na; }
     if (pdl) { attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[na].val.programmaticStreamSerializationAllowed = 1; ++na; }
     cfg.attrs = attr; cfg.numAttrs = na;
-    cudaError_t err = cudaLaunchKernelEx(&cfg, convgemm_kernel<BN, CG, D>, maps[0], maps[1], maps[2], maps[3], kp);
+    cudaError_t err = cudaLaunchKernelEx(&cfg, convgemm_kernel<BN, CG, D, HALO>, maps[0], maps[1], maps[2], maps[3], kp);
     if (err == cudaSuccess) err = cudaGetLastError();
     if (err != cudaSuccess) { set_error("convgemm launch: %s", cudaGetErrorString(err)); return -1; }
     return 0;
 }
 
-int convgemm_dispatch(int bn, int cg, const CUtensorMap* maps, const CgParams& kp, int grid, cudaStream_t st);   // resnet.cu
+int convgemm_dispatch(int bn, int cg, int halo, const CUtensorMap* maps, const CgParams& kp, int grid, cudaStream_t st);   // resnet.cu
 
 // true when the launch fits this kernel (N a multiple of 64, channels a multiple of 64, tile geometry of the 4-D boxes)
 inline bool convgemm_supported(const ConvGemmArgs& g) {
-    if (g.N % 64 != 0 || g.K % 64 != 0 || !g.out || !g.bias) return false;
+    if (g.N % 64 != 0 || g.K % 64 != 0 || (!g.out && !g.pool_out) || !g.bias) return false;
     if ((reinterpret_cast<uintptr_t>(g.out) | reinterpret_cast<uintptr_t>(g.res) | reinterpret_cast<uintptr_t>(g.A) | reinterpret_cast<uintptr_t>(g.W)) & 15) return false;
     return true;
 }
@@ -334,10 +470,24 @@ inline bool convgemm_supported(const ConvGemmArgs& g) {
 inline int convgemm_launch(const ConvGemmArgs& g, cudaStream_t st) {
     CgParams kp;
     memset(&kp, 0, sizeof(kp));
-    int bn = g.block_n;
-    if (bn == 0) bn = g.N >= 256 ? 256 : (g.N >= 128 ? 128 : 64);
     static const int env_cg = getenv("SQ_CONV_CG") ? atoi(getenv("SQ_CONV_CG")) : 0;
     int cg = g.cta_group ? g.cta_group : (env_cg ? env_cg : 2);
+    int bn = g.block_n;
+    static const int env_bnsel = getenv("SQ_CONV_BNSEL") ? atoi(getenv("SQ_CONV_BNSEL")) : 0;   // wave-aware widths: -23 us per batch alone, but -3 % with two extractor lanes (fuller grids leave the other lane no SMs)
+    static const int env_l2pf = getenv("SQ_CONV_L2PF") ? atoi(getenv("SQ_CONV_L2PF")) : 0;      // measured: +13 us per batch when on
+    kp.l2pf = env_l2pf;
+    if (bn == 0 && !env_bnsel) bn = g.N >= 256 ? 256 : (g.N >= 128 ? 128 : 64);
+    if (bn == 0) {
+        // widest tile whose waves are not mostly empty: cost = waves x tile width (64-wide MMAs run at ~half rate: x1.5)
+        const long long mp = ((g.M + GEMM_BM - 1) / GEMM_BM + cg - 1) / cg, G = num_sms() / cg;
+        long long best = -1;
+        for (int w = 256; w >= 64; w >>= 1) {
+            if (g.N % w != 0) continue;
+            const long long tiles = mp * (g.N / w), cost = ((tiles + G - 1) / G) * w * (w == 64 ? 3 : 2);
+            if (best < 0 || cost < best) { best = cost; bn = w; }
+        }
+        if (bn == 0) bn = 64;
+    }
     if (cg == 1 && bn == 256) bn = 128;                     // a single CTA has no room for 256-wide stages beside the ring
     if (g.N % bn != 0) bn = 64;
     kp.M = g.M; kp.N = g.N;
@@ -346,9 +496,28 @@ inline int convgemm_launch(const ConvGemmArgs& g, cudaStream_t st) {
     kp.total_tiles = ((num_m + cg - 1) / cg) * kp.num_n;
     kp.bias = g.bias; kp.relu = g.relu; kp.has_res = g.res != nullptr;
     kp.prof = gemm_prof_buffer();
+    kp.pool_out = g.pool_out; kp.batch = g.pool_batch;
 
     CUtensorMap maps[4];
-    if (g.conv.enabled) {
+    // halo mode: 3x3 / stride 1 / pad 1 without a residual, output map tiled by 16 x 8 patches
+    static const int env_halo = getenv("SQ_CONV_HALO") ? atoi(getenv("SQ_CONV_HALO")) : 1;     // 0 off, 1 on, 2 on with descriptor base offset
+    const ConvGeom& cc = g.conv;
+    // (measured: 49 -> 41 us on layer 1, 31.6 -> 29.4 us on layer 2; with 256-wide tiles the three weight stages that fit beside
+    //  the halo slots starve the MMAs, 25.2 -> 26.6 us on layer 3, so those keep the per-tap boxes)
+    const int halo = (env_halo && cc.enabled && cc.R == 3 && cc.S == 3 && cc.stride == 1 && cc.pad == 1 && !g.res && cc.Wo % HALO_TW == 0 &&
+                      cc.Ho % HALO_TH == 0 && cc.C % 64 == 0 && (bn <= 128 || env_halo == 3)) ? 1 : 0;
+    if (halo) {
+        const ConvGeom& c = g.conv;
+        kp.conv = 1; kp.cblocks = c.C / 64; kp.S = 3; kp.stride = 1; kp.pad = 1;
+        kp.tiles_x = c.Wo / HALO_TW; kp.tiles_per_img = (c.Ho / HALO_TH) * kp.tiles_x; kp.Ho = c.Ho; kp.halo_bo = env_halo == 2;
+        kp.nk = 9 * kp.cblocks;
+        if (g.M != c.batch * c.Ho * c.Wo) { set_error("conv: M mismatch"); return -1; }
+        cuuint64_t dims[4] = {(cuuint64_t)c.C, (cuuint64_t)c.W, (cuuint64_t)c.H, (cuuint64_t)c.batch};
+        cuuint64_t strides[3] = {(cuuint64_t)c.C * 2, (cuuint64_t)c.W * c.C * 2, (cuuint64_t)c.H * c.W * c.C * 2};
+        cuuint32_t box[4] = {64, HALO_PITCH, HALO_TH + 2, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        if (encode_map(&maps[0], g.A, 4, dims, strides, box, estr)) return -1;
+    } else if (g.conv.enabled) {
         const ConvGeom& c = g.conv;
         if (c.C % 64 != 0) { set_error("conv: C=%d must be a multiple of 64", c.C); return -1; }
         int BW = c.Wo, BH, BIMG = 1;
@@ -370,18 +539,28 @@ inline int convgemm_launch(const ConvGemmArgs& g, cudaStream_t st) {
         if (make_operand_map(&maps[0], g.A, 0, g.lda, g.M, g.K, GEMM_BM)) return -1;
     }
     if (make_operand_map(&maps[1], g.W, 0, (long long)kp.nk * 64, g.N, kp.nk * 64, bn / cg)) return -1;
+    if (halo) {
+        // output sub-tiles: 64 channels x 8 pixels x 4 output rows (= the 32 accumulator rows of one epilogue warp)
+        const ConvGeom& c = g.conv;
+        cuuint64_t dims[3] = {(cuuint64_t)g.N, (cuuint64_t)c.Wo, (cuuint64_t)c.Ho * c.batch};
+        cuuint64_t strides[2] = {(cuuint64_t)g.N * 2, (cuuint64_t)c.Wo * g.N * 2};
+        cuuint32_t box[3] = {64, HALO_TW, 4}, estr[3] = {1, 1, 1};
+        if (encode_map(&maps[3], g.out, 3, dims, strides, box, estr)) return -1;
+        maps[2] = maps[3];
+    } else
     // residual / output sub-tiles: 64 channels x 32 rows
     {
         cuuint64_t dims[2] = {(cuuint64_t)g.N, (cuuint64_t)g.M}, strides[1] = {(cuuint64_t)g.N * 2};
         cuuint32_t box[2] = {64, 32}, estr[2] = {1, 1};
-        if (encode_map(&maps[3], g.out, 2, dims, strides, box, estr)) return -1;
         if (g.res) { if (encode_map(&maps[2], g.res, 2, dims, strides, box, estr)) return -1; }
-        else maps[2] = maps[3];
+        if (g.out) { if (encode_map(&maps[3], g.out, 2, dims, strides, box, estr)) return -1; }
+        else maps[3] = maps[2];
+        if (!g.res) maps[2] = maps[3];
     }
     const int clusters_max = num_sms() / cg;
     const int clusters = kp.total_tiles < clusters_max ? kp.total_tiles : clusters_max;
     gemm_timing_begin(st, 2.0 * g.M * g.N * (double)kp.nk * 64);
-    const int rc = convgemm_dispatch(bn, cg, maps, kp, clusters * cg, st);
+    const int rc = convgemm_dispatch(bn, cg, halo, maps, kp, clusters * cg, st);
     gemm_timing_end(st);
     return rc;
 }

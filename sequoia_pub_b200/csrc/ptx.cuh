@@ -139,6 +139,15 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* s
                  "r"(smem_u32(src)), "r"(c0), "r"(c1)
                  : "memory");
 }
+// asks the TMA unit to bring a box into L2 only (no shared-memory destination, no completion tracking)
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* m, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // waits until at most N of this thread's bulk groups still have to READ their shared-memory source
 template <int N> __device__ __forceinline__ void bulk_wait_group_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
@@ -204,8 +213,9 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
 //   K-major  tile [rows][64 k]   : 8-row groups 1024 B apart (SBO), LBO unused.
 //   MN-major tile [64 k][64 mn] per 64-wide MN atom: 8-k-row groups 1024 B apart (SBO),
 //            atoms `atom_bytes` apart (LBO).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t lbo_bytes) {
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t lbo_bytes, uint32_t base_offset = 0) {
     uint64_t d = 0;
+    d |= static_cast<uint64_t>(base_offset & 7u) << 49;   // phase of the 8-row swizzle pattern when the start is not 1024-byte aligned
     d |= static_cast<uint64_t>((saddr >> 4) & 0x3FFF);
     d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
     d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;

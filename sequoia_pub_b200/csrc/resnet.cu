@@ -355,12 +355,21 @@ static ResNetWs ws_layout(int batch, int H, int W) {
 }
 
 // one instantiation per (tile width, CTA group); ring depth 3
-int convgemm_dispatch(int bn, int cg, const CUtensorMap* maps, const CgParams& kp, int grid, cudaStream_t st) {
-#define SQ_CG_CASE(BN, CG) if (bn == BN && cg == CG) return convgemm_launch_inst<BN, CG, 3>(maps, kp, grid, st);
+int convgemm_dispatch(int bn, int cg, int halo, const CUtensorMap* maps, const CgParams& kp, int grid, cudaStream_t st) {
+#define SQ_CG_CASE(BN, CG) if (bn == BN && cg == CG && !halo) return convgemm_launch_inst<BN, CG, 3, 0>(maps, kp, grid, st);
+#define SQ_CG_HALO(BN, CG, D) if (bn == BN && cg == CG && halo) return convgemm_launch_inst<BN, CG, D, 1>(maps, kp, grid, st);
     SQ_CG_CASE(64, 2) SQ_CG_CASE(128, 2) SQ_CG_CASE(256, 2) SQ_CG_CASE(64, 1) SQ_CG_CASE(128, 1)
+    SQ_CG_HALO(64, 2, 3) SQ_CG_HALO(128, 2, 3) SQ_CG_HALO(256, 2, 2) SQ_CG_HALO(64, 1, 3) SQ_CG_HALO(128, 1, 3)     // 256-wide: ring depth 2 leaves room for 5 weight stages
+#undef SQ_CG_HALO
 #undef SQ_CG_CASE
     set_error("convgemm: no kernel for block_n %d cta_group %d", bn, cg);
     return -1;
+}
+
+static int pool_fused_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SQ_POOL_FUSED"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v;
 }
 
 static int convgemm_enabled() {
@@ -370,10 +379,11 @@ static int convgemm_enabled() {
 }
 
 static int run_conv(const ConvSpec& c, const bf16* wbase, const float* sbase, const bf16* in, int batch, int H, int W, bf16* out_bf,
-                    float* out_f32, const bf16* res, bool relu, cudaStream_t st, int* Ho_out, int* Wo_out) {
+                    float* out_f32, const bf16* res, bool relu, cudaStream_t st, int* Ho_out, int* Wo_out, float* pool_out = nullptr) {
     const int Ho = (H + 2 * c.pad - c.k) / c.stride + 1, Wo = (W + 2 * c.pad - c.k) / c.stride + 1;
-    if (convgemm_enabled() && out_bf && !out_f32) {
+    if (convgemm_enabled() && ((out_bf && !out_f32) || pool_out)) {
         ConvGemmArgs a; memset(&a, 0, sizeof(a));
+        a.pool_out = pool_out; a.pool_batch = batch;
         a.M = batch * Ho * Wo; a.N = c.cout; a.K = c.k * c.k * c.cin;
         a.A = in; a.lda = c.cin; a.W = wbase + c.w_off; a.bias = sbase + c.s_off; a.res = res; a.out = out_bf; a.relu = relu ? 1 : 0;
         a.conv.enabled = (c.k == 1 && c.stride == 1) ? 0 : 1; a.conv.batch = batch; a.conv.H = H; a.conv.W = W; a.conv.C = c.cin; a.conv.Ho = Ho; a.conv.Wo = Wo;
@@ -490,6 +500,7 @@ int sq_resnet50_extract(const void* input, int input_kind, int batch, int H, int
     }
     // ---- 16 bottlenecks
     const int blocks[4] = {3, 4, 6, 3};
+    bool pooled = false;
     int ci = 1; int x = 0;   // big[x] holds the block input
     for (int stg = 0; stg < 4; ++stg)
         for (int b = 0; b < blocks[stg]; ++b) {
@@ -505,11 +516,18 @@ int sq_resnet50_extract(const void* input, int input_kind, int batch, int H, int
                 if (run_conv(p.conv[ci + 3], wp, shifts, big[x], batch, h, w, big[d], nullptr, nullptr, false, st, &hd, &wd)) return -1;
                 res = big[d];
             }
+            // the last convolution of an 8x8 final map feeds the fused average pool (no fp32 map, no pooling kernel)
+            const bool fuse_pool = last && h2 == 8 && w2 == 8 && convgemm_enabled() && pool_fused_enabled();
+            if (fuse_pool) {
+                cudaMemsetAsync(features, 0, (size_t)batch * 2048 * sizeof(float), st);
+                if (run_conv(c3, wp, shifts, small_[1], batch, h2, w2, nullptr, nullptr, res, true, st, &h3, &w3, features)) return -1;
+                pooled = true;
+            } else
             if (run_conv(c3, wp, shifts, small_[1], batch, h2, w2, last ? nullptr : big[y], last ? fmap : nullptr, res, true, st, &h3, &w3)) return -1;
             x = y; h = h3; w = w3;
             ci += down ? 4 : 3;
         }
-    {
+    if (!pooled) {
         const long long n = (long long)batch * 2048;
         avgpool7_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(fmap, features, batch, h, w, 2048);
     }

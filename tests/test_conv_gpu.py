@@ -1,0 +1,96 @@
+"""CTA-pair tcgen05 convolution kernel (csrc/convgemm.cuh, `sq_conv_bf16`) against torch's fp64 conv2d on the same
+bf16-rounded operands: out = relu(conv(x, w) + shift [+ residual]) rounded to bf16 (src/resnet.py:73-93 with BatchNorm folded).
+Covers 1x1 / 3x3 / strided geometries of every ResNet-50 stage, the halo-staged 3x3 mode, both CTA-group sizes, every tile
+width, ragged row counts (batch not a multiple of the tile) and the residual path."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _gm():
+    from sequoia_pub_b200 import _gemm, _lib
+    _lib.require_device()
+    return _gemm
+
+
+def _case(B, H, Cin, Cout, k, stride, res, relu, block_n=0, cta_group=0, seed=0):
+    gm = _gm()
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    pad = k // 2
+    x = torch.randn(B, H, H, Cin, device="cuda", generator=g).to(torch.bfloat16)
+    w = (torch.randn(Cout, k, k, Cin, device="cuda", generator=g) * (1.0 / (k * k * Cin) ** 0.5)).to(torch.bfloat16)
+    sh = torch.randn(Cout, device="cuda", generator=g)
+    Ho = (H + 2 * pad - k) // stride + 1
+    r = torch.randn(B, Ho, Ho, Cout, device="cuda", generator=g).to(torch.bfloat16) if res else None
+    out = torch.full((B, Ho, Ho, Cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+    gm.conv_bf16(x, w, sh, r, relu, stride, pad, block_n, cta_group, out=out)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.double().permute(0, 3, 1, 2), w.double().permute(0, 3, 1, 2), stride=stride, padding=pad).permute(0, 2, 3, 1)
+    ref = ref + sh.double()
+    if res:
+        ref = ref + r.double()
+    if relu:
+        ref = ref.clamp_min(0)
+    assert torch.isfinite(out.float()).all()
+    err = (out.double() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 6e-3, err            # one bf16 rounding of the result (2^-8 relative) plus fp32 accumulation noise
+    return out
+
+
+@pytest.mark.parametrize("geom", [
+    (4, 64, 64, 64, 1, 1, False),      # layer1 conv1 (first block)
+    (4, 64, 64, 64, 3, 1, False),      # layer1 conv2: halo mode, 64-wide tiles
+    (4, 64, 64, 256, 1, 1, True),      # layer1 conv3 + residual
+    (4, 64, 256, 64, 1, 1, False),     # layer1 conv1 (later blocks)
+    (4, 64, 128, 128, 3, 2, False),    # layer2 conv2, stride 2 (per-tap boxes)
+    (4, 64, 256, 512, 1, 2, False),    # layer2 downsample, 1x1 stride 2
+    (4, 32, 128, 128, 3, 1, False),    # layer2 conv2: halo mode, two channel blocks
+    (4, 32, 128, 512, 1, 1, True),
+    (8, 16, 256, 256, 3, 1, False),    # layer3 conv2
+    (8, 16, 256, 1024, 1, 1, True),
+    (8, 16, 1024, 256, 1, 1, False),
+    (16, 8, 512, 512, 3, 1, False),    # layer4 conv2: two images per 128-row tile
+    (16, 8, 512, 2048, 1, 1, True),
+])
+def test_resnet_geometries(geom):
+    B, H, Cin, Cout, k, stride, res = geom
+    _case(B, H, Cin, Cout, k, stride, res, True)
+
+
+@pytest.mark.parametrize("cta_group", [1, 2])
+@pytest.mark.parametrize("block_n", [64, 128, 256])
+def test_tile_widths_and_cta_groups(block_n, cta_group):
+    if cta_group == 1 and block_n == 256:
+        pytest.skip("a single CTA has no 256-wide configuration (falls back to 128)")
+    _case(3, 32, 128, 256, 1, 1, True, True, block_n, cta_group)       # 3072 rows: 24 tiles, ragged pair count for some grids
+    _case(3, 32, 64, 256, 3, 1, False, True, block_n, cta_group)
+
+
+def test_ragged_rows_and_no_relu():
+    _case(5, 16, 64, 64, 1, 1, False, False)      # 1280 rows = 10 tiles; 5 CTA pairs
+    _case(1, 16, 64, 128, 3, 1, False, True)      # 256 rows: a single pair
+    _case(3, 8, 128, 128, 1, 1, True, False)      # 192 rows: the second tile of the pair is half out of range
+    _case(7, 8, 64, 64, 3, 1, False, True)        # 448 rows, two images per tile, odd image count
+
+
+def test_fused_average_pool_matches_unfused():
+    """Last convolution + AvgPool2d(7) on the 8x8 map (top-left 7x7, src/resnet.py:110,166) fused into the epilogue: the
+    extractor output must agree with the un-fused path (fp32 map + pooling kernel) to fp32 summation-order noise."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys, torch; sys.path.insert(0, %r)\n"
+            "from oracle import resnet50_oracle as O\n"
+            "from sequoia_pub_b200.resnet import resnet50\n"
+            "m = resnet50().eval(); m.load_state_dict(O.make_state_dict(0)); m = m.cuda()\n"
+            "f = m.extract_uint8(O.make_patches(5, 3).cuda()); torch.save(f.cpu(), sys.argv[1])\n") % root
+    outs = []
+    for fused in ("1", "0"):
+        path = f"/tmp/sq_pool_{fused}.pt"
+        subprocess.run([sys.executable, "-c", code, path], env=dict(os.environ, SQ_POOL_FUSED=fused), check=True, timeout=300)
+        outs.append(torch.load(path))
+    rel = ((outs[0] - outs[1]).norm() / outs[1].norm()).item()
+    assert rel < 1e-6, rel
