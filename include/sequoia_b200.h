@@ -235,15 +235,21 @@ SQ_API int sq_vitl16_extract(const void* input, int input_kind, int batch, int d
  * The MT19937 draws are data independent and come from the caller:
  *   first_center = RandomState(seed).choice(n, p=uniform);  uniforms = the next (k-1)*trials .uniform() doubles (device),
  *   trials = 2 + int(ln k).
+ * init_rows (may be NULL): int32 [k] device, explicit initial centre rows instead of k-means++ (sklearn's `init=X[rows]`;
+ *   duplicates are allowed and exercise the empty-cluster relocation); uniforms may then be NULL.
  * Outputs (device): labels int32 [n]; cluster_means fp32 [k, d] = mean of the RAW rows of every label, ascending row
- * order (a row of NaN for an empty label, like np.mean); chosen (may be NULL) int32 [k] = k-means++ seed rows.
- * n_iter_host (may be NULL) receives sklearn's n_iter_.  UNLIKE the other entry points this one synchronises the stream
- * once per Lloyd iteration (the convergence test decides on the host whether another iteration is enqueued).
- * Returns -2 if an iteration produces an empty cluster (sklearn's relocation step is not implemented). */
+ * order (a row of NaN for an empty label, like np.mean); chosen (may be NULL) int32 [k] = initial centre rows;
+ * n_iter_dev (may be NULL) int32 [1] = sklearn's n_iter_.
+ * Empty clusters are relocated like sklearn's _relocate_empty_clusters_dense (farthest samples in descending distance).
+ * Like every other entry point this one only ENQUEUES: the Lloyd loop is a CUDA graph with a device-controlled WHILE node
+ * (one graph per workspace and shape, cached); with SQ_KMEANS_GRAPH=0, or a driver without conditional graph nodes, it falls back
+ * to a host loop that synchronises the stream once per iteration.
+ * Limits: d % 4 == 0; 2 <= trials <= 10 (k < 2981); n <= ~40 000 samples (single-block selection kernels; the reference caps a
+ * slide at max_patch_number = 4000 tiles, pre_processing/compute_features_hdf5.py:26). */
 SQ_API size_t sq_kmeans_workspace_bytes(int n, int d, int k);
 SQ_API int sq_kmeans_fit(const float* features, int n, int d, int k, int trials, int first_center, const double* uniforms,
-                         int max_iter, float tol_scale, int* labels, float* cluster_means, int* chosen, int* n_iter_host,
-                         void* workspace, size_t workspace_bytes, void* stream);
+                         const int* init_rows, int max_iter, float tol_scale, int* labels, float* cluster_means, int* chosen,
+                         int* n_iter_dev, void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -104,8 +104,8 @@ SIGNATURES = {
     "sq_vitl16_workspace_bytes": (c_size_t, [c_int]),
     "sq_vitl16_extract": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "sq_kmeans_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
-    "sq_kmeans_fit": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p,
-                              C.POINTER(c_int), c_void_p, c_size_t, c_void_p]),
+    "sq_kmeans_fit": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p,
+                              c_void_p, c_void_p, c_size_t, c_void_p]),
 }
 
 _lib = None
@@ -138,9 +138,18 @@ def ptr(t):
     return None if t is None else c_void_p(t.data_ptr())
 
 
-def stream_ptr():
+def stream_ptr(t=None):
+    """Current CUDA stream of the device that holds tensor `t` (or of the current device).  The library enqueues on the device
+    that is current when it is called, so callers whose tensors may live on another device wrap the call in `on_device(t)`."""
     import torch
-    return c_void_p(torch.cuda.current_stream().cuda_stream)
+    dev = t.device if t is not None and getattr(t, "is_cuda", False) else None
+    return c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def on_device(t):
+    """Context manager that makes the device of tensor `t` current (models built with device='cuda:1' and no set_device)."""
+    import torch
+    return torch.cuda.device(t.device if getattr(t, "is_cuda", False) else torch.cuda.current_device())
 
 
 _device_checked = set()

@@ -18,9 +18,9 @@
 namespace sq {
 
 constexpr int KM_NB = 4096;          // OpenBLAS sgemv_t block length
-constexpr int KM_MAXT = 8;           // max local trials
+constexpr int KM_MAXT = 10;          // max local trials: 2 + int(ln k) for k < 2981
 
-struct KmFlags { int n_changed; int tol_ok; int n_empty; int pad; float shift_tot; float tol; };
+struct KmFlags { int n_changed; int tol_ok; int n_empty; int reloc_skip; float shift_tot; float tol; int iter; int done; int strict; int max_iter; };
 
 // ---------------------------------------------------------------- preparation
 // One thread per column: sequential float32 sum over rows (numpy's order), mean = sum / n; second pass: variance.
@@ -147,8 +147,11 @@ __device__ void km_gemv_order_block(const float* __restrict__ rows, int T, int n
     const int t = tid >> 3, l = tid & 7;           // lane-threads: tid < 8*T
     const bool worker = t < T;
     const unsigned wmask = __ballot_sync(0xffffffffu, worker);
+    // rows go to the 4-column kernel four at a time (kind 0), a remaining pair to the 2-column kernel (kind 1), a remaining
+    // single row to the 1-column kernel, whose order equals kind 0 (oracle/kmeans_oracle.py: gemv_row_kind)
     const int rem = T & 3;
-    const int kind = (worker && t < T - rem) ? 0 : 1;
+    int kind = 0;
+    if (worker && t >= T - rem) { const int rr = t - (T - rem); kind = ((rem & 2) && rr < 2) ? 1 : 0; }
     const int m1 = n - (n & 3);
     float y = 0.f, acc = 0.f;
     for (int b0 = 0; b0 < m1; b0 += KM_NB) {
@@ -180,8 +183,9 @@ __device__ void km_gemv_order_block(const float* __restrict__ rows, int T, int n
         if (worker) {
             const unsigned mask = wmask;
             const int base = (tid & 31) & ~7;
-            float sfold = acc;
-            if (kind == 0) sfold = __fadd_rn(acc, __shfl_sync(mask, acc, base + ((l + 4) & 7)));
+            // (the shuffle is executed by every worker lane of the warp: rows of both kinds can share a warp, e.g. 7 trials)
+            const float other = __shfl_sync(mask, acc, base + ((l + 4) & 7));
+            const float sfold = kind == 0 ? __fadd_rn(acc, other) : acc;
             const float p01 = __fadd_rn(__shfl_sync(mask, sfold, base + 0), __shfl_sync(mask, sfold, base + 1));
             const float p23 = __fadd_rn(__shfl_sync(mask, sfold, base + 2), __shfl_sync(mask, sfold, base + 3));
             y = __fadd_rn(y, __fadd_rn(p01, p23));
@@ -292,7 +296,15 @@ __global__ void km_gather_centers_kernel(const float* __restrict__ Xc, const int
         *reinterpret_cast<float4*>(centers + (size_t)j * d + c) = *reinterpret_cast<const float4*>(Xc + (size_t)chosen[j] * d + c);
 }
 
-__global__ void km_center_norm_kernel(const float* __restrict__ centers, int k, int d, float* __restrict__ csq) {
+// The Lloyd kernels take both centre buffers and pick "current" / "next" from the parity of the device-side iteration counter,
+// so the same launches serve every iteration of the loop (host loop or CUDA-graph while node).
+__device__ __forceinline__ const float* km_cur(const float* c0, const float* c1, const KmFlags* f) { return (f->iter & 1) ? c1 : c0; }
+__device__ __forceinline__ float* km_nxt(float* c0, float* c1, const KmFlags* f) { return (f->iter & 1) ? c0 : c1; }
+
+__global__ void km_center_norm_kernel(const float* __restrict__ c0, const float* __restrict__ c1, const KmFlags* __restrict__ flags, int final_pass,
+                                      int k, int d, float* __restrict__ csq) {
+    if (final_pass && flags->strict) return;
+    const float* centers = km_cur(c0, c1, flags);
     const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (j >= k) return;
@@ -306,9 +318,12 @@ __global__ void km_center_norm_kernel(const float* __restrict__ centers, int k, 
 // label[i] = first argmin_j (csq[j] - 2 <x_i, c_j>) in float32.  Block = 32 rows x 128 centres (looping over centre
 // tiles when k > 128), 128 threads, each 4 rows x 8 centres (centres tx*4..+3 and 64+tx*4..+3); K is consumed in
 // ascending chunks of 32 through shared memory, one FMA chain per (row, centre).
-__global__ void __launch_bounds__(128) km_assign_kernel(const float* __restrict__ Xc, const float* __restrict__ centers, const float* __restrict__ csq,
-                                                        int n, int d, int k, const int* __restrict__ labels_old, int* __restrict__ labels,
-                                                        KmFlags* flags) {
+__global__ void __launch_bounds__(128) km_assign_kernel(const float* __restrict__ Xc, const float* __restrict__ c0, const float* __restrict__ c1,
+                                                        const float* __restrict__ csq, int n, int d, int k, const int* __restrict__ labels_old_in,
+                                                        int* __restrict__ labels, KmFlags* flags, int final_pass) {
+    if (final_pass && flags->strict) return;               // labels of a strictly converged run are final (sklearn L741-753)
+    const float* centers = km_cur(c0, c1, flags);
+    const int* labels_old = (final_pass || flags->iter == 0) ? nullptr : labels_old_in;
     __shared__ __align__(16) float Xs[32][36];       // [k][row]    (+4 padding keeps float4 reads aligned)
     __shared__ __align__(16) float Cs[32][132];      // [k][centre]
     __shared__ float bestv[32][16];
@@ -406,16 +421,93 @@ __global__ void __launch_bounds__(1024) km_bucket_kernel(const int* __restrict__
     }
 }
 
+// ---------------------------------------------------------------- empty-cluster relocation (sklearn _relocate_empty_clusters_dense)
+// numpy's float32 pairwise summation (loops_utils.h.src: blocks of <= 128 elements with 8 accumulators, halves split on
+// multiples of 8) of (x[i] - c[i])^2 over i < n: the order of `((X - centers_old[labels])**2).sum(axis=1)`.
+__device__ float km_pairwise_sqdist(const float* __restrict__ x, const float* __restrict__ c, int n) {
+    if (n < 8) {
+        float res = 0.f;
+        for (int i = 0; i < n; ++i) { const float e = __fsub_rn(x[i], c[i]); res = __fadd_rn(res, __fmul_rn(e, e)); }
+        return res;
+    }
+    if (n <= 128) {
+        float r[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const float e = __fsub_rn(x[u], c[u]); r[u] = __fmul_rn(e, e); }
+        const int m = n - (n % 8);
+        for (int i = 8; i < m; i += 8) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { const float e = __fsub_rn(x[i + u], c[i + u]); r[u] = __fadd_rn(r[u], __fmul_rn(e, e)); }
+        }
+        float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])), __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+        for (int i = m; i < n; ++i) { const float e = __fsub_rn(x[i], c[i]); res = __fadd_rn(res, __fmul_rn(e, e)); }
+        return res;
+    }
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    return __fadd_rn(km_pairwise_sqdist(x, c, n2), km_pairwise_sqdist(x + n2, c + n2, n - n2));
+}
+
+// distances[i] = ||x_i - centers_old[label_i]||^2 in numpy's order; only runs when the bucketing found an empty cluster
+__global__ void km_reloc_dist_kernel(const float* __restrict__ Xc, const float* __restrict__ c0, const float* __restrict__ c1,
+                                     const int* __restrict__ labels, int n, int d, const KmFlags* __restrict__ flags, float* __restrict__ dist) {
+    if (flags->n_empty == 0) return;
+    const float* centers = km_cur(c0, c1, flags);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dist[i] = km_pairwise_sqdist(Xc + (size_t)i * d, centers + (size_t)labels[i] * d, d);
+}
+
+// One block: empty cluster ids (ascending) and the n_empty samples farthest from their centres in descending distance (ties:
+// lower row first) - the order numpy 2.x's argpartition(distances, -n_empty)[:-n_empty-1:-1] returns on x86-64 (see the oracle).
+__global__ void __launch_bounds__(1024) km_reloc_select_kernel(float* __restrict__ dist, const int* __restrict__ offsets, int n, int k,
+                                                               KmFlags* flags, int* __restrict__ empty_ids, int* __restrict__ far) {
+    const int n_empty = flags->n_empty;
+    if (n_empty == 0) return;
+    __shared__ float bv[32];
+    __shared__ int bi[32];
+    __shared__ int s_pick;
+    const int tid = threadIdx.x;
+    if (tid == 0) { int e = 0; for (int j = 0; j < k; ++j) if (offsets[j + 1] == offsets[j]) empty_ids[e++] = j; }
+    for (int e = 0; e < n_empty; ++e) {
+        float v = -1.0f; int idx = 0x7fffffff;
+        for (int i = tid; i < n; i += blockDim.x) { const float x = dist[i]; if (x > v || (x == v && i < idx)) { v = x; idx = i; } }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float v2 = __shfl_xor_sync(0xffffffffu, v, o); const int i2 = __shfl_xor_sync(0xffffffffu, idx, o);
+            if (v2 > v || (v2 == v && i2 < idx)) { v = v2; idx = i2; }
+        }
+        if ((tid & 31) == 0) { bv[tid >> 5] = v; bi[tid >> 5] = idx; }
+        __syncthreads();
+        if (tid == 0) {
+            float m = bv[0]; int mi = bi[0];
+            for (int w = 1; w < (int)(blockDim.x >> 5); ++w) if (bv[w] > m || (bv[w] == m && bi[w] < mi)) { m = bv[w]; mi = bi[w]; }
+            if (e == 0) flags->reloc_skip = (m == 0.0f) ? 1 : 0;       // np.max(distances) == 0: relocation is pointless, centres stay 0
+            far[e] = mi; s_pick = mi;
+        }
+        __syncthreads();
+        if (tid == 0) dist[s_pick] = -1.0f;                            // taken
+        __syncthreads();
+    }
+}
+
 // out[j, c] = (sum over members of cluster j, ascending rows, of src[row, c]) * (1/count)   [mode 0: sklearn _average_centers]
 //                                                                          / count          [mode 1: np.mean]
 // and, when `old` is given, per-(cluster, block) partial sums of (new - old)^2 for the centre shift.
+// mode 0 also applies the relocation of empty clusters (reloc != null): an empty cluster takes its far sample, the cluster that
+// sample was assigned to loses it (sum - x, count - 1, in the order of the empty cluster ids); a cluster left without weight keeps
+// its sum (sklearn only scales clusters with weight > 0).
 __global__ void __launch_bounds__(128) km_segment_mean_kernel(const float* __restrict__ src, const int* __restrict__ offsets,
-                                                              const int* __restrict__ members, int d, int mode, float* __restrict__ out,
-                                                              const float* __restrict__ old, float* __restrict__ shift_part) {
+                                                              const int* __restrict__ members, int d, int mode, float* __restrict__ out_in,
+                                                              float* __restrict__ c0, float* __restrict__ c1, float* __restrict__ shift_part,
+                                                              const KmFlags* __restrict__ flags, const int* __restrict__ labels,
+                                                              const int* __restrict__ empty_ids, const int* __restrict__ far) {
     __shared__ float red[4];
     const int j = blockIdx.y;
     const int c = (blockIdx.x * 128 + threadIdx.x) * 4;
     const int b = offsets[j], e = offsets[j + 1];
+    const int n_reloc = (mode == 0 && flags->n_empty > 0 && !flags->reloc_skip) ? flags->n_empty : 0;
+    float* out = mode == 0 ? km_nxt(c0, c1, flags) : out_in;
+    const float* old = mode == 0 ? km_cur(c0, c1, flags) : nullptr;
     float sq = 0.f;
     if (c < d) {
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -423,8 +515,14 @@ __global__ void __launch_bounds__(128) km_segment_mean_kernel(const float* __res
             const float4 v = *reinterpret_cast<const float4*>(src + (size_t)members[p] * d + c);
             a.x = __fadd_rn(a.x, v.x); a.y = __fadd_rn(a.y, v.y); a.z = __fadd_rn(a.z, v.z); a.w = __fadd_rn(a.w, v.w);
         }
-        const float cnt = (float)(e - b);
-        if (mode == 0) { const float inv = __fdiv_rn(1.0f, cnt); a.x = __fmul_rn(a.x, inv); a.y = __fmul_rn(a.y, inv); a.z = __fmul_rn(a.z, inv); a.w = __fmul_rn(a.w, inv); }
+        float cnt = (float)(e - b);
+        for (int r = 0; r < n_reloc; ++r) {
+            const int fi = far[r];
+            const float4 v = *reinterpret_cast<const float4*>(src + (size_t)fi * d + c);
+            if (empty_ids[r] == j) { a = v; cnt = 1.0f; }
+            else if (labels[fi] == j) { a.x = __fsub_rn(a.x, v.x); a.y = __fsub_rn(a.y, v.y); a.z = __fsub_rn(a.z, v.z); a.w = __fsub_rn(a.w, v.w); cnt -= 1.0f; }
+        }
+        if (mode == 0) { if (cnt > 0.0f) { const float inv = __fdiv_rn(1.0f, cnt); a.x = __fmul_rn(a.x, inv); a.y = __fmul_rn(a.y, inv); a.z = __fmul_rn(a.z, inv); a.w = __fmul_rn(a.w, inv); } }
         else { a.x = __fdiv_rn(a.x, cnt); a.y = __fdiv_rn(a.y, cnt); a.z = __fdiv_rn(a.z, cnt); a.w = __fdiv_rn(a.w, cnt); }
         *reinterpret_cast<float4*>(out + (size_t)j * d + c) = a;
         if (old) {
@@ -443,7 +541,11 @@ __global__ void __launch_bounds__(128) km_segment_mean_kernel(const float* __res
 }
 
 // center_shift_tot = sum_j ||new_j - old_j||^2 ; tol test (sklearn L717-727)
-__global__ void km_converge_kernel(const float* __restrict__ shift_part, int k, int nparts, KmFlags* flags) {
+// ... and the loop control of _kmeans_single_lloyd (L700-735): strict convergence (labels unchanged) is tested first, then the
+// tolerance; advances the iteration counter (which also swaps the centre buffers) and, inside a CUDA-graph while node, clears the
+// node's condition when the loop is over.
+__global__ void km_converge_kernel(const float* __restrict__ shift_part, int k, int nparts, KmFlags* flags, int* __restrict__ n_iter_out,
+                                   unsigned long long cond_handle) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     float tot = 0.f;
     for (int j = 0; j < k; ++j) {
@@ -453,10 +555,19 @@ __global__ void km_converge_kernel(const float* __restrict__ shift_part, int k, 
         tot += sh * sh;
     }
     flags->shift_tot = tot;
-    flags->tol_ok = tot <= flags->tol ? 1 : 0;
+    const int tol_ok = tot <= flags->tol ? 1 : 0;
+    flags->tol_ok = tol_ok;
+    const int it = flags->iter;
+    const int strict = (it > 0 && flags->n_changed == 0) ? 1 : 0;
+    const int done = (strict || tol_ok || it + 1 >= flags->max_iter) ? 1 : 0;
+    flags->strict = strict; flags->done = done;
+    flags->iter = it + 1;
+    flags->n_changed = 0;
+    if (n_iter_out) *n_iter_out = it + 1;
+    if (done && cond_handle) cudaGraphSetConditional((cudaGraphConditionalHandle)cond_handle, 0);
 }
 
-struct KmWs { size_t xc, xx64, mean, var, closest, newc, cand, chosen, pot, cA, cB, csq, labels_old, offsets, members, shift, flags, total; };
+struct KmWs { size_t xc, xx64, mean, var, closest, newc, cand, chosen, pot, cA, cB, csq, labels, labels_old, offsets, members, shift, flags, rdist, empty_ids, far, n_iter, total; };
 
 static void km_ws_layout(int n, int d, int k, KmWs* w) {
     size_t off = 0;
@@ -464,8 +575,9 @@ static void km_ws_layout(int n, int d, int k, KmWs* w) {
     w->xc = take((size_t)n * d * 4); w->xx64 = take((size_t)n * 8); w->mean = take((size_t)d * 4); w->var = take((size_t)d * 4);
     w->closest = take((size_t)n * 4); w->newc = take((size_t)KM_MAXT * n * 4); w->cand = take(KM_MAXT * 4); w->chosen = take((size_t)k * 4);
     w->pot = take(4); w->cA = take((size_t)k * d * 4); w->cB = take((size_t)k * d * 4); w->csq = take((size_t)k * 4);
-    w->labels_old = take((size_t)n * 4); w->offsets = take((size_t)(k + 1) * 4); w->members = take((size_t)n * 4);
+    w->labels = take((size_t)n * 4); w->labels_old = take((size_t)n * 4); w->offsets = take((size_t)(k + 1) * 4); w->members = take((size_t)n * 4);
     w->shift = take((size_t)k * ((d + 511) / 512) * 4); w->flags = take(sizeof(KmFlags));
+    w->rdist = take((size_t)n * 4); w->empty_ids = take((size_t)k * 4); w->far = take((size_t)k * 4); w->n_iter = take(4);
     w->total = off;
 }
 
@@ -487,16 +599,84 @@ size_t sq_kmeans_workspace_bytes(int n, int d, int k) {
     return w.total;
 }
 
-int sq_kmeans_fit(const float* features, int n, int d, int k, int trials, int first_center, const double* uniforms, int max_iter, float tol_scale,
-                  int* labels, float* cluster_means, int* chosen_out, int* n_iter_host, void* workspace, size_t workspace_bytes, void* stream) {
-    if (!features || !uniforms || !labels || !cluster_means) { set_error("kmeans: null pointer"); return -1; }
+}  // extern "C"
+
+namespace sq {
+
+struct KmPtrs {
+    float *Xc, *cA, *cB, *csq, *shift, *rdist; int *labels, *labels_old, *offsets, *members, *empty_ids, *far, *n_iter; KmFlags* flags;
+    int n, d, k;
+};
+
+// one Lloyd iteration (lloyd_iter_chunked_dense + relocation + averaging + centre shift + loop control)
+static void km_enqueue_iteration(const KmPtrs& P, unsigned long long cond, cudaStream_t st) {
+    const int n = P.n, d = P.d, k = P.k, nparts = (d + 511) / 512;
+    const size_t bucket_smem = (size_t)n * 4 + (size_t)(k + 1) * 4;
+    km_center_norm_kernel<<<(k + 7) / 8, 256, 0, st>>>(P.cA, P.cB, P.flags, 0, k, d, P.csq);
+    km_assign_kernel<<<(n + 31) / 32, 128, 0, st>>>(P.Xc, P.cA, P.cB, P.csq, n, d, k, P.labels_old, P.labels, P.flags, 0);
+    km_bucket_kernel<<<1, 1024, bucket_smem, st>>>(P.labels, n, k, P.offsets, P.members, P.flags);
+    km_reloc_dist_kernel<<<(n + 127) / 128, 128, 0, st>>>(P.Xc, P.cA, P.cB, P.labels, n, d, P.flags, P.rdist);
+    km_reloc_select_kernel<<<1, 1024, 0, st>>>(P.rdist, P.offsets, n, k, P.flags, P.empty_ids, P.far);
+    km_segment_mean_kernel<<<dim3(nparts, k), 128, 0, st>>>(P.Xc, P.offsets, P.members, d, 0, nullptr, P.cA, P.cB, P.shift, P.flags, P.labels, P.empty_ids, P.far);
+    km_converge_kernel<<<1, 32, 0, st>>>(P.shift, k, nparts, P.flags, P.n_iter, cond);
+    cudaMemcpyAsync(P.labels_old, P.labels, (size_t)n * 4, cudaMemcpyDeviceToDevice, st);
+}
+
+// The Lloyd loop as a CUDA graph with a WHILE conditional node (CUDA >= 12.4): the body is one iteration, the condition is
+// cleared on the device by km_converge_kernel - no host round trip per iteration.  Graphs are cached per (device, workspace, shape).
+struct KmGraph { int dev; void* ws; int n, d, k; cudaGraphExec_t exec; cudaGraph_t graph; unsigned long long stamp; };
+static KmGraph g_km_graphs[8];
+static unsigned long long g_km_stamp = 0;
+static cudaStream_t g_km_capture[16];
+
+static cudaGraphExec_t km_lloyd_graph(const KmPtrs& P, void* ws) {
+    int dev = 0; cudaGetDevice(&dev);
+    for (auto& e : g_km_graphs)
+        if (e.exec && e.dev == dev && e.ws == ws && e.n == P.n && e.d == P.d && e.k == P.k) { e.stamp = ++g_km_stamp; return e.exec; }
+    if (dev < 0 || dev >= 16) return nullptr;
+    if (!g_km_capture[dev] && cudaStreamCreateWithFlags(&g_km_capture[dev], cudaStreamNonBlocking) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+    cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
+    if (cudaGraphCreate(&graph, 0) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+    cudaGraphConditionalHandle h;
+    cudaGraphNodeParams np = {};
+    bool ok = cudaGraphConditionalHandleCreate(&h, graph, 1, cudaGraphCondAssignDefault) == cudaSuccess;
+    cudaGraphNode_t node;
+    if (ok) {
+        np.type = cudaGraphNodeTypeConditional; np.conditional.handle = h; np.conditional.type = cudaGraphCondTypeWhile; np.conditional.size = 1;
+        ok = cudaGraphAddNode(&node, graph, nullptr, 0, &np) == cudaSuccess;
+    }
+    if (ok) {
+        cudaGraph_t body = np.conditional.phGraph_out[0];
+        ok = cudaStreamBeginCaptureToGraph(g_km_capture[dev], body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+        if (ok) {
+            km_enqueue_iteration(P, (unsigned long long)h, g_km_capture[dev]);
+            ok = cudaStreamEndCapture(g_km_capture[dev], nullptr) == cudaSuccess;
+        }
+    }
+    if (ok) ok = cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+    if (!ok) { (void)cudaGetLastError(); if (graph) cudaGraphDestroy(graph); return nullptr; }
+    KmGraph* slot = &g_km_graphs[0];
+    for (auto& e : g_km_graphs) { if (!e.exec) { slot = &e; break; } if (e.stamp < slot->stamp) slot = &e; }
+    if (slot->exec) { cudaGraphExecDestroy(slot->exec); cudaGraphDestroy(slot->graph); }
+    *slot = KmGraph{dev, ws, P.n, P.d, P.k, exec, graph, ++g_km_stamp};
+    return exec;
+}
+
+}  // namespace sq
+
+extern "C" {
+
+int sq_kmeans_fit(const float* features, int n, int d, int k, int trials, int first_center, const double* uniforms, const int* init_rows,
+                  int max_iter, float tol_scale, int* labels, float* cluster_means, int* chosen_out, int* n_iter_dev, void* workspace,
+                  size_t workspace_bytes, void* stream) {
+    if (!features || (!uniforms && !init_rows) || !labels || !cluster_means) { set_error("kmeans: null pointer"); return -1; }
     if (n < k || k < 1) { set_error("kmeans: need n >= k >= 1 (n=%d, k=%d)", n, k); return -1; }
     if (d % 4 != 0) { set_error("kmeans: feature dim %d must be a multiple of 4", d); return -1; }
-    if (trials < 1 || trials > KM_MAXT || !((trials & 3) == 0 || (trials & 3) == 2)) {
-        set_error("kmeans: %d local trials unsupported (the restated sgemv order covers trials %% 4 in {0, 2}; k in [55,148] gives 6)", trials); return -1;
-    }
-    if (first_center < 0 || first_center >= n) { set_error("kmeans: first centre out of range"); return -1; }
-    if ((size_t)n * 4 + (size_t)(k + 1) * 4 > 160 * 1024) { set_error("kmeans: n=%d too large for the single-block selection kernels", n); return -1; }
+    if (!init_rows && (trials < 2 || trials > KM_MAXT)) { set_error("kmeans: %d local trials unsupported (2 .. %d, i.e. k < 2981)", trials, KM_MAXT); return -1; }
+    if (!init_rows && (first_center < 0 || first_center >= n)) { set_error("kmeans: first centre out of range"); return -1; }
+    if (max_iter < 1) { set_error("kmeans: max_iter must be >= 1"); return -1; }
+    // the selection / bucketing kernels keep one value per sample in the shared memory of a single block
+    if ((size_t)n * 4 + (size_t)(k + 1) * 4 > 160 * 1024) { set_error("kmeans: n=%d exceeds the %d samples the single-block selection kernels hold", n, (160 * 1024 - (k + 1) * 4) / 4); return -1; }
     KmWs L; km_ws_layout(n, d, k, &L);
     if (!workspace || workspace_bytes < L.total) { set_error("kmeans: workspace %zu < %zu", workspace_bytes, L.total); return -1; }
     cudaStream_t st = (cudaStream_t)stream;
@@ -505,70 +685,80 @@ int sq_kmeans_fit(const float* features, int n, int d, int k, int trials, int fi
     float* mean = (float*)(ws + L.mean); float* var = (float*)(ws + L.var);
     float* closest = (float*)(ws + L.closest); float* newc = (float*)(ws + L.newc);
     int* cand = (int*)(ws + L.cand); int* chosen = (int*)(ws + L.chosen); float* pot = (float*)(ws + L.pot);
-    float* cA = (float*)(ws + L.cA); float* cB = (float*)(ws + L.cB); float* csq = (float*)(ws + L.csq);
-    int* labels_old = (int*)(ws + L.labels_old); int* offsets = (int*)(ws + L.offsets); int* members = (int*)(ws + L.members);
-    float* shift = (float*)(ws + L.shift); KmFlags* flags = (KmFlags*)(ws + L.flags);
+    KmPtrs P;
+    P.Xc = Xc; P.cA = (float*)(ws + L.cA); P.cB = (float*)(ws + L.cB); P.csq = (float*)(ws + L.csq); P.shift = (float*)(ws + L.shift);
+    P.rdist = (float*)(ws + L.rdist); P.labels = (int*)(ws + L.labels); P.labels_old = (int*)(ws + L.labels_old); P.offsets = (int*)(ws + L.offsets);
+    P.members = (int*)(ws + L.members); P.empty_ids = (int*)(ws + L.empty_ids); P.far = (int*)(ws + L.far); P.n_iter = (int*)(ws + L.n_iter);
+    P.flags = (KmFlags*)(ws + L.flags); P.n = n; P.d = d; P.k = k;
+    KmFlags* flags = P.flags;
 
     static bool attr_done = false;
     if (!attr_done) {
-        cudaFuncSetAttribute(km_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(km_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         cudaFuncSetAttribute(km_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_done = true;
     }
     const size_t sel_smem = (size_t)((n + 31) & ~31) * 4 + (size_t)KM_MAXT * KM_CHUNK * 4;
-    cudaMemsetAsync(flags, 0, sizeof(KmFlags), st);
+    KmFlags h0; memset(&h0, 0, sizeof(h0)); h0.max_iter = max_iter;
+    cudaMemcpyAsync(flags, &h0, sizeof(KmFlags), cudaMemcpyHostToDevice, st);      // pageable source: copied before the call returns
     // ---- preparation (fit L1490-1500)
     km_colstats_kernel<<<(d + 63) / 64, 64, 0, st>>>(features, n, d, mean, var);
     km_tol_kernel<<<1, 256, 0, st>>>(var, d, tol_scale, flags);
     km_center_kernel<<<(n + 7) / 8, 256, 0, st>>>(features, mean, n, d, Xc, xx64);
-    // ---- k-means++ (L180-279)
-    cudaMemcpyAsync(cand, &first_center, sizeof(int), cudaMemcpyHostToDevice, st);
-    launch_dist<1>(Xc, xx64, cand, nullptr, n, d, newc, st);
-    km_select_kernel<<<1, 1024, sel_smem, st>>>(newc, 1, n, 0, k, trials, uniforms, closest, cand, chosen, pot);
-    for (int c = 1; c < k; ++c) {
-        switch (trials) {
-            case 2: launch_dist<2>(Xc, xx64, cand, closest, n, d, newc, st); break;
-            case 4: launch_dist<4>(Xc, xx64, cand, closest, n, d, newc, st); break;
-            case 6: launch_dist<6>(Xc, xx64, cand, closest, n, d, newc, st); break;
-            default: launch_dist<8>(Xc, xx64, cand, closest, n, d, newc, st); break;
+    if (init_rows) {
+        // explicit initial centres (sklearn's `init=X[rows]`): no seeding; duplicates are allowed and give empty clusters
+        cudaMemcpyAsync(chosen, init_rows, (size_t)k * 4, cudaMemcpyDeviceToDevice, st);
+    } else {
+        // ---- k-means++ (L180-279)
+        cudaMemcpyAsync(cand, &first_center, sizeof(int), cudaMemcpyHostToDevice, st);
+        launch_dist<1>(Xc, xx64, cand, nullptr, n, d, newc, st);
+        km_select_kernel<<<1, 1024, sel_smem, st>>>(newc, 1, n, 0, k, trials, uniforms, closest, cand, chosen, pot);
+        for (int c = 1; c < k; ++c) {
+            switch (trials) {
+                case 2: launch_dist<2>(Xc, xx64, cand, closest, n, d, newc, st); break;
+                case 3: launch_dist<3>(Xc, xx64, cand, closest, n, d, newc, st); break;
+                case 4: launch_dist<4>(Xc, xx64, cand, closest, n, d, newc, st); break;
+                case 5: launch_dist<5>(Xc, xx64, cand, closest, n, d, newc, st); break;
+                case 6: launch_dist<6>(Xc, xx64, cand, closest, n, d, newc, st); break;
+                case 7: launch_dist<7>(Xc, xx64, cand, closest, n, d, newc, st); break;
+                case 8: launch_dist<8>(Xc, xx64, cand, closest, n, d, newc, st); break;
+                case 9: launch_dist<9>(Xc, xx64, cand, closest, n, d, newc, st); break;
+                default: launch_dist<10>(Xc, xx64, cand, closest, n, d, newc, st); break;
+            }
+            km_select_kernel<<<1, 1024, sel_smem, st>>>(newc, trials, n, c, k, trials, uniforms, closest, cand, chosen, pot);
         }
-        km_select_kernel<<<1, 1024, sel_smem, st>>>(newc, trials, n, c, k, trials, uniforms, closest, cand, chosen, pot);
     }
-    km_gather_centers_kernel<<<k, 256, 0, st>>>(Xc, chosen, k, d, cA);
+    km_gather_centers_kernel<<<k, 256, 0, st>>>(Xc, chosen, k, d, P.cA);
     if (chosen_out) cudaMemcpyAsync(chosen_out, chosen, (size_t)k * 4, cudaMemcpyDeviceToDevice, st);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) { set_error("kmeans seeding: %s", cudaGetErrorString(err)); return -1; }
-    // ---- Lloyd (L630-758). The convergence test needs the host: one 24-byte read + stream sync per iteration.
-    float* cur = cA; float* nxt = cB;
+    // ---- Lloyd (L630-758)
+    static const int use_graph = getenv("SQ_KMEANS_GRAPH") ? atoi(getenv("SQ_KMEANS_GRAPH")) : 1;
+    cudaGraphExec_t exec = use_graph ? km_lloyd_graph(P, workspace) : nullptr;
+    if (exec) {
+        err = cudaGraphLaunch(exec, st);
+        if (err != cudaSuccess) { set_error("kmeans lloyd graph: %s", cudaGetErrorString(err)); return -1; }
+    } else {
+        // no conditional graph nodes (old driver) or SQ_KMEANS_GRAPH=0: host loop, one 40-byte read + stream sync per iteration
+        KmFlags h;
+        for (int it = 0; it < max_iter; ++it) {
+            km_enqueue_iteration(P, 0ull, st);
+            cudaMemcpyAsync(&h, flags, sizeof(KmFlags), cudaMemcpyDeviceToHost, st);
+            err = cudaStreamSynchronize(st);
+            if (err != cudaSuccess) { set_error("kmeans lloyd: %s", cudaGetErrorString(err)); return -1; }
+            if (h.done) break;
+        }
+    }
+    // rerun the E-step with the final centres unless the run converged strictly (L741-753)
     const int nparts = (d + 511) / 512;
     const size_t bucket_smem = (size_t)n * 4 + (size_t)(k + 1) * 4;
-    bool strict = false;
-    int it = 0;
-    KmFlags h;
-    for (it = 0; it < max_iter; ++it) {
-        cudaMemsetAsync(&flags->n_changed, 0, sizeof(int), st);
-        km_center_norm_kernel<<<(k + 7) / 8, 256, 0, st>>>(cur, k, d, csq);
-        km_assign_kernel<<<(n + 31) / 32, 128, 0, st>>>(Xc, cur, csq, n, d, k, it == 0 ? nullptr : labels_old, labels, flags);
-        km_bucket_kernel<<<1, 1024, bucket_smem, st>>>(labels, n, k, offsets, members, flags);
-        km_segment_mean_kernel<<<dim3(nparts, k), 128, 0, st>>>(Xc, offsets, members, d, 0, nxt, cur, shift);
-        km_converge_kernel<<<1, 32, 0, st>>>(shift, k, nparts, flags);
-        cudaMemcpyAsync(labels_old, labels, (size_t)n * 4, cudaMemcpyDeviceToDevice, st);
-        cudaMemcpyAsync(&h, flags, sizeof(KmFlags), cudaMemcpyDeviceToHost, st);
-        err = cudaStreamSynchronize(st);
-        if (err != cudaSuccess) { set_error("kmeans lloyd: %s", cudaGetErrorString(err)); return -1; }
-        if (h.n_empty > 0) { set_error("kmeans: %d empty cluster(s) at iteration %d; sklearn's _relocate_empty_clusters_dense is not implemented", h.n_empty, it); return -2; }
-        float* t = cur; cur = nxt; nxt = t;                    // centers, centers_new = centers_new, centers
-        if (it > 0 && h.n_changed == 0) { strict = true; ++it; break; }
-        if (h.tol_ok) { ++it; break; }
-    }
-    if (!strict) {                                                 // rerun the E-step with the final centres (L741-753)
-        km_center_norm_kernel<<<(k + 7) / 8, 256, 0, st>>>(cur, k, d, csq);
-        km_assign_kernel<<<(n + 31) / 32, 128, 0, st>>>(Xc, cur, csq, n, d, k, nullptr, labels, flags);
-    }
-    if (n_iter_host) *n_iter_host = it > max_iter ? max_iter : it;
+    km_center_norm_kernel<<<(k + 7) / 8, 256, 0, st>>>(P.cA, P.cB, flags, 1, k, d, P.csq);
+    km_assign_kernel<<<(n + 31) / 32, 128, 0, st>>>(Xc, P.cA, P.cB, P.csq, n, d, k, nullptr, P.labels, flags, 1);
     // ---- cluster features: per-label mean of the RAW features (kmean_features.py:99-105)
-    km_bucket_kernel<<<1, 1024, bucket_smem, st>>>(labels, n, k, offsets, members, flags);
-    km_segment_mean_kernel<<<dim3(nparts, k), 128, 0, st>>>(features, offsets, members, d, 1, cluster_means, nullptr, nullptr);
+    km_bucket_kernel<<<1, 1024, bucket_smem, st>>>(P.labels, n, k, P.offsets, P.members, flags);
+    km_segment_mean_kernel<<<dim3(nparts, k), 128, 0, st>>>(features, P.offsets, P.members, d, 1, cluster_means, nullptr, nullptr, nullptr, flags, nullptr, nullptr, nullptr);
+    cudaMemcpyAsync(labels, P.labels, (size_t)n * 4, cudaMemcpyDeviceToDevice, st);
+    if (n_iter_dev) cudaMemcpyAsync(n_iter_dev, P.n_iter, 4, cudaMemcpyDeviceToDevice, st);
     err = cudaGetLastError();
     if (err != cudaSuccess) { set_error("kmeans: %s", cudaGetErrorString(err)); return -1; }
     return 0;

@@ -7,6 +7,9 @@
 `random_state`; `.fit(X)`; `.labels_`, `.n_iter_`) and adds `.cluster_features_` (the per-label means the script computes
 next).  All arithmetic runs in `sq_kmeans_fit` (csrc/kmeans.cu); only the MT19937 stream — which does not depend on the
 data — is drawn on the host with numpy's `RandomState`, exactly as `sklearn.utils.check_random_state(0)` would.
+Empty clusters are relocated like sklearn does; any `n_clusters` < 2981 works (2 + int(ln k) local seeding trials <= 10);
+a slide may hold up to ~40 000 tiles (the reference's `max_patch_number` default is 4000).  The C call only enqueues work
+(the Lloyd loop is a device-controlled CUDA-graph while node); this wrapper synchronises when it copies the results to the host.
 There is no CPU fallback.
 """
 import ctypes as C
@@ -30,7 +33,9 @@ class KMeans:
         self.device = torch.device(device)
         self._ws = None
 
-    def fit(self, X, y=None, sample_weight=None):
+    def fit(self, X, y=None, sample_weight=None, _init_rows=None):
+        """`_init_rows` (tests): int array [n_clusters] of rows of X used as initial centres instead of k-means++ — sklearn's
+        `init=X[rows], n_init=1`; duplicate rows produce empty clusters and exercise the relocation step."""
         if sample_weight is not None:
             raise NotImplementedError("sample_weight is not used by the reference")
         _lib.require_device()
@@ -44,6 +49,8 @@ class KMeans:
         if n < k:
             raise ValueError(f"n_samples={n} should be >= n_clusters={k}.")          # sklearn's message
         trials = 2 + int(math.log(k))
+        if trials > 10:
+            raise NotImplementedError("n_clusters >= 2981 (more than 10 local seeding trials) is not supported")
         # sklearn: random_state.choice(n, p=sample_weight / sample_weight.sum()), then uniform(size=trials) per new centre
         rs = np.random.RandomState(self.random_state)
         w = np.ones(n, dtype=np.float32)
@@ -56,15 +63,21 @@ class KMeans:
         labels = torch.empty(n, dtype=torch.int32, device=X.device)
         means = torch.empty(k, d, dtype=torch.float32, device=X.device)
         chosen = torch.empty(k, dtype=torch.int32, device=X.device)
-        n_iter = C.c_int(0)
-        _lib.check(L.sq_kmeans_fit(_lib.ptr(X), n, d, k, trials, first, _lib.ptr(uniforms), self.max_iter, self.tol,
-                                   _lib.ptr(labels), _lib.ptr(means), _lib.ptr(chosen), C.byref(n_iter), _lib.ptr(self._ws),
-                                   self._ws.numel(), _lib.stream_ptr()))
+        n_iter = torch.zeros(1, dtype=torch.int32, device=X.device)
+        init = None
+        if _init_rows is not None:
+            init = torch.as_tensor(np.asarray(_init_rows), dtype=torch.int32).to(X.device)
+            if init.numel() != k or int(init.min()) < 0 or int(init.max()) >= n:
+                raise ValueError("_init_rows must hold n_clusters valid row indices")
+        with _lib.on_device(X):
+            _lib.check(L.sq_kmeans_fit(_lib.ptr(X), n, d, k, trials, first, _lib.ptr(uniforms), _lib.ptr(init), self.max_iter, self.tol,
+                                       _lib.ptr(labels), _lib.ptr(means), _lib.ptr(chosen), _lib.ptr(n_iter), _lib.ptr(self._ws),
+                                       self._ws.numel(), _lib.stream_ptr(X)))
         self.labels_device_, self.cluster_features_device_ = labels, means
         self.labels_ = labels.cpu().numpy()
         self.cluster_features_ = means.cpu().numpy()
         self.seed_rows_ = chosen.cpu().numpy()
-        self.n_iter_ = n_iter.value
+        self.n_iter_ = int(n_iter.item())
         return self
 
 

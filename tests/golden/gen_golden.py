@@ -126,6 +126,52 @@ def gen_kmeans():
         out[f"{tag}_means_head"] = feats[:, :8].copy()
         print("kmeans golden", tag, n, d, "iters", km.n_iter_, "sizes", np.bincount(labels).min(), np.bincount(labels).max())
     np.savez_compressed(os.path.join(HERE, "kmeans_golden.npz"), **out)
+    gen_kmeans_extra()
+
+
+# (tag, slide id, n, d, modes, k): other --num_clusters values (kmean_features.py:19) = other local-trial counts 2 + int(ln k)
+KMEANS_K_CASES = [("k20", 11, 1500, 256, 40, 20), ("k50", 12, 2000, 128, 80, 50), ("k200", 13, 3000, 256, 260, 200), ("k400", 14, 4096, 128, 500, 400)]
+# (tag, slide id, n, d, modes, k, duplicated initial centres): sklearn's `init=X[rows], n_init=1` with duplicate rows ->
+# empty clusters in the first iteration(s) -> _relocate_empty_clusters_dense
+KMEANS_RELOC_CASES = [("r1", 21, 1500, 64, 150, 100, 1), ("r3", 22, 2000, 128, 150, 100, 3), ("r7", 23, 1237, 256, 150, 100, 7),
+                      ("r2", 24, 3000, 64, 150, 50, 2), ("r12", 25, 2500, 128, 150, 200, 12)]
+
+
+def kmeans_reloc_rows(sid, n, k, ndup):
+    rs = np.random.RandomState(sid)
+    rows = rs.choice(n, k, replace=False)
+    for j in rs.choice(k, ndup, replace=False):
+        rows[j] = rows[(j + 1 + rs.randint(k - 1)) % k]
+    return rows.astype(np.int32)
+
+
+def gen_kmeans_extra():
+    import warnings
+    from sklearn.cluster import KMeans
+    from oracle import kmeans_oracle as K
+    out = {}
+    for tag, sid, n, d, modes, k in KMEANS_K_CASES:
+        X = K.make_slide_features(sid, n=n, d=d, modes=modes)
+        km = KMeans(n_clusters=k, random_state=0).fit(X)
+        lo, idx, it = K.fit_labels(X, k=k)
+        assert np.array_equal(lo, km.labels_) and it == km.n_iter_, f"oracle differs from sklearn on {tag}"
+        assert np.array_equal(K.fit_labels(X, k=k, pot_mode="emulated")[0], km.labels_), f"emulated BLAS order differs on {tag}"
+        out[f"{tag}_labels"] = km.labels_.astype(np.int16); out[f"{tag}_n_iter"] = np.array(km.n_iter_); out[f"{tag}_seed_rows"] = idx.astype(np.int32)
+        print("kmeans golden", tag, "k", k, "trials", K.N_LOCAL_TRIALS(k), "iters", km.n_iter_)
+    for tag, sid, n, d, modes, k, ndup in KMEANS_RELOC_CASES:
+        X = K.make_slide_features(sid, n=n, d=d, modes=modes)
+        rows = kmeans_reloc_rows(sid, n, k, ndup)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            km = KMeans(n_clusters=k, init=X[rows], n_init=1).fit(X)
+        Xc = np.array(X, dtype=np.float32, copy=True)
+        tol = np.float32(np.mean(np.var(Xc, axis=0)) * 1e-4)
+        Xc -= Xc.mean(axis=0)
+        lo, it = K.lloyd(Xc, Xc[rows].copy(), tol)
+        assert np.array_equal(lo, km.labels_) and it == km.n_iter_, f"oracle relocation differs from sklearn on {tag}"
+        out[f"{tag}_labels"] = km.labels_.astype(np.int16); out[f"{tag}_n_iter"] = np.array(km.n_iter_); out[f"{tag}_rows"] = rows
+        print("kmeans relocation golden", tag, "dups", ndup, "iters", km.n_iter_, "clusters used", len(np.unique(km.labels_)))
+    np.savez_compressed(os.path.join(HERE, "kmeans_extra_golden.npz"), **out)
 
 
 def gen_metrics():

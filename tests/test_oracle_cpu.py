@@ -1,5 +1,6 @@
 """CPU: the oracle restatements against the golden fixtures produced by the unmodified reference."""
 import os
+import sys
 
 import numpy as np
 import torch
@@ -79,6 +80,56 @@ def test_kmeans_blas_order_restatement_matches_numpy():
         got = np.array([K.blas_order_gemv_row(M[t], t, 6) for t in range(6)], np.float32)
         assert np.array_equal(ref, got), n
         assert (M[:1] @ w)[0] == K.blas_order_sdot(M[0]), n
+
+
+def test_kmeans_blas_order_other_row_counts():
+    """sgemv row grouping for every local-trial count 2 + int(ln k) can take (2 .. 10): groups of four (kind 0), a pair
+    (kind 1), a single row (kind 0 order)."""
+    from oracle import kmeans_oracle as K
+    rng = np.random.RandomState(1)
+    for T in range(2, 11):
+        for n in (1237, 4096, 4100, 5003):
+            M = (rng.rand(T, n) * 3).astype(np.float32)
+            ref = (M @ np.ones((n, 1), np.float32))[:, 0]
+            got = np.array([K.blas_order_gemv_row(M[t], t, T) for t in range(T)], np.float32)
+            assert np.array_equal(ref, got), (T, n)
+
+
+def test_kmeans_relocation_restatement_matches_sklearn():
+    """oracle.relocate_empty_clusters against scikit-learn's own _relocate_empty_clusters_dense, the numpy pairwise-sum
+    restatement the CUDA kernel follows, and a full duplicate-initialised fit against the golden."""
+    from sklearn.cluster._k_means_common import _relocate_empty_clusters_dense
+    from oracle import kmeans_oracle as K
+    rs = np.random.RandomState(3)
+    for n in (5, 8, 17, 100, 128, 129, 300, 1000, 1024, 2048, 2050):
+        a = rs.rand(n).astype(np.float32)
+        assert K.pairwise_sum_f32(a) == a.reshape(1, -1).sum(axis=1)[0], n
+    for trial in range(10):
+        n, d, k = 800, 48, 40
+        X = rs.randn(n, d).astype(np.float32); co = rs.randn(k, d).astype(np.float32)
+        labels = rs.randint(0, k - 1 - trial % 6, size=n).astype(np.int32)
+        w = np.bincount(labels, minlength=k).astype(np.float32)
+        cn = np.zeros((k, d), np.float32)
+        for i, l in enumerate(labels):
+            cn[l] += X[i]
+        a_cn, a_w, b_cn, b_w = cn.copy(), w.copy(), cn.copy(), w.copy()
+        _relocate_empty_clusters_dense(X, np.ones(n, np.float32), co, a_cn, a_w, labels)
+        K.relocate_empty_clusters(X, co, b_cn, b_w, labels)
+        assert np.array_equal(a_cn, b_cn) and np.array_equal(a_w, b_w), trial
+    sys.path.insert(0, GOLD)
+    from gen_golden import kmeans_reloc_rows
+    g = np.load(os.path.join(GOLD, "kmeans_extra_golden.npz"))
+    tag, sid, n, d, modes, k, ndup = "r3", 22, 2000, 128, 150, 100, 3
+    X = K.make_slide_features(sid, n=n, d=d, modes=modes)
+    rows = kmeans_reloc_rows(sid, n, k, ndup)
+    assert np.array_equal(rows, g[f"{tag}_rows"])
+    Xc = np.array(X, dtype=np.float32, copy=True)
+    tol = np.float32(np.mean(np.var(Xc, axis=0)) * 1e-4)
+    Xc -= Xc.mean(axis=0)
+    lab, it = K.lloyd(Xc, Xc[rows].copy(), tol)
+    assert np.array_equal(lab, g[f"{tag}_labels"]) and it == int(g[f"{tag}_n_iter"])
+    labels, _, it = K.fit_labels(K.make_slide_features(11, n=1500, d=256, modes=40), k=20)
+    assert np.array_equal(labels, g["k20_labels"]) and it == int(g["k20_n_iter"])
 
 
 def test_kmeans_oracle_matches_sklearn_golden_and_live():
