@@ -228,6 +228,17 @@ SQ_API size_t sq_vitl16_workspace_bytes(int batch);
 SQ_API int sq_vitl16_extract(const void* input, int input_kind, int batch, int depth, const void* packed_w, const float* packed_v,
                              float* features, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Image resize in front of UNI: `transforms.Resize(224)` of a PIL image (pre_processing/compute_features_hdf5.py:53-56,125-126)
+ * = Pillow's antialiased bilinear resample in 22-bit fixed point (libImaging/Resample.c), bit-identical on the GPU.
+ * sq_resize_ksize / sq_resize_coeffs are HOST helpers (no GPU): window bounds int32 [out, 2] = (first input index, count) and
+ * weights int32 [out, ksize] for one axis.  sq_resize_bilinear_u8: uint8 [n, Hin, Win, 3] -> uint8 [n, Hout, Wout, 3]; the tables
+ * are DEVICE copies of the helpers' output (NULL for an axis that keeps its size); tmp: n*Hin*Wout*3 bytes when both axes change. */
+SQ_API int sq_resize_ksize(int in_size, int out_size);
+SQ_API int sq_resize_coeffs(int in_size, int out_size, int* bounds_host, int* coeffs_host);
+SQ_API int sq_resize_bilinear_u8(const void* in, int n, int Hin, int Win, void* out, int Hout, int Wout, const int* xbounds,
+                                 const int* xcoeffs, int xksize, const int* ybounds, const int* ycoeffs, int yksize, void* tmp,
+                                 void* stream);
+
 /* ------------------------------------------------------------------ per-slide k-means reduction
  * Replaces `KMeans(n_clusters=100, random_state=0).fit(features)` and the per-label mean loop of
  * pre_processing/kmean_features.py:96-105 (the arithmetic is scikit-learn's: init='k-means++', n_init=1,

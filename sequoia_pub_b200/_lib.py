@@ -103,6 +103,10 @@ SIGNATURES = {
     "sq_vitl16_prepack": (c_int, [C.POINTER(c_void_p), c_int, c_void_p, c_void_p, c_void_p]),
     "sq_vitl16_workspace_bytes": (c_size_t, [c_int]),
     "sq_vitl16_extract": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "sq_resize_ksize": (c_int, [c_int, c_int]),
+    "sq_resize_coeffs": (c_int, [c_int, c_int, C.POINTER(c_int), C.POINTER(c_int)]),
+    "sq_resize_bilinear_u8": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                                      c_int, c_void_p, c_void_p]),
     "sq_kmeans_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "sq_kmeans_fit": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p,
                               c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -27,7 +27,10 @@ def select_keys(keys, max_patch_number=4000, rng=_random):
 
 
 class SlideExtractor:
-    """Runs `model.extract_uint8` over all tiles of a slide.  H2D copies (pinned staging, copy stream) overlap compute, and
+    """Runs the model's uint8 extractor over all tiles of a slide; the model is either extractor of the reference script
+    (`--feat_type resnet`: `resnet.ResNet`, 2048 features; `--feat_type uni`: `uni.VisionTransformer`, 1024 features, with the
+    script's `Resize(224)` of the 256-px tiles done on the GPU) - anything exposing `feature_dim`, `new_lane_workspace` and
+    `extract_tiles_into`.  H2D copies (pinned staging, copy stream) overlap compute, and
     consecutive batches alternate between two compute lanes (stream + extractor workspace each), so the persistent
     convolution kernels of one batch fill the SMs the other leaves idle in partial waves and launch gaps.  There are twice as
     many device tile buffers as lanes: the tiles of a lane's NEXT batch are already on the device when its current batch
@@ -49,14 +52,18 @@ class SlideExtractor:
         self.copied = [torch.cuda.Event() for _ in range(n)]
         self.consumed = [torch.cuda.Event() for _ in range(n)]
         self.workspaces = [None] * self.LANES
+        self._ws_hw = None
+        self.feature_dim = int(model.feature_dim)
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
     def _workspace(self, slot, h, w):
-        from . import _lib
-        need = _lib.lib().sq_resnet50_workspace_bytes(self.bs, h, w)
-        if self.workspaces[slot] is None or self.workspaces[slot].numel() < need:
-            self.workspaces[slot] = torch.empty(need, dtype=torch.uint8, device=self.device)
+        # the model sizes its own lane state (ResNet: conv workspace; UNI: ViT workspace + the Resize(224) buffers)
+        if self.workspaces[slot] is None or self._ws_hw != (h, w):
+            self.workspaces = [None] * self.LANES
+            self._ws_hw = (h, w)
+        if self.workspaces[slot] is None:
+            self.workspaces[slot] = self.model.new_lane_workspace(self.bs, h, w, self.device)
         return self.workspaces[slot]
 
     def __call__(self, tiles):
@@ -67,10 +74,10 @@ class SlideExtractor:
             raise ValueError("tiles must be uint8 [n, H, W, 3]")
         n = tiles.shape[0]
         if n == 0:
-            return np.zeros((0, 2048), dtype=np.float32)
+            return np.zeros((0, self.feature_dim), dtype=np.float32)
         pinned = tiles.is_pinned()
         main = torch.cuda.current_stream(self.device)
-        out = torch.empty(n, 2048, dtype=torch.float32, device=self.device)
+        out = torch.empty(n, self.feature_dim, dtype=torch.float32, device=self.device)
         self.model._prepack()
         for s in self.lanes:
             s.wait_stream(main)
@@ -94,7 +101,7 @@ class SlideExtractor:
             with torch.cuda.stream(lane):
                 lane.wait_event(self.copied[slot])
                 buf = self.dev_buf[slot][: hi - lo]
-                self.model._run(buf, 0, hi - lo, buf.shape[1], buf.shape[2], out[lo:hi], workspace=self._workspace(li, buf.shape[1], buf.shape[2]))
+                self.model.extract_tiles_into(buf, out[lo:hi], self._workspace(li, buf.shape[1], buf.shape[2]))
                 self.consumed[slot].record(lane)
             self.h2d_bytes += (hi - lo) * tiles[0].numel()
         for s in self.lanes:

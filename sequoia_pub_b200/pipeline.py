@@ -59,6 +59,12 @@ def reduce_features(features, num_clusters=100):
 
 def extract_slide(model, patch_file, feature_file, feat_type="resnet", max_patch_number=4000, rng=_random, batch_size=64,
                   extractor=None, prefer_h5py=True):
+    """`feat_type` is the script's --feat_type ('resnet' | 'uni', :31) and must name the model that is passed: the dataset is
+    written as "{feat_type}_features" and read back under that name by kmean_features.py / read_data.py."""
+    if feat_type not in ("resnet", "uni"):
+        raise ValueError(f"feat_type must be 'resnet' or 'uni', got {feat_type!r}")
+    if getattr(model, "feat_type", None) != feat_type:
+        raise ValueError(f"feat_type={feat_type!r} but the model is a {getattr(model, 'feat_type', type(model).__name__)!r} extractor")
     with hdf5.open_file(patch_file, "r", prefer_h5py) as f:
         keys = select_keys(list(f.keys()), max_patch_number, rng)          # :111-113
         tiles = read_tiles(f, keys)                                        # :117

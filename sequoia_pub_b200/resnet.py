@@ -41,6 +41,9 @@ class Bottleneck(nn.Module):
 class ResNet(nn.Module):
     """ResNet-50 whose forward passes run in the sequoia_b200 CUDA library."""
 
+    feat_type = "resnet"         # dataset name prefix the extraction script writes (compute_features_hdf5.py:134-135)
+    feature_dim = 2048
+
     def __init__(self, block=Bottleneck, layers=(3, 4, 6, 3), num_classes=1000):
         super().__init__()
         if block is not Bottleneck or tuple(layers) != (3, 4, 6, 3):
@@ -161,6 +164,14 @@ class ResNet(nn.Module):
         for s, _ in self._lanes:
             main.wait_stream(s)
         return out
+
+    # ------------------------------------------------------------------ hooks of the slide extractor (extract.SlideExtractor)
+    def new_lane_workspace(self, batch, H, W, device):
+        return torch.empty(_lib.lib().sq_resnet50_workspace_bytes(batch, H, W), dtype=torch.uint8, device=device)
+
+    def extract_tiles_into(self, tiles, out, workspace):
+        """uint8 [n,H,W,3] device tiles -> out [n,2048] on the current stream, using a lane's workspace."""
+        self._run(tiles, 0, tiles.shape[0], tiles.shape[1], tiles.shape[2], out, workspace=workspace)
 
     # ------------------------------------------------------------------ reference surface
     @torch.no_grad()

@@ -64,6 +64,9 @@ class _PatchEmbed(_Container):
 class VisionTransformer(nn.Module):
     """ViT-L/16 at 224 px, token pooling, no classification head (the configuration UNI uses)."""
 
+    feat_type = "uni"            # dataset name prefix the extraction script writes (compute_features_hdf5.py:134-135)
+    feature_dim = 1024
+
     def __init__(self, img_size=224, patch_size=16, embed_dim=1024, depth=24, num_heads=16, mlp_ratio=4.0, init_values=1e-5,
                  num_classes=0, dynamic_img_size=True, **unused):
         super().__init__()
@@ -78,6 +81,7 @@ class VisionTransformer(nn.Module):
         self._packed = None
         self._ws = None
         self._lanes = None           # [(stream, workspace)] for extract_many
+        self._lanes_key = None
 
     def _tensors(self):
         t = [self.cls_token, self.pos_embed, self.patch_embed.proj.weight, self.patch_embed.proj.bias]
@@ -130,16 +134,17 @@ class VisionTransformer(nn.Module):
     def extract_many(self, patches, out=None, batch_size=64, lanes=2):
         """All tiles of a slide resident on the device: uint8 [n,224,224,3] -> float32 [n,1024]; batches alternate between
         `lanes` CUDA streams with their own workspaces (same scheme as ResNet.extract_many)."""
-        if patches.dim() != 4 or tuple(patches.shape[1:]) != (224, 224, 3) or patches.dtype != torch.uint8 or not patches.is_cuda:
-            raise ValueError("extract_many expects a CUDA uint8 [n,224,224,3] tensor")
+        if patches.dim() != 4 or patches.shape[3] != 3 or patches.dtype != torch.uint8 or not patches.is_cuda:
+            raise ValueError("extract_many expects a CUDA uint8 [n,H,W,3] tensor")
         patches = patches.contiguous()
-        n = patches.shape[0]
+        n, H, W = patches.shape[0], patches.shape[1], patches.shape[2]
         if out is None:
             out = torch.empty(n, 1024, dtype=torch.float32, device=patches.device)
-        need = _lib.lib().sq_vitl16_workspace_bytes(min(batch_size, max(n, 1)))
-        if self._lanes is None or len(self._lanes) != lanes or self._lanes[0][1].numel() < need or self._lanes[0][1].device != patches.device:
-            self._lanes = [(torch.cuda.Stream(device=patches.device), torch.empty(need, dtype=torch.uint8, device=patches.device))
-                           for _ in range(lanes)]
+        bs = min(batch_size, max(n, 1))
+        key = (lanes, bs, H, W, str(patches.device))
+        if self._lanes is None or self._lanes_key != key:
+            self._lanes = [(torch.cuda.Stream(device=patches.device), self.new_lane_workspace(bs, H, W, patches.device)) for _ in range(lanes)]
+            self._lanes_key = key
         self._prepack()
         main = torch.cuda.current_stream(patches.device)
         for s, _ in self._lanes:
@@ -147,10 +152,31 @@ class VisionTransformer(nn.Module):
         for i, b in enumerate(range(0, n, batch_size)):
             s, ws = self._lanes[i % lanes]
             with torch.cuda.stream(s):
-                self._run(patches[b:b + batch_size], 0, min(batch_size, n - b), out[b:b + batch_size], workspace=ws)
+                self.extract_tiles_into(patches[b:b + batch_size], out[b:b + batch_size], ws)
         for s, _ in self._lanes:
             main.wait_stream(s)
         return out
+
+    # ------------------------------------------------------------------ hooks of the slide extractor (extract.SlideExtractor)
+    def new_lane_workspace(self, batch, H, W, device):
+        """Extractor workspace plus, for tiles that are not 224 px, the buffers of the `Resize(224)` step (:54)."""
+        from . import preproc
+        ws = {"ws": torch.empty(_lib.lib().sq_vitl16_workspace_bytes(batch), dtype=torch.uint8, device=device)}
+        if (H, W) != (224, 224):
+            if preproc.resize_size(H, W, 224) != (224, 224):
+                raise NotImplementedError("UNI needs square tiles (Resize(224) of a non-square tile is not 224x224)")
+            ws["resized"] = torch.empty(batch, 224, 224, 3, dtype=torch.uint8, device=device)
+            ws["tmp"] = torch.empty(max(preproc.resize_scratch_bytes(batch, H, W, 224), 1), dtype=torch.uint8, device=device)
+        return ws
+
+    def extract_tiles_into(self, tiles, out, workspace):
+        """uint8 [n,H,W,3] device tiles -> out [n,1024] on the current stream: Resize(224) (bit-identical to Pillow) when the tiles
+        are not 224 px, then ToTensor / Normalize fused into the patch-embedding kernel."""
+        n = tiles.shape[0]
+        if tuple(tiles.shape[1:3]) != (224, 224):
+            from . import preproc
+            tiles = preproc.resize_tiles(tiles, 224, out=workspace["resized"][:n], tmp=workspace["tmp"])
+        self._run(tiles, 0, n, out, workspace=workspace["ws"])
 
     @torch.no_grad()
     def forward(self, x):
@@ -161,10 +187,17 @@ class VisionTransformer(nn.Module):
 
     @torch.no_grad()
     def extract_uint8(self, patches, out=None):
-        """patches: uint8 [B,224,224,3] raw RGB tiles -> float32 [B,1024] (ToTensor + Normalize fused)."""
-        if patches.dim() != 4 or tuple(patches.shape[1:]) != (224, 224, 3) or patches.dtype != torch.uint8:
-            raise ValueError("expected uint8 [B,224,224,3]")
-        return self._run(patches.contiguous(), 0, patches.shape[0], out)
+        """patches: uint8 [B,H,W,3] raw RGB tiles -> float32 [B,1024].  224-px tiles go straight in (ToTensor + Normalize fused);
+        other square sizes (the pipeline's 256-px tiles) pass through the Pillow-exact `Resize(224)` first (:54)."""
+        if patches.dim() != 4 or patches.shape[3] != 3 or patches.dtype != torch.uint8:
+            raise ValueError("expected uint8 [B,H,W,3]")
+        patches = patches.contiguous()
+        if tuple(patches.shape[1:3]) != (224, 224):
+            from . import preproc
+            if preproc.resize_size(patches.shape[1], patches.shape[2], 224) != (224, 224):
+                raise NotImplementedError("UNI needs square tiles (Resize(224) of a non-square tile is not 224x224)")
+            patches = preproc.resize_tiles(patches, 224)
+        return self._run(patches, 0, patches.shape[0], out)
 
 
 def create_model(name, **kwargs):

@@ -127,3 +127,25 @@ def test_read_tiles_builtin_codec_and_h5py_like_objects(tmp_path):
     ff = FakeFile({k: FakeDataset(v) for k, v in tiles.items()})
     got2 = pipeline.read_tiles(ff, keys)
     assert isinstance(got2, np.ndarray) and np.array_equal(got2, got.numpy())
+
+
+def test_resize_coefficient_tables_match_the_pillow_restatement():
+    """Host half of the GPU resize: the library's precompute_coeffs restatement (no GPU needed) vs oracle/resize_oracle.py."""
+    import numpy as np
+    from oracle import resize_oracle as R
+    from sequoia_pub_b200 import preproc
+    for a, b in ((256, 224), (300, 224), (512, 224), (200, 224), (224, 224), (257, 224), (1000, 224)):
+        bo, ko = R.coeffs(a, b)
+        bl, kl = preproc.coeff_tables(a, b)
+        assert np.array_equal(bo, bl) and np.array_equal(ko, kl), (a, b)
+    assert preproc.resize_size(256, 320) == (224, 280) and preproc.resize_size(512, 256) == (448, 224)
+
+
+def test_extract_slide_refuses_a_mismatched_feat_type():
+    import pytest
+    from sequoia_pub_b200 import pipeline
+    from sequoia_pub_b200.resnet import resnet50
+    with pytest.raises(ValueError):
+        pipeline.extract_slide(resnet50(), "nope.hdf5", "out.h5", feat_type="uni")
+    with pytest.raises(ValueError):
+        pipeline.extract_slide(resnet50(), "nope.hdf5", "out.h5", feat_type="dino")

@@ -167,3 +167,19 @@ def test_uni_oracle_structure_matches_torchvision_vit_l_16():
         got = U.forward(sd, x).numpy()
     assert got.shape == (2, 1024)
     assert _rel(got, want) < 1e-5
+
+
+def test_resize_oracle_matches_pillow():
+    """oracle/resize_oracle.py (Resample.c restated) against Pillow through the reference's own transform object
+    (pre_processing/compute_features_hdf5.py:53-56: transforms.Resize(224) on Image.fromarray(tile).convert("RGB"))."""
+    pytest = __import__("pytest")
+    Image = pytest.importorskip("PIL.Image")
+    from torchvision import transforms
+    from oracle import resize_oracle as R
+    rs = np.random.RandomState(0)
+    tf = transforms.Resize(224)
+    for hw in ((256, 256), (300, 300), (224, 224), (512, 512), (256, 320), (250, 250), (200, 200)):
+        for kind in range(2):
+            a = (rs.rand(*hw, 3) * 255).astype(np.uint8) if kind == 0 else np.clip(np.cumsum(rs.randn(*hw, 3), axis=1) * 8 + 128, 0, 255).astype(np.uint8)
+            ref = np.asarray(tf(Image.fromarray(a).convert("RGB")))
+            assert np.array_equal(R.resize(a, 224), ref), hw
