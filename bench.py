@@ -149,6 +149,59 @@ def cpu_kmeans_rate(slides=2):
     return 1.0 / dt, os.cpu_count(), f"{slides} slides through sklearn.cluster.KMeans + numpy means"
 
 
+def headline_config(world):
+    """`config` of the JSON line; identical for both arms (the reference arm times a bounded sample of this workload)."""
+    return {"workload": WORKLOAD, "l2": "inputs (805 MB/slide) larger than L2; no flush needed",
+            "parallelism": f"slide-sharded x{world}, no collective; batches of 64 alternate between 2 CUDA streams per GPU"}
+
+
+def cpu_resnet_batch1_rate(n_tiles=16):
+    """The reference's actual loop (compute_features_hdf5.py:116-123): one tile per forward, feature copied to the host each time."""
+    import torch
+    from oracle import resnet50_oracle as O
+    torch.set_num_threads(os.cpu_count())
+    sd = O.make_state_dict(0)
+    patches = O.make_patches(2, n_tiles)
+    with torch.no_grad():
+        O.forward_extract(sd, O.preprocess(patches[:1]))
+        t0 = time.perf_counter()
+        for i in range(n_tiles):
+            O.forward_extract(sd, O.preprocess(patches[i:i + 1]))[0].numpy()
+        dt = time.perf_counter() - t0
+    return n_tiles / dt
+
+
+def cpu_vis_forward_rate(reps=5):
+    """BASELINE configs[0]: ViS forward of one slide, 100x2048 -> 1000 genes, CPU."""
+    import torch
+    from oracle import vis_oracle as V
+    torch.set_num_threads(os.cpu_count())
+    sd = V.make_state_dict(0, 1000)
+    x, _ = V.make_inputs(0, 1, 1000)
+    with torch.no_grad():
+        V.forward(sd, x)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            V.forward(sd, x)
+        dt = (time.perf_counter() - t0) / reps
+    return 1.0 / dt
+
+
+def cpu_uni_rate(batch=8):
+    """UNI ViT-L/16 restatement (oracle/uni_oracle.py; parity unpinned), batch 8, CPU."""
+    import torch
+    from oracle import uni_oracle as U
+    torch.set_num_threads(os.cpu_count())
+    sd = U.make_state_dict(0)
+    x = U.preprocess(U.make_patches(0, batch))
+    with torch.no_grad():
+        U.forward(sd, x[:1])
+        t0 = time.perf_counter()
+        U.forward(sd, x)
+        dt = time.perf_counter() - t0
+    return batch / dt
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -163,22 +216,26 @@ def run_reference(args):
     v = sum(rates) / len(rates)
     vr, vc, vs = cpu_vis_rate(1)
     kr, kc, ks = cpu_kmeans_rate(1)
+    extra = {"resnet_batch1_loop_patches_s": cpu_resnet_batch1_rate(16), "vis_forward_config1_slides_s": cpu_vis_forward_rate(5),
+             "uni_vitl16_batch8_patches_s": cpu_uni_rate(8),
+             "note": "BASELINE.md 4 rows C3 (batch-1 loop of compute_features_hdf5.py:116-123), C1, C5 (restatement, parity unpinned); oracle ports, all host threads"}
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "patches/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample": f"{sample} patches per step"},
+            "config": headline_config(args.gpus),
             "cpu_baseline": {"value": v, "unit": "patches/s", "cores": cores, "kind": "port",
-                             "sample": f"{sample} patches per step, {args.steps} steps, oracle/resnet50_oracle.py (torch CPU)"},
+                             "sample": f"{sample} patches (one batch of 64) per step, {args.steps} steps, oracle/resnet50_oracle.py (torch CPU fp32, pinned to the reference class by tests/golden)"},
             "e2e": {"value": v, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "vis_train": {"value": vr, "unit": "slides/s", "cpu_baseline": {"value": vr, "unit": "slides/s", "cores": vc, "kind": "port", "sample": vs}},
             "kmeans": {"value": kr, "unit": "slides/s", "cpu_baseline": {"value": kr, "unit": "slides/s", "cores": kc, "kind": "reference", "sample": ks}},
+            "cpu_baselines_extra": extra,
             "gpu_launches": 0}
     emit(line)
 
 
 def ncu_traffic(key):
-    """DRAM bytes per launch of gemm_tc_kernel from the committed ncu capture (tools/gpu_traffic.sh -> profiles/r01_traffic.json)."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (tools/gpu_prof_r02.sh -> profiles/r02_traffic.json)."""
+    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
     try:
         return json.load(open(p))[key]["traffic_bytes_per_launch"]
     except Exception:
@@ -315,97 +372,134 @@ def bench_vit(args, dev, rank, world, timed):
     return out
 
 
-UNI_BATCH, UNI_PATCHES = 64, 1024
+UNI_BATCH, UNI_PATCHES = 64, 8192
 UNI_FLOP_PER_PATCH = 123.107e9
-UNI_WORKLOAD = "UNI ViT-L/16 extraction: 1024 synthetic 224x224x3 uint8 patches per rank per step, batch 64 (BASELINE configs[3] shape, slide-sharded)"
+UNI_WORKLOAD = "UNI ViT-L/16 extraction: 1 slide = 8192 synthetic 224x224x3 uint8 patches per rank per step, batch 64, whole slides sharded over the ranks (BASELINE configs[3])"
 
 
 def bench_uni(args, dev, rank, world, timed, pk):
-    """patches/s of the UNI ViT-L/16 extractor (parity unpinned: no timm / UNI weights offline; see oracle/uni_oracle.py)."""
+    """patches/s of the UNI ViT-L/16 extractor (parity unpinned: no timm / UNI weights offline; see oracle/uni_oracle.py).
+    One step = one 8192-patch slide per rank; e2e goes through the product call (SlideExtractor over pinned host tiles)."""
     import torch
     from oracle import uni_oracle as U
     from sequoia_pub_b200 import _lib
+    from sequoia_pub_b200.extract import SlideExtractor
     from sequoia_pub_b200.uni import VisionTransformer
     L = _lib.lib()
     m = VisionTransformer().eval()
     m.load_state_dict(U.make_state_dict(0))
     m = m.to(dev)
     g = torch.Generator(device=dev).manual_seed(2000 + rank)
-    tiles = torch.randint(0, 256, (UNI_PATCHES, 224, 224, 3), generator=g, dtype=torch.uint8, device=dev)     # 154 MB > L2
+    tiles = torch.randint(0, 256, (UNI_PATCHES, 224, 224, 3), generator=g, dtype=torch.uint8, device=dev)     # 1.23 GB > L2
     host = torch.empty(tiles.shape, dtype=torch.uint8).pin_memory()
     host.copy_(tiles)
     feats = torch.empty(UNI_PATCHES, 1024, dtype=torch.float32, device=dev)
-    stage = torch.empty(UNI_BATCH, 224, 224, 3, dtype=torch.uint8, device=dev)
-    out_h = torch.empty(UNI_PATCHES, 1024, dtype=torch.float32).pin_memory()
 
     def step_dev():
         m.extract_many(tiles, out=feats, batch_size=UNI_BATCH, lanes=2)
 
     def step_serial():
-        for b in range(0, UNI_PATCHES, UNI_BATCH):
+        for b in range(0, 1024, UNI_BATCH):
             m.extract_uint8(tiles[b:b + UNI_BATCH], out=feats[b:b + UNI_BATCH])
 
-    def step_e2e():
-        for b in range(0, UNI_PATCHES, UNI_BATCH):
-            stage.copy_(host[b:b + UNI_BATCH], non_blocking=True)
-            m.extract_uint8(stage, out=feats[b:b + UNI_BATCH])
-        out_h.copy_(feats, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-
-    for _ in range(2):
-        step_dev()
-    steps = 3
+    step_dev()
+    steps = 2
     ms = timed(step_dev, steps) / steps
-    step_e2e()
-    e2e_ms = timed(step_e2e, steps) / steps
+    ex = SlideExtractor(m, UNI_BATCH, (224, 224), dev)
+    ex(host)
+    ex.h2d_bytes = ex.d2h_bytes = 0
+    e2e_ms = timed(lambda: ex(host), steps) / steps
     out = {"value": world * UNI_PATCHES / (ms * 1e-3), "unit": "patches/s", "ms_per_step": ms, "dtype": "bf16",
            "config": {"workload": UNI_WORKLOAD, "parity": "unpinned (restatement of timm's forward)"},
            "e2e": {"value": world * UNI_PATCHES / (e2e_ms * 1e-3), "unit": "patches/s", "ms_per_step": e2e_ms,
-                   "h2d_bytes_per_step": host.numel(), "d2h_bytes_per_step": out_h.numel() * 4}}
+                   "h2d_bytes_per_step": ex.h2d_bytes // steps, "d2h_bytes_per_step": ex.d2h_bytes // steps, "api": "extract.SlideExtractor"}}
     if rank == 0:
         step_serial()
-        tms, n, fl = gemm_timing(L, _lib, step_serial)       # one stream: kernel durations without inter-batch overlap
-        ach = UNI_FLOP_PER_PATCH * UNI_PATCHES / (tms * 1e-3) / 1e12
+        tms, n, fl = gemm_timing(L, _lib, step_serial)       # 1024 patches on one stream: kernel durations without inter-batch overlap
+        ach = UNI_FLOP_PER_PATCH * 1024 / (tms * 1e-3) / 1e12
         out["roofline"] = {"bound": "tensor", "kernel": "gemm_tc_kernel (qkv / proj / fc1 / fc2 / patch-embed GEMMs)", "achieved": ach,
                            "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_sustained"], "traffic": None, "launches": n,
-                           "timing_note": "kernel durations measured on one stream (no inter-batch overlap)"}
-    del m, tiles, host, feats
+                           "step_frac": out["value"] / world * UNI_FLOP_PER_PATCH / 1e12 / pk["bf16_sustained"],
+                           "timing_note": "kernel durations measured on one stream (no inter-batch overlap); step_frac = whole-step patches/s x FLOP/patch / peak"}
+    del m, tiles, host, feats, ex
     torch.cuda.empty_cache()
     return out
 
 
 def bench_kmeans(args, dev, rank, world, pk):
-    """slides/s of the per-slide k-means reduction (independent slides per rank, no collective)."""
+    """slides/s of the per-slide k-means reduction (independent slides per rank, no collective).  The C call only enqueues
+    (device-controlled Lloyd loop), so the fit is timed with CUDA events; the seeding / per-iteration split comes from a second
+    timing with max_iter = 1."""
     import torch
     from oracle import kmeans_oracle as K
     from sequoia_pub_b200.kmeans import KMeans
     Xh = torch.from_numpy(K.make_slide_features(rank, n=KM_N, d=KM_D)).pin_memory()
     Xd = Xh.to(dev)
     km = KMeans(n_clusters=KM_K, random_state=0, device=dev)
-    km.fit(Xd)
-    torch.cuda.synchronize()
+    km1 = KMeans(n_clusters=KM_K, random_state=0, device=dev, max_iter=1)
+    km.fit(Xd); km1.fit(Xd)
     reps = 3
-    t0 = time.perf_counter()
-    for _ in range(reps):
-        km.fit(Xd)                         # device-resident features in; labels + cluster features read back on the host
-    torch.cuda.synchronize()
-    ms = (time.perf_counter() - t0) / reps * 1e3
-    t0 = time.perf_counter()
-    for _ in range(reps):
-        km.fit(Xh)                         # host features in (H2D inside)
-    torch.cuda.synchronize()
-    e2e_ms = (time.perf_counter() - t0) / reps * 1e3
-    return {"value": world * 1e3 / ms, "unit": "slides/s", "ms_per_slide": ms, "lloyd_iterations": km.n_iter_,
-            "config": {"workload": KM_WORKLOAD, "timing": "host wall clock around fit() (the call synchronises once per Lloyd iteration)"},
+
+    def ev_ms(fn):
+        torch.cuda.synchronize()
+        s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s_.record()
+        for _ in range(reps):
+            fn()
+        e_.record(); torch.cuda.synchronize()
+        return s_.elapsed_time(e_) / reps
+    ms = ev_ms(lambda: km.fit(Xd))            # device-resident features in; labels + cluster features read back on the host
+    ms1 = ev_ms(lambda: km1.fit(Xd))
+    e2e_ms = ev_ms(lambda: km.fit(Xh))        # host features in (H2D inside)
+    iters = max(int(km.n_iter_), 1)
+    it_ms = (ms - ms1) / max(iters - 1, 1) if iters > 1 else None
+    flops_it = 2.0 * KM_N * KM_K * KM_D
+    return {"value": world * 1e3 / ms, "unit": "slides/s", "ms_per_slide": ms, "lloyd_iterations": iters,
+            "lloyd_iteration_ms": it_ms, "seeding_plus_first_iteration_ms": ms1,
+            "config": {"workload": KM_WORKLOAD, "timing": "CUDA events around fit() (enqueue-only C call, results copied to the host inside)"},
             "e2e": {"value": world * 1e3 / e2e_ms, "unit": "slides/s", "ms_per_slide": e2e_ms, "h2d_bytes_per_step": KM_N * KM_D * 4,
                     "d2h_bytes_per_step": KM_N * 4 + KM_K * KM_D * 4},
-            "roofline": {"bound": "latency", "note": "99 dependent k-means++ steps (sequential fp32 cumsum) + ~5 Lloyd iterations of 1.68 GFLOP fp32; "
-                         "label parity with scikit-learn is the gate (SURVEY §8d)", "achieved": None, "peak": None, "frac": None, "traffic": None}}
+            "roofline": {"bound": "hbm", "kernel": "km_assign_kernel (fp32 FMA distances, 1.68 GFLOP and one 33.5 MB pass over the L2-resident features per Lloyd iteration)",
+                         "achieved": (KM_N * KM_D * 4 / (it_ms * 1e-3) / 1e9) if it_ms else None, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                         "frac": (KM_N * KM_D * 4 / (it_ms * 1e-3) / 1e9 / pk["hbm_gbs"]) if it_ms else None, "traffic": None,
+                         "fp32_tflops": (flops_it / (it_ms * 1e-3) / 1e12) if it_ms else None,
+                         "note": "label parity with scikit-learn is the gate (SURVEY 8d); the fit is latency-bound: 99 dependent k-means++ steps (sequential fp32 cumsum) + ~5 Lloyd iterations"}}
+
+
+def compact(obj, depth=0):
+    """The printed line stays below ~3 KB (the driver stores only a tail of stdout): numbers and short strings survive, prose
+    goes to the detail file (gpurun_out/bench_detail_*.json when that directory exists)."""
+    if isinstance(obj, dict):
+        out = {}
+        for k, v in obj.items():
+            if depth > 0 and k in ("note", "timing_note", "traffic_note", "peak_source", "timing", "l2", "parity", "kernel", "final_loss", "steps",
+                                   "samples", "source", "serialized_step_ms", "issued_mma_tflops", "issued_frac_of_peak", "api"):
+                continue
+            if depth > 0 and k == "config":
+                v = {kk: vv for kk, vv in v.items() if kk in ("global_batch",)}
+                if not v:
+                    continue
+            c = compact(v, depth + 1)
+            if c is not None or v is None:
+                out[k] = c
+        return out
+    if isinstance(obj, float):
+        return float(f"{obj:.5g}")
+    if isinstance(obj, str) and len(obj) > 90 and depth > 1:
+        return obj[:87] + "..."
+    return obj
 
 
 def emit(line):
     """Prints the ONE JSON line on the real stdout (libraries such as NCCL write banners to fd 1, which is redirected to stderr)."""
-    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+    try:
+        d = os.path.join(ROOT, "gpurun_out")
+        if os.path.isdir(d):
+            tag = ("ref" if line.get("impl") == "reference" else "ours") + f"_n{line.get('n_gpus', 1)}"
+            json.dump(line, open(os.path.join(d, f"bench_detail_{tag}.json"), "w"), indent=1)
+    except Exception:
+        pass
+    os.write(_REAL_STDOUT, (json.dumps(compact(line)) + "\n").encode())
 
 
 _REAL_STDOUT = os.dup(1)
@@ -483,7 +577,8 @@ def main():
     slide_host.copy_(slide_dev)
     feats = torch.empty(PATCHES_PER_SLIDE, 2048, dtype=torch.float32, device=dev)
     fused_stem = os.environ.get("SQ_STEM_FUSED", "1") != "0"     # one kernel for preprocessing + conv1 + max-pool (csrc/resnet.cu)
-    launches_per_step = (PATCHES_PER_SLIDE // BATCH) * (L.sq_resnet50_num_convs() + (1 if fused_stem else 3))
+    # per batch of 64: the fused stem + 52 bottleneck convolutions (the 7x7 average pool is fused into the last one)
+    launches_per_step = (PATCHES_PER_SLIDE // BATCH) * (L.sq_resnet50_num_convs() + (0 if fused_stem else 3))
 
     def step_device():
         # batch 64 per extractor launch (BASELINE configs[1]); consecutive batches alternate between two CUDA streams
@@ -518,11 +613,12 @@ def main():
         # stem_fused_kernel, not in gemm_tc_kernel, and is left out of the numerator
         alg_flops = (FLOP_PER_PATCH - (STEM_FLOP_PER_PATCH if fused_stem else 0.0)) * PATCHES_PER_SLIDE
         achieved = alg_flops / (tms * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (implicit-GEMM conv, bf16 -> fp32 TMEM)",
+        roof = {"bound": "tensor", "kernel": "convgemm_kernel (CTA-pair tcgen05 implicit-GEMM convolution, TMA epilogue; 52 launches per batch of 64)",
                 "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
                 "peak_source": pk["source"] + " bf16 sustained", "traffic": ncu_traffic("resnet"),
-                "traffic_note": "dram read+write bytes per launch, mean over the gemm_tc_kernel launches of one batch (ncu, profiles/r01_traffic.json; captured before the stem left this kernel: 53 launches)",
+                "traffic_note": "dram read+write bytes per launch, mean over the 52 convolution launches of one batch (ncu, profiles/r02_traffic.json)",
                 "launches": n, "avg_launch_us": tms * 1e3 / max(n, 1),
+                "step_frac": value / world * FLOP_PER_PATCH / 1e12 / pk["bf16_sustained"],
                 "kernel_share_of_step": tms / ser_ms, "serialized_step_ms": ser_ms,
                 "timing_note": "kernel durations and share measured on one stream (no inter-batch overlap); the per-launch event brackets serialise launches that "
                                "overlap through programmatic dependent launch in the untimed step, so the share can read slightly above 1 and `achieved` is conservative",
@@ -546,27 +642,27 @@ def main():
         return
 
     cpu = None
-    if not args.no_cpu_baseline and world == 1:
-        r, cores, done = cpu_reference_rate(args.cpu_sample)
+    if not args.no_cpu_baseline:
+        r, cores, done = cpu_reference_rate(args.cpu_sample if world == 1 else 64)
         cpu = {"value": r, "unit": "patches/s", "cores": cores, "kind": "port",
                "sample": f"{done} patches (batch 64) through oracle/resnet50_oracle.py, torch CPU fp32"}
-        if vis is not None:
+        if vis is not None and world == 1:
             vr, vc, vs = cpu_vis_rate(2)
             vis["cpu_baseline"] = {"value": vr, "unit": "slides/s", "cores": vc, "kind": "port", "sample": vs}
-        if kmn is not None:
+        if kmn is not None and world == 1:
             kr, kc, ks = cpu_kmeans_rate(2)
             kmn["cpu_baseline"] = {"value": kr, "unit": "slides/s", "cores": kc, "kind": "reference", "sample": ks}
 
     line = {"metric": METRIC, "value": value, "unit": "patches/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "l2": "inputs (805 MB/slide) larger than L2; no flush needed",
-                       "parallelism": f"slide-sharded x{world}, no collective; batches of 64 alternate between 2 CUDA streams per GPU"},
+            "vis_train": vis,
+            "config": headline_config(world),
             "clocks": clk.summary(),
             "e2e": {"value": e2e_value, "unit": "patches/s", "h2d_bytes_per_step": ex_h2d // e2e_steps,
                     "d2h_bytes_per_step": ex_d2h // e2e_steps, "ms_per_step": e2e_ms},
             "gpu_launches": launches_per_step * args.steps,
-            "roofline": roof, "cpu_baseline": cpu, "vis_train": vis, "kmeans": kmn, "uni_extract": uni, "vit_train": vit}
+            "roofline": roof, "cpu_baseline": cpu, "kmeans": kmn, "uni_extract": uni, "vit_train": vit}
     emit(line)
     if world > 1:
         dist.destroy_process_group()

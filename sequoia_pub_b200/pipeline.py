@@ -50,11 +50,18 @@ def extract_tiles(model, tiles, batch_size=64, extractor=None):
     return ex(tiles)
 
 
+_km_objects = {}
+
+
 def reduce_features(features, num_clusters=100):
-    """float32 [n, D] -> float32 [num_clusters, D] or None when the slide has fewer tiles than clusters (kmean_features.py:86-89)."""
+    """float32 [n, D] -> float32 [num_clusters, D] or None when the slide has fewer tiles than clusters (kmean_features.py:86-89).
+    One KMeans object per cluster count is kept, so consecutive slides reuse its workspace and its cached Lloyd-loop graph."""
     if features.shape[0] < num_clusters:
         return None
-    return KMeans(n_clusters=num_clusters, random_state=0).fit(features).cluster_features_
+    km = _km_objects.get(num_clusters)
+    if km is None:
+        km = _km_objects[num_clusters] = KMeans(n_clusters=num_clusters, random_state=0)
+    return km.fit(features).cluster_features_
 
 
 def extract_slide(model, patch_file, feature_file, feat_type="resnet", max_patch_number=4000, rng=_random, batch_size=64,
