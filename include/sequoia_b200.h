@@ -206,11 +206,11 @@ SQ_API int sq_vit_backward(const sq_vit_config* cfg, const float* params, const 
 
 /* ------------------------------------------------------------------ per-step training metrics
  * Replaces sklearn mean_absolute_error + he2rna.compute_correlations of the training loop (src/vit.py:167-168,
- * src/he2rna.py:140-149).  labels, preds: fp32 [batch, num_outputs] (device).  out3 (device): {mean absolute error,
- * mean over genes of the Pearson correlation (genes with constant labels skipped, NaN correlations dropped),
- * number of genes that entered the mean}. */
+ * src/he2rna.py:140-149) and evaluate()'s smape (src/vit.py:32-33,269).  labels, preds: fp32 [batch, num_outputs] (device).
+ * out4 (device): {mean absolute error, mean over genes of the Pearson correlation (genes with constant labels skipped, NaN
+ * correlations dropped), number of genes that entered the mean, SMAPE = 100 / batch * sum(2|F-A| / (|A|+|F|))}. */
 SQ_API size_t sq_step_metrics_scratch_bytes(int num_outputs);
-SQ_API int sq_step_metrics(const float* labels, const float* preds, int batch, int num_outputs, float* out3, void* scratch,
+SQ_API int sq_step_metrics(const float* labels, const float* preds, int batch, int num_outputs, float* out4, void* scratch,
                            size_t scratch_bytes, void* stream);
 
 /* ------------------------------------------------------------------ UNI ViT-L/16 feature extractor

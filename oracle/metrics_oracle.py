@@ -27,6 +27,11 @@ def mean_absolute_error(labels, preds):
     return float(np.mean(np.abs(np.asarray(labels, dtype=np.float64) - np.asarray(preds, dtype=np.float64))))
 
 
+def smape(A, F):
+    """src/vit.py:32-33, verbatim semantics (float32 arrays in evaluate(), :269)."""
+    return 100 / len(A) * np.sum(2 * np.abs(F - A) / (np.abs(A) + np.abs(F)))
+
+
 def make_batch(seed, batch=32, genes=20530):
     """Synthetic (labels, preds): log-FPKM-like labels with some constant genes, noisy predictions, a few constant columns."""
     rs = np.random.RandomState(seed)

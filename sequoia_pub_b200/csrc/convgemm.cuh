@@ -286,11 +286,11 @@ convgemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             const int t = cluster_id + ti * num_clusters;
             const int pm = t / p.num_n, nt = t - pm * p.num_n;
             const int row0 = (pm * CG + (int)rank) * GEMM_BM + q * 32;
-            [[maybe_unused]] int h_ox0 = 0, h_row0 = 0;
+            [[maybe_unused]] int h_ox0 = 0, h_row0 = 0, h_img = 0;
             if constexpr (HALO) {
-                const int mt = pm * CG + (int)rank, img_h = mt / p.tiles_per_img, rem = mt - img_h * p.tiles_per_img;
+                const int mt = pm * CG + (int)rank, rem = mt - (mt / p.tiles_per_img) * p.tiles_per_img;
                 const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
-                h_ox0 = tx * HALO_TW; h_row0 = img_h * p.Ho + ty * HALO_TH + q * 4;
+                h_img = mt / p.tiles_per_img; h_ox0 = tx * HALO_TW; h_row0 = ty * HALO_TH + q * 4;
             }
             const int as = ti & 1; const uint32_t aphase = (ti >> 1) & 1;
             // this warp's CPH*64 shift values of the tile: requested before the accumulator wait, published after it (all warps
@@ -388,7 +388,7 @@ convgemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) {
-                    if constexpr (HALO) tma_store_3d(&mapO, sl, nt * BN + c * 64, h_ox0, h_row0);     // 4 output rows x 8 pixels
+                    if constexpr (HALO) tma_store_4d(&mapO, sl, nt * BN + c * 64, h_ox0, h_row0, h_img);     // 4 output rows x 8 pixels (clipped at the map edge)
                     else tma_store_2d(&mapO, sl, nt * BN + c * 64, row0);
                     bulk_commit_group();
                     if (has_res && pf_j < n_items) {
@@ -432,6 +432,7 @@ struct ConvGemmArgs {
     int block_n;                 // 0 = auto
     int cta_group;               // 0 = auto
     float* pool_out; int pool_batch;   // fused 7x7 average pool of an 8x8 final map (out may then be null)
+    bf16* scratch; size_t scratch_bytes;   // im2col buffer for geometries neither TMA mode tiles (strided convolutions on odd-sized maps)
 };
 
 template <int BN, int CG, int D, int HALO>
@@ -459,6 +460,17 @@ int convgemm_launch_inst(const CUtensorMap* maps, const CgParams& kp, int grid, 
 }
 
 int convgemm_dispatch(int bn, int cg, int halo, const CUtensorMap* maps, const CgParams& kp, int grid, cudaStream_t st);   // resnet.cu
+
+// per-tap mode tiles the output map with boxes of 128 pixels: whole rows (Wo divides 128) and whole row groups / images
+inline bool conv_pertap_geometry_ok(const ConvGeom& c) {
+    if (c.Wo > 128 || 128 % c.Wo != 0) return false;
+    int BH = 128 / c.Wo;
+    if (BH > c.Ho) { const int BIMG = BH / c.Ho; return BIMG * c.Ho * c.Wo == 128; }
+    return c.Ho % BH == 0;
+}
+
+struct ConvGemmArgs;
+inline int convgemm_im2col_fallback(const ConvGemmArgs& g, cudaStream_t st);
 
 // true when the launch fits this kernel (N a multiple of 64, channels a multiple of 64, tile geometry of the 4-D boxes)
 inline bool convgemm_supported(const ConvGemmArgs& g) {
@@ -493,7 +505,7 @@ inline int convgemm_launch(const ConvGemmArgs& g, cudaStream_t st) {
     kp.M = g.M; kp.N = g.N;
     const int num_m = (g.M + GEMM_BM - 1) / GEMM_BM;
     kp.num_n = g.N / bn;
-    kp.total_tiles = ((num_m + cg - 1) / cg) * kp.num_n;
+    kp.total_tiles = ((num_m + cg - 1) / cg) * kp.num_n;      // (halo mode recounts: one tile per 16 x 8 patch)
     kp.bias = g.bias; kp.relu = g.relu; kp.has_res = g.res != nullptr;
     kp.prof = gemm_prof_buffer();
     kp.pool_out = g.pool_out; kp.batch = g.pool_batch;
@@ -504,14 +516,21 @@ inline int convgemm_launch(const ConvGemmArgs& g, cudaStream_t st) {
     const ConvGeom& cc = g.conv;
     // (measured: 49 -> 41 us on layer 1, 31.6 -> 29.4 us on layer 2; with 256-wide tiles the three weight stages that fit beside
     //  the halo slots starve the MMAs, 25.2 -> 26.6 us on layer 3, so those keep the per-tap boxes)
-    const int halo = (env_halo && cc.enabled && cc.R == 3 && cc.S == 3 && cc.stride == 1 && cc.pad == 1 && !g.res && cc.Wo % HALO_TW == 0 &&
-                      cc.Ho % HALO_TH == 0 && cc.C % 64 == 0 && (bn <= 128 || env_halo == 3)) ? 1 : 0;
+    // Patches that hang over the map edge are handled by TMA clipping, so ANY output size works in halo mode; maps that do not tile
+    // by the per-tap boxes (Wo not a divisor of 128: 224-px inputs, odd sizes) always take it.
+    const bool pertap_ok = cc.enabled && conv_pertap_geometry_ok(cc);
+    const bool halo_shape = cc.enabled && cc.R == 3 && cc.S == 3 && cc.stride == 1 && cc.pad == 1 && !g.res && cc.C % 64 == 0;
+    const bool even = cc.Wo % HALO_TW == 0 && cc.Ho % HALO_TH == 0;
+    const int halo = (halo_shape && (!pertap_ok || (env_halo && even && (bn <= 128 || env_halo == 3)))) ? 1 : 0;
+    if (cc.enabled && !halo && !pertap_ok) return convgemm_im2col_fallback(g, st);
     if (halo) {
         const ConvGeom& c = g.conv;
         kp.conv = 1; kp.cblocks = c.C / 64; kp.S = 3; kp.stride = 1; kp.pad = 1;
-        kp.tiles_x = c.Wo / HALO_TW; kp.tiles_per_img = (c.Ho / HALO_TH) * kp.tiles_x; kp.Ho = c.Ho; kp.halo_bo = env_halo == 2;
+        kp.tiles_x = (c.Wo + HALO_TW - 1) / HALO_TW; kp.tiles_per_img = ((c.Ho + HALO_TH - 1) / HALO_TH) * kp.tiles_x; kp.Ho = c.Ho; kp.halo_bo = env_halo == 2;
         kp.nk = 9 * kp.cblocks;
         if (g.M != c.batch * c.Ho * c.Wo) { set_error("conv: M mismatch"); return -1; }
+        // one 128-row tile per 16 x 8 patch (partial patches included)
+        kp.total_tiles = ((c.batch * kp.tiles_per_img + cg - 1) / cg) * kp.num_n;
         cuuint64_t dims[4] = {(cuuint64_t)c.C, (cuuint64_t)c.W, (cuuint64_t)c.H, (cuuint64_t)c.batch};
         cuuint64_t strides[3] = {(cuuint64_t)c.C * 2, (cuuint64_t)c.W * c.C * 2, (cuuint64_t)c.H * c.W * c.C * 2};
         cuuint32_t box[4] = {64, HALO_PITCH, HALO_TH + 2, 1};
@@ -540,12 +559,13 @@ inline int convgemm_launch(const ConvGemmArgs& g, cudaStream_t st) {
     }
     if (make_operand_map(&maps[1], g.W, 0, (long long)kp.nk * 64, g.N, kp.nk * 64, bn / cg)) return -1;
     if (halo) {
-        // output sub-tiles: 64 channels x 8 pixels x 4 output rows (= the 32 accumulator rows of one epilogue warp)
+        // output sub-tiles: 64 channels x 8 pixels x 4 output rows (= the 32 accumulator rows of one epilogue warp); a 4-D map
+        // so that patches hanging over the right / bottom edge of an image are clipped by the TMA unit
         const ConvGeom& c = g.conv;
-        cuuint64_t dims[3] = {(cuuint64_t)g.N, (cuuint64_t)c.Wo, (cuuint64_t)c.Ho * c.batch};
-        cuuint64_t strides[2] = {(cuuint64_t)g.N * 2, (cuuint64_t)c.Wo * g.N * 2};
-        cuuint32_t box[3] = {64, HALO_TW, 4}, estr[3] = {1, 1, 1};
-        if (encode_map(&maps[3], g.out, 3, dims, strides, box, estr)) return -1;
+        cuuint64_t dims[4] = {(cuuint64_t)g.N, (cuuint64_t)c.Wo, (cuuint64_t)c.Ho, (cuuint64_t)c.batch};
+        cuuint64_t strides[3] = {(cuuint64_t)g.N * 2, (cuuint64_t)c.Wo * g.N * 2, (cuuint64_t)c.Ho * c.Wo * g.N * 2};
+        cuuint32_t box[4] = {64, HALO_TW, 4, 1}, estr[4] = {1, 1, 1, 1};
+        if (encode_map(&maps[3], g.out, 4, dims, strides, box, estr)) return -1;
         maps[2] = maps[3];
     } else
     // residual / output sub-tiles: 64 channels x 32 rows
@@ -563,6 +583,36 @@ inline int convgemm_launch(const ConvGemmArgs& g, cudaStream_t st) {
     const int rc = convgemm_dispatch(bn, cg, halo, maps, kp, clusters * cg, st);
     gemm_timing_end(st);
     return rc;
+}
+
+// Generic fallback: explicit im2col (NHWC -> [M, R*S*C], zero padding) followed by the plain GEMM mode.  Only reached for
+// geometries the TMA boxes cannot tile (e.g. the stride-2 convolutions of a 224-px or 256x265 input).
+static __global__ void im2col_nhwc_kernel(const bf16* __restrict__ in, bf16* __restrict__ col, int batch, int H, int W, int C, int R, int S, int stride,
+                                          int pad, int Ho, int Wo) {
+    const int C8 = C / 8;
+    const long long total = (long long)batch * Ho * Wo * R * S * C8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c8 = (int)(i % C8); long long t = i / C8;
+        const int s_ = (int)(t % S); t /= S; const int r = (int)(t % R); t /= R;
+        const int ow = (int)(t % Wo); t /= Wo; const int oh = (int)(t % Ho); const int img = (int)(t / Ho);
+        const int ih = oh * stride - pad + r, iw = ow * stride - pad + s_;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = *reinterpret_cast<const uint4*>(in + (((long long)img * H + ih) * W + iw) * C + c8 * 8);
+        *reinterpret_cast<uint4*>(col + i * 8) = v;
+    }
+}
+
+inline int convgemm_launch(const ConvGemmArgs& g, cudaStream_t st);
+inline int convgemm_im2col_fallback(const ConvGemmArgs& g, cudaStream_t st) {
+    const ConvGeom& c = g.conv;
+    const size_t need = (size_t)g.M * g.K * sizeof(bf16);
+    if (!g.scratch || g.scratch_bytes < need) { set_error("conv: geometry %dx%d -> %dx%d needs an im2col scratch of %zu bytes", c.H, c.W, c.Ho, c.Wo, need); return -1; }
+    const long long total = (long long)g.M * (g.K / 8);
+    long long blocks = (total + 255) / 256; if (blocks > 148LL * 32) blocks = 148LL * 32;
+    im2col_nhwc_kernel<<<(unsigned)blocks, 256, 0, st>>>(g.A, g.scratch, c.batch, c.H, c.W, c.C, c.R, c.S, c.stride, c.pad, c.Ho, c.Wo);
+    ConvGemmArgs p = g;
+    p.A = g.scratch; p.lda = g.K; p.conv.enabled = 0;
+    return convgemm_launch(p, st);
 }
 
 }  // namespace sq

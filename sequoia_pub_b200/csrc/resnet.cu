@@ -191,7 +191,9 @@ __global__ void __launch_bounds__(ST_THREADS, 2) stem_fused_kernel(const void* _
         s_lut[i] = __float2bfloat16_rn((static_cast<float>(i & 255) / 255.0f - mu) / sd);
     }
     for (int i = threadIdx.x; i < ST_IROW; i += ST_THREADS) s_in[39 * ST_IROW + i] = __float2bfloat16_rn(0.f);   // over-read row
-    const int Hc = H / 2, Wc = W / 2, Hp = H / 4, Wp = W / 4, tiles_x = Wp / 8, tiles_y = Hp / 8;
+    // conv1 7x7/2 pad 3 and max-pool 3x3/2 pad 1 output sizes (any H, W; partial 8x8 pooled tiles are masked on store)
+    const int Hc = (H - 1) / 2 + 1, Wc = (W - 1) / 2 + 1, Hp = (Hc - 1) / 2 + 1, Wp = (Wc - 1) / 2 + 1;
+    const int tiles_x = (Wp + 7) / 8, tiles_y = (Hp + 7) / 8;
     const int ntiles = batch * tiles_y * tiles_x;
     for (int i = threadIdx.x; i < 64 * (ST_KSTEPS * 2); i += ST_THREADS) {          // [64][192] packed -> [64][176] slab
         const int n = i / (ST_KSTEPS * 2), q = i - n * (ST_KSTEPS * 2);
@@ -286,6 +288,7 @@ __global__ void __launch_bounds__(ST_THREADS, 2) stem_fused_kernel(const void* _
         __syncthreads();
         for (int i = threadIdx.x; i < 64 * 8; i += ST_THREADS) {
             const int c8 = i & 7, pp = i >> 3, ply = pp >> 3, plx = pp & 7;
+            if (8 * ty + ply >= Hp || 8 * tx + plx >= Wp) continue;
             uint4 m = *reinterpret_cast<const uint4*>(s_c + ((2 * ply) * 17 + 2 * plx) * ST_CLD + c8 * 8);
             __nv_bfloat162* mh = reinterpret_cast<__nv_bfloat162*>(&m);
 #pragma unroll
@@ -314,7 +317,8 @@ static int launch_stem_fused(const void* input, int kind, int batch, int H, int 
         }
         attr_set = true;
     }
-    const int ntiles = batch * (H / 32) * (W / 32);
+    const int Hp_ = ((H - 1) / 2) / 2 + 1, Wp_ = ((W - 1) / 2) / 2 + 1;
+    const int ntiles = batch * ((Hp_ + 7) / 8) * ((Wp_ + 7) / 8);
     int grid = 2 * num_sms(); if (grid > ntiles) grid = ntiles;
     if (kind == 0 && (reinterpret_cast<uintptr_t>(input) & 3) == 0 && W % 4 == 0) kind = 2;
     stem_fused_kernel<<<grid, ST_THREADS, ST_SMEM, st>>>(input, kind, batch, H, W, wpk, shift, out);
@@ -338,18 +342,41 @@ __global__ void avgpool7_kernel(const float* __restrict__ in, float* __restrict_
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct ResNetWs {
-    size_t col, stem, big[3], small[2], fmap, total;
+    size_t col, stem, big[3], small[2], fmap, im2col, total;
 };
+
+static inline int conv_out(int x, int k, int stride, int pad) { return (x + 2 * pad - k) / stride + 1; }
 
 static ResNetWs ws_layout(int batch, int H, int W) {
     ResNetWs w; size_t off = 0;
-    const size_t Ho = H / 2, Wo = W / 2, Hp = H / 4, Wp = W / 4;
+    const size_t Ho = conv_out(H, 7, 2, 3), Wo = conv_out(W, 7, 2, 3), Hp = conv_out((int)Ho, 3, 2, 1), Wp = conv_out((int)Wo, 3, 2, 1);
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
-    w.col = take((size_t)batch * Ho * Wo * STEM_K * 2);
-    w.stem = take((size_t)batch * Ho * Wo * 64 * 2);
+    const bool fused = stem_fused_enabled() != 0;
+    w.col = take(fused ? 0 : (size_t)batch * Ho * Wo * STEM_K * 2);
+    w.stem = take(fused ? 0 : (size_t)batch * Ho * Wo * 64 * 2);
     for (int i = 0; i < 3; ++i) w.big[i] = take((size_t)batch * Hp * Wp * 256 * 2);
     for (int i = 0; i < 2; ++i) w.small[i] = take((size_t)batch * Hp * Wp * 128 * 2);
-    w.fmap = take((size_t)batch * (H / 32) * (W / 32) * 2048 * 4);
+    // final map (only materialised when the average pool is not fused) and the im2col scratch of the stride-2 convolutions on maps
+    // the TMA boxes cannot tile (inputs other than 256x256)
+    int h = (int)Hp, wd = (int)Wp; size_t im2col = 0;
+    {
+        const int planes[4] = {64, 128, 256, 512}, strides[4] = {1, 2, 2, 2};
+        int inpl = 64;
+        for (int st = 0; st < 4; ++st) {
+            if (strides[st] == 2) {
+                const int ho = conv_out(h, 3, 2, 1), wo = conv_out(wd, 3, 2, 1);
+                ConvGeom g; memset(&g, 0, sizeof(g)); g.enabled = 1; g.Ho = ho; g.Wo = wo;
+                if (!conv_pertap_geometry_ok(g)) {
+                    const size_t a = (size_t)batch * ho * wo * 9 * planes[st] * 2, b = (size_t)batch * ho * wo * inpl * 2;
+                    im2col = a > im2col ? a : im2col; im2col = b > im2col ? b : im2col;
+                }
+                h = ho; wd = wo;
+            }
+            inpl = planes[st] * 4;
+        }
+    }
+    w.fmap = take((size_t)batch * h * wd * 2048 * 4);
+    w.im2col = take(im2col);
     w.total = off;
     return w;
 }
@@ -379,11 +406,12 @@ static int convgemm_enabled() {
 }
 
 static int run_conv(const ConvSpec& c, const bf16* wbase, const float* sbase, const bf16* in, int batch, int H, int W, bf16* out_bf,
-                    float* out_f32, const bf16* res, bool relu, cudaStream_t st, int* Ho_out, int* Wo_out, float* pool_out = nullptr) {
+                    float* out_f32, const bf16* res, bool relu, cudaStream_t st, int* Ho_out, int* Wo_out, float* pool_out = nullptr,
+                    bf16* scratch = nullptr, size_t scratch_bytes = 0) {
     const int Ho = (H + 2 * c.pad - c.k) / c.stride + 1, Wo = (W + 2 * c.pad - c.k) / c.stride + 1;
     if (convgemm_enabled() && ((out_bf && !out_f32) || pool_out)) {
         ConvGemmArgs a; memset(&a, 0, sizeof(a));
-        a.pool_out = pool_out; a.pool_batch = batch;
+        a.pool_out = pool_out; a.pool_batch = batch; a.scratch = scratch; a.scratch_bytes = scratch_bytes;
         a.M = batch * Ho * Wo; a.N = c.cout; a.K = c.k * c.k * c.cin;
         a.A = in; a.lda = c.cin; a.W = wbase + c.w_off; a.bias = sbase + c.s_off; a.res = res; a.out = out_bf; a.relu = relu ? 1 : 0;
         a.conv.enabled = (c.k == 1 && c.stride == 1) ? 0 : 1; a.conv.batch = batch; a.conv.H = H; a.conv.W = W; a.conv.C = c.cin; a.conv.Ho = Ho; a.conv.Wo = Wo;
@@ -463,9 +491,16 @@ size_t sq_resnet50_workspace_bytes(int batch, int H, int W) { return ws_layout(b
 int sq_resnet50_extract(const void* input, int input_kind, int batch, int H, int W, const void* packed_w, const float* shifts,
                         float* features, void* workspace, size_t workspace_bytes, void* stream) {
     if (batch <= 0) return 0;
-    // Tile geometry (full output rows per 128-pixel MMA tile, pooled map in [7,13]) is laid out for the
-    // 256 px tiles the reference pipeline produces (pre_processing/patch_gen_hdf5.py:119-120).
-    if (H != 256 || W != 256) { set_error("resnet50_extract: only 256x256 patches are supported (got %dx%d)", H, W); return -1; }
+    // Any patch size whose final map is 7..13 pixels per side (AvgPool2d(7) then yields one 2048-vector, src/resnet.py:110,166-167):
+    // 193..416 px.  256x256 - the tiles the reference pipeline produces (pre_processing/patch_gen_hdf5.py:119-120) - is the tuned
+    // case; other sizes (224 px, spatial_vis/visualize.py's 256x265) run the same kernels with clipped edge tiles and an im2col
+    // scratch for their stride-2 convolutions.
+    {
+        int hf = conv_out(conv_out(H, 7, 2, 3), 3, 2, 1), wf = conv_out(conv_out(W, 7, 2, 3), 3, 2, 1);
+        for (int i = 0; i < 3; ++i) { hf = conv_out(hf, 3, 2, 1); wf = conv_out(wf, 3, 2, 1); }
+        if (hf < 7 || hf > 13 || wf < 7 || wf > 13) { set_error("resnet50_extract: %dx%d patches give a %dx%d final map; AvgPool2d(7) needs 7..13 per side", H, W, hf, wf); return -1; }
+        if ((H != 256 || W != 256) && (!convgemm_enabled() || !stem_fused_enabled())) { set_error("resnet50_extract: SQ_CONVGEMM=0 / SQ_STEM_FUSED=0 (round-1 kernels) support 256x256 patches only"); return -1; }
+    }
     const ResNetWs L = ws_layout(batch, H, W);
     if (!workspace || workspace_bytes < L.total) { set_error("resnet50_extract: workspace %zu < %zu", workspace_bytes, L.total); return -1; }
     const ResNetPlan& p = plan();
@@ -480,8 +515,10 @@ int sq_resnet50_extract(const void* input, int input_kind, int batch, int H, int
 
     // ---- stem: one fused kernel (preprocessing + conv1 + BN shift + ReLU + max-pool); SQ_STEM_FUSED=0 selects the older
     //      im2col -> tcgen05 GEMM -> max-pool chain (kept for A/B measurements)
-    const int Ho = H / 2, Wo = W / 2;
-    int h = Ho / 2, w = Wo / 2;
+    const int Ho = conv_out(H, 7, 2, 3), Wo = conv_out(W, 7, 2, 3);
+    int h = conv_out(Ho, 3, 2, 1), w = conv_out(Wo, 3, 2, 1);
+    bf16* im2col = (bf16*)(ws + L.im2col);
+    const size_t im2col_bytes = L.total - L.im2col;
     if (stem_fused_enabled()) {
         if (launch_stem_fused(input, input_kind, batch, H, W, wp + p.conv[0].w_off, shifts + p.conv[0].s_off, big[0], st)) return -1;
     } else {
@@ -509,11 +546,11 @@ int sq_resnet50_extract(const void* input, int input_kind, int batch, int H, int
             const ConvSpec& c1 = p.conv[ci]; const ConvSpec& c2 = p.conv[ci + 1]; const ConvSpec& c3 = p.conv[ci + 2];
             int h1, w1, h2, w2, h3, w3, hd, wd;
             if (run_conv(c1, wp, shifts, big[x], batch, h, w, small_[0], nullptr, nullptr, true, st, &h1, &w1)) return -1;
-            if (run_conv(c2, wp, shifts, small_[0], batch, h1, w1, small_[1], nullptr, nullptr, true, st, &h2, &w2)) return -1;
+            if (run_conv(c2, wp, shifts, small_[0], batch, h1, w1, small_[1], nullptr, nullptr, true, st, &h2, &w2, nullptr, im2col, im2col_bytes)) return -1;
             const bf16* res = big[x];
             const int y = (x + 1) % 3, d = (x + 2) % 3;
             if (down) {
-                if (run_conv(p.conv[ci + 3], wp, shifts, big[x], batch, h, w, big[d], nullptr, nullptr, false, st, &hd, &wd)) return -1;
+                if (run_conv(p.conv[ci + 3], wp, shifts, big[x], batch, h, w, big[d], nullptr, nullptr, false, st, &hd, &wd, nullptr, im2col, im2col_bytes)) return -1;
                 res = big[d];
             }
             // the last convolution of an 8x8 final map feeds the fused average pool (no fp32 map, no pooling kernel)

@@ -1,6 +1,6 @@
 """Device-side versions of the per-step metrics of the reference training loop (src/vit.py:167-168):
 `sklearn.metrics.mean_absolute_error(labels, preds)` and `he2rna.compute_correlations(labels, preds)`
-(src/he2rna.py:140-149).  The reference copies pred / labels to the host and loops over ~20k genes in numpy every step;
+(src/he2rna.py:140-149), plus evaluate()'s `smape` (src/vit.py:32-33,269).  The reference copies pred / labels to the host and loops over ~20k genes in numpy every step;
 here one kernel produces both numbers without leaving the device.  No CPU fallback."""
 import numpy as np
 import torch
@@ -9,7 +9,7 @@ from . import _lib
 
 
 def step_metrics(labels, preds):
-    """labels, preds: float32 [B, G] CUDA tensors -> float32[3] device tensor (MAE, mean per-gene Pearson r, #genes used)."""
+    """labels, preds: float32 [B, G] CUDA tensors -> float32[4] device tensor (MAE, mean per-gene Pearson r, #genes used, SMAPE)."""
     if isinstance(labels, np.ndarray):
         labels = torch.from_numpy(np.ascontiguousarray(labels, dtype=np.float32)).cuda()
     if isinstance(preds, np.ndarray):
@@ -23,7 +23,7 @@ def step_metrics(labels, preds):
     B, G = labels.shape
     L = _lib.lib()
     scratch = torch.empty(L.sq_step_metrics_scratch_bytes(G), dtype=torch.uint8, device=labels.device)
-    out = torch.empty(3, dtype=torch.float32, device=labels.device)
+    out = torch.empty(4, dtype=torch.float32, device=labels.device)
     _lib.check(L.sq_step_metrics(_lib.ptr(labels), _lib.ptr(preds), B, G, _lib.ptr(out), _lib.ptr(scratch), scratch.numel(),
                                  _lib.stream_ptr()))
     return out
@@ -36,3 +36,9 @@ def compute_correlations(labels, preds):
 
 def mean_absolute_error(labels, preds):
     return float(step_metrics(labels, preds)[0].item())
+
+
+def smape(labels, preds):
+    """`smape(A, F)` of src/vit.py:32-33 as evaluate() calls it (:269): 100 / len(A) * sum(2 |F - A| / (|A| + |F|)) over the whole
+    [B, G] array, len(A) = B."""
+    return float(step_metrics(labels, preds)[3].item())

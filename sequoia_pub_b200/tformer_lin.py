@@ -153,7 +153,18 @@ class _FlatAggregator:
 
     def _apply(self, fn, *args, **kwargs):
         out = super()._apply(fn, *args, **kwargs)
-        self.__dict__["_flat"] = None          # .to()/.cuda() re-allocate every parameter
+        # .to()/.cuda()/.float() re-allocate the parameters only when something actually changes: keep the flat buffer (and with
+        # it the optimizer state bound to it) when every parameter still is the view it was
+        flat = self.__dict__.get("_flat")
+        if flat is not None:
+            base = flat.data_ptr()
+            try:
+                slots, _ = self._slots(self._cfg)
+                same = all(p.data_ptr() == base + 4 * off and p.dtype == torch.float32 for p, off in slots)
+            except Exception:
+                same = False
+            if not same:
+                self.__dict__["_flat"] = None
         return out
 
     def _ensure_flat(self):
@@ -257,17 +268,16 @@ class _FlatAggregator:
         return pred, act
 
     def _grad_buffer(self):
-        """A flat gradient buffer that is not currently aliased by the parameters' .grad tensors."""
-        g = self.pos_emb1D.grad
-        busy = None
-        if g is not None:
-            for i, b in enumerate(self._gbufs):
-                if b is not None and b.data_ptr() <= g.data_ptr() < b.data_ptr() + 4 * b.numel():
-                    busy = i
-        i = 1 if busy == 0 else 0
-        if self._gbufs[i] is None:
-            self._gbufs[i] = torch.zeros(self._total, dtype=torch.float32, device=self._flat.device)
-        return self._gbufs[i]
+        """A flat gradient buffer nobody else references.  The per-parameter gradients handed to autograd are VIEWS of the buffer:
+        AccumulateGrad may keep them as `.grad`, and when the model is called several times inside one graph
+        (`loss = f(model(x1)) + f(model(x2))`) autograd's input buffers hold the views of the first backward while the second one
+        runs.  A buffer is reused only when its storage has no other user (tensor + the probing storage handle = 2 references)."""
+        for b in self._gbufs:
+            if b is not None and torch._C._storage_Use_Count(b.untyped_storage()._cdata) <= 2:
+                return b
+        b = torch.zeros(self._total, dtype=torch.float32, device=self._flat.device)
+        self._gbufs = [g for g in self._gbufs if g is not None] + [b]
+        return b
 
     def _scratch_for(self, B):
         need = getattr(_lib.lib(), self._C["bwd_bytes"])(C.byref(self._cfg), B)

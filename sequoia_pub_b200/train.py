@@ -35,6 +35,7 @@ class FusedTrainer:
         m._ensure_flat()
         if self._token != m._flat_token:
             dev = m._flat.device
+            old = (self.m, self.v, self.stage_range) if self._token is not None else None
             self.m = torch.zeros_like(m._flat)
             self.v = torch.zeros_like(m._flat)
             self.g = torch.zeros_like(m._flat)
@@ -42,6 +43,17 @@ class FusedTrainer:
             self.mse_scratch = torch.empty(1024, dtype=torch.float32, device=dev)
             self._token = m._flat_token
             self.stage_range = m._stage_ranges()         # contiguous slices of the flat buffer per backward stage
+            if old is not None:
+                # the parameters were re-laid out (a .to() that moved them, a replaced head): the Adam moments follow them, like
+                # torch.optim state does - everything when the layout is unchanged, the layers below a replaced head otherwise
+                om, ov, orange = old
+                if om.numel() == self.m.numel() and orange == self.stage_range:
+                    self.m.copy_(om); self.v.copy_(ov)
+                elif orange[:-1] == self.stage_range[:-1]:
+                    keep = self.stage_range[-1][0]
+                    self.m[:keep].copy_(om[:keep]); self.v[:keep].copy_(ov[:keep])
+                else:
+                    self.step_count = 0                  # a different architecture: nothing carries over, bias correction restarts
         return m
 
     def step(self, x, y):

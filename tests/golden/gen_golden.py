@@ -184,11 +184,17 @@ def gen_metrics():
     fn = [n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "compute_correlations"][0]
     ns = {"np": np}
     exec(compile(ast.Module(body=[fn], type_ignores=[]), "he2rna.py", "exec"), ns)
+    # the reference's own smape (src/vit.py:32-33), extracted the same way (src.vit imports he2rna -> tkinter)
+    vsrc = open("/root/reference/src/vit.py").read()
+    sfn = [n for n in ast.parse(vsrc).body if isinstance(n, ast.FunctionDef) and n.name == "smape"][0]
+    exec(compile(ast.Module(body=[sfn], type_ignores=[]), "vit.py", "exec"), ns)
     out = {}
     for tag, seed, b, g in (("cfg3", 0, 32, 20530), ("small", 1, 5, 301), ("b2", 2, 2, 64)):
         y, p = MO.make_batch(seed, b, g)
         out[f"{tag}_corr"] = np.array(ns["compute_correlations"](y, p))
         out[f"{tag}_mae"] = np.array(mean_absolute_error(y, p))
+        out[f"{tag}_smape"] = np.array(ns["smape"](y, p), dtype=np.float64)
+        assert abs(MO.smape(y, p) - out[f"{tag}_smape"]) <= 1e-12 * abs(out[f"{tag}_smape"])
         assert abs(MO.compute_correlations(y, p) - out[f"{tag}_corr"]) < 1e-12
         print("metrics golden", tag, float(out[f"{tag}_corr"]), float(out[f"{tag}_mae"]))
     np.savez_compressed(os.path.join(HERE, "metrics_golden.npz"), **out)

@@ -14,6 +14,7 @@ def test_metrics_oracle_matches_reference_golden():
         y, p = MO.make_batch(seed, b, n)
         assert abs(MO.compute_correlations(y, p) - float(g[f"{tag}_corr"])) < 1e-12
         assert abs(MO.mean_absolute_error(y, p) - float(g[f"{tag}_mae"])) < 1e-6
+        assert abs(MO.smape(y, p) - float(g[f"{tag}_smape"])) <= 1e-9 * float(g[f"{tag}_smape"])
 
 
 @pytest.mark.gpu
@@ -29,3 +30,5 @@ def test_step_metrics_match_reference(tag, seed, b, n):
     assert abs(out[0] - float(g[f"{tag}_mae"])) < 1e-6 * max(1.0, float(g[f"{tag}_mae"]))
     assert abs(metrics.compute_correlations(y, p) - float(g[f"{tag}_corr"])) < 1e-6      # numpy in, float out (reference signature)
     assert out[2] > 0
+    assert abs(out[3] - float(g[f"{tag}_smape"])) < 2e-5 * float(g[f"{tag}_smape"])      # evaluate()'s smape (src/vit.py:32-33,269)
+    assert abs(metrics.smape(y, p) - float(g[f"{tag}_smape"])) < 2e-5 * float(g[f"{tag}_smape"])

@@ -115,3 +115,29 @@ def test_two_lane_extraction_is_bit_identical_to_sequential():
         got = ex(src)
         assert got.shape == (150, 2048) and np.array_equal(got, seq.cpu().numpy())
     assert ex(tiles[:0]).shape == (0, 2048)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("hw", [(224, 224), (256, 265), (288, 320), (200, 200)])
+def test_other_patch_sizes_match_oracle(hw):
+    """src/resnet.py:155-170 is size-agnostic: 224 px gives an exact 7x7 global mean, spatial_vis/visualize.py:213 resizes tiles to
+    (256, 265).  Same kernels with clipped edge tiles; the stride-2 convolutions of maps the TMA boxes cannot tile go through im2col."""
+    from oracle import resnet50_oracle as RO
+    from sequoia_pub_b200.resnet import resnet50
+    sd = RO.make_state_dict(0)
+    m = resnet50().eval()
+    m.load_state_dict(sd)
+    m = m.cuda()
+    g = torch.Generator().manual_seed(hw[0] + hw[1])
+    patches = torch.randint(0, 256, (3,) + hw + (3,), generator=g, dtype=torch.uint8)
+    with torch.no_grad():
+        x = RO.preprocess(patches)
+        want = RO.forward_extract(RO.to_double(sd) if hasattr(RO, "to_double") else sd, x.double() if hasattr(RO, "to_double") else x)
+    got = m.extract_uint8(patches.cuda()).cpu()
+    got2 = m.forward_extract(x.cuda()).cpu()
+    err = ((got.double() - want.double()).norm() / want.double().norm()).item()
+    err2 = ((got2.double() - want.double()).norm() / want.double().norm()).item()
+    print(f"\n[resnet parity] {hw}: L2-rel vs oracle {err:.3e} (uint8 path), {err2:.3e} (fp32 NCHW path)")
+    assert got.shape == (3, 2048) and err < 5e-3 and err2 < 5e-3
+    with pytest.raises(RuntimeError):
+        m.extract_uint8(torch.zeros(1, 128, 128, 3, dtype=torch.uint8, device="cuda"))      # 4x4 final map: AvgPool2d(7) has no output

@@ -236,3 +236,56 @@ def test_error_paths_and_other_shapes():
     assert float(next(iter(opt.state.values()))["step"]) == 1.0
     empty = m.eval()(torch.zeros(0, N, D, device="cuda"))
     assert tuple(empty.shape) == (0, G)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["vis", "vit"])
+def test_two_forwards_one_backward_accumulate(kind):
+    """`loss = f(model(x1)) + f(model(x2))`: both backward calls run before any gradient is accumulated, so each needs its own
+    flat gradient buffer (the views of the first are still held by autograd).  Gradients must equal g1 + g2 from separate passes."""
+    from oracle import vis_oracle as V
+    D, G, B, depth = 1024, 130, 2, 1
+    if kind == "vis":
+        m = _model(V.make_state_dict(4, G, input_dim=D, depth=depth), G, D, depth).train()
+    else:
+        from sequoia_pub_b200.vit import ViT
+        torch.manual_seed(4)
+        m = ViT(num_outputs=G, dim=D, depth=depth, heads=16, mlp_dim=512, dim_head=64).cuda().train()
+    x1, y1 = V.make_inputs(6, B, G, input_dim=D)
+    x2, y2 = V.make_inputs(7, B, G, input_dim=D)
+    x1, y1, x2, y2 = (t.cuda() for t in (x1, y1, x2, y2))
+    f = torch.nn.functional.mse_loss
+    sep = []
+    for x, y in ((x1, y1), (x2, y2)):
+        m.zero_grad(set_to_none=True)
+        f(m(x), y).backward()
+        sep.append([p.grad.clone() for p in m.parameters()])
+    m.zero_grad(set_to_none=True)
+    (f(m(x1), y1) + f(m(x2), y2)).backward()
+    for p, a, b in zip(m.parameters(), sep[0], sep[1]):
+        want = a + b
+        assert torch.allclose(p.grad, want, rtol=2e-4, atol=1e-6 * float(want.abs().max()) + 1e-12)
+    assert any((a - b).abs().max() > 0 for a, b in zip(sep[0], sep[1]))          # the two passes really differ
+
+
+@pytest.mark.gpu
+def test_trainer_keeps_adam_state_across_a_noop_move():
+    """model.to(device) in the middle of training must not reset the fused trainer's Adam moments (torch.optim keeps its state)."""
+    from oracle import vis_oracle as V
+    from sequoia_pub_b200.train import FusedTrainer
+    D, G, B, depth = 1024, 130, 2, 1
+    sd = V.make_state_dict(5, G, input_dim=D, depth=depth)
+    batches = [V.make_inputs(20 + s, B, G, input_dim=D) for s in range(3)]
+    runs = []
+    for move in (False, True):
+        m = _model(sd, G, D, depth).train()
+        tr = FusedTrainer(m, lr=1e-3)
+        for s, (x, y) in enumerate(batches):
+            if move and s == 2:
+                m.to("cuda")                     # nothing moves
+                m.float()
+            tr.step(x.cuda(), y.cuda())
+        runs.append(torch.cat([p.detach().reshape(-1) for p in m.parameters()]).clone())
+    assert torch.equal(runs[0], runs[1])
+    want = V.train_steps(sd, batches)
+    assert abs(tr.loss.item() - want[-1]) / want[-1] < 2e-4
