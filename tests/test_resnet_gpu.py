@@ -76,7 +76,8 @@ def test_train_mode_and_bad_shapes_fail_loudly():
         m.train(); m.forward_extract(torch.zeros(1, 3, 256, 256, device="cuda"))
     m.eval()
     with pytest.raises(RuntimeError):
-        m.forward_extract(torch.zeros(1, 3, 224, 224, device="cuda"))
+        m.forward_extract(torch.zeros(1, 3, 512, 512, device="cuda"))       # 16x16 final map: the pooled output would not be [B, 2048]
+    assert m.forward_extract(torch.zeros(1, 3, 224, 224, device="cuda")).shape == (1, 2048)
 
 
 @pytest.mark.gpu
