@@ -120,6 +120,17 @@ SQ_API int sq_resnet50_extract(const void* input, int input_kind, int batch, int
                                const float* shifts, float* features, void* workspace, size_t workspace_bytes,
                                void* stream);
 
+/* Opt-in split-precision ("bf16x3") extraction: same interface, every convolution computed as hi*hi + hi*lo + lo*hi with fp32
+ * residuals (~1e-5 from the fp64 reference instead of 1.4e-3 for plain bf16 operands, at roughly a fifth of the throughput).
+ * Exists to QUANTIFY what the bf16 operands of sq_resnet50_extract cost downstream; 256x256 patches only.
+ * sq_resnet50_prepack_planes also writes the lo plane of the folded weights (same element count as packed_w). */
+SQ_API int sq_resnet50_prepack_planes(const void* const* tensors, void* packed_w, void* packed_w_lo, float* shifts, float bn_eps,
+                                      void* stream);
+SQ_API size_t sq_resnet50_hp_workspace_bytes(int batch, int H, int W);
+SQ_API int sq_resnet50_extract_hp(const void* input, int input_kind, int batch, int H, int W, const void* packed_w,
+                                  const void* packed_w_lo, const float* shifts, float* features, void* workspace,
+                                  size_t workspace_bytes, void* stream);
+
 /* One bottleneck convolution on the CTA-pair tcgen05 kernel (csrc/convgemm.cuh):
  *   out = act(conv(in, weight) + shift [+ residual]),  NHWC bf16 in / out, weight [Cout][R][S][Cin] bf16 (BatchNorm scale folded),
  *   shift fp32 [Cout], residual bf16 [batch*Ho*Wo, Cout] or NULL.  Cin and Cout multiples of 64.

@@ -76,6 +76,10 @@ SIGNATURES = {
     "sq_resnet50_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "sq_resnet50_extract": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                     c_size_t, c_void_p]),
+    "sq_resnet50_prepack_planes": (c_int, [C.POINTER(c_void_p), c_void_p, c_void_p, c_void_p, c_float, c_void_p]),
+    "sq_resnet50_hp_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "sq_resnet50_extract_hp": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                       c_size_t, c_void_p]),
     "sq_vis_param_table_len": (c_int, [C.POINTER(VisConfig)]),
     "sq_vis_param_layout": (c_int, [C.POINTER(VisConfig), C.POINTER(c_ll), c_int, C.POINTER(c_ll)]),
     "sq_vis_act_bytes": (c_size_t, [C.POINTER(VisConfig), c_int]),

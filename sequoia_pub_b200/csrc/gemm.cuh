@@ -1058,7 +1058,7 @@ inline int gemm_launch(const GemmArgs& g, cudaStream_t st) {
     if (g.conv.enabled) {
         const ConvGeom& c = g.conv;
         if (c.C % 64 != 0) { set_error("conv: C=%d must be a multiple of 64", c.C); return -1; }
-        if (g.A.mn_major || g.nterms != 1) { set_error("conv: A must be NHWC, single term"); return -1; }
+        if (g.A.mn_major) { set_error("conv: A must be NHWC"); return -1; }
         int BW = c.Wo, BH, BIMG = 1;
         if (BW > 128 || 128 % BW != 0) { set_error("conv: Wo=%d must divide 128", c.Wo); return -1; }
         BH = 128 / BW;
@@ -1073,7 +1073,8 @@ inline int gemm_launch(const GemmArgs& g, cudaStream_t st) {
         cuuint32_t box[4] = {64, (cuuint32_t)(BW * c.stride), (cuuint32_t)(BH * c.stride), (cuuint32_t)BIMG};
         cuuint32_t estr[4] = {1, (cuuint32_t)c.stride, (cuuint32_t)c.stride, 1};
         if (encode_map(&maps[0], g.A.hi, 4, dims, strides, box, estr)) return -1;
-        maps[1] = maps[0];
+        if (g.nterms == 3) { if (encode_map(&maps[1], g.A.lo, 4, dims, strides, box, estr)) return -1; }      // split precision: the lo plane of the NHWC input
+        else maps[1] = maps[0];
     } else {
         kp.nk = (g.K + GEMM_BK - 1) / GEMM_BK;
         if (make_operand_map(&maps[0], g.A.hi, g.A.mn_major, g.A.ld, g.M, g.a_koff_per_ntile ? (int)g.A.ld : g.K, GEMM_BM)) return -1;

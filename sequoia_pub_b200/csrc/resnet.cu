@@ -53,7 +53,7 @@ static const ResNetPlan& plan() {
 // OIHW fp32 + BN(gamma, beta, mean, var) -> [O][R][S][I] bf16 (scale folded) + fp32 shift
 __global__ void fold_bn_kernel(const float* __restrict__ w, const float* __restrict__ gamma, const float* __restrict__ beta,
                                const float* __restrict__ mean, const float* __restrict__ var, float eps, int cout, int cin, int k,
-                               int kpad /*0 = dense*/, bf16* __restrict__ wp, float* __restrict__ shift) {
+                               int kpad /*0 = dense*/, bf16* __restrict__ wp, float* __restrict__ shift, bf16* __restrict__ wlo = nullptr) {
     const int kk = k * k * cin;
     const int row = kpad ? kpad : kk;
     const long long n = (long long)cout * row;
@@ -69,7 +69,9 @@ __global__ void fold_bn_kernel(const float* __restrict__ w, const float* __restr
             const int c = j % cin; const int rs = j / cin; const int s = rs % k; const int r = rs / k;
             v = w[(((long long)o * cin + c) * k + r) * k + s] * sc;
         }
-        wp[i] = __float2bfloat16_rn(v);
+        const bf16 hi = __float2bfloat16_rn(v);
+        wp[i] = hi;
+        if (wlo) wlo[i] = __float2bfloat16_rn(v - __bfloat162float(hi));       // split-precision mode: w = hi + lo
         if (j == 0) shift[o] = beta[o] - mean[o] * sc;
     }
 }
@@ -455,7 +457,13 @@ int sq_resnet50_conv_info(int idx, int* cin, int* cout, int* k, int* stride, int
     return 0;
 }
 
+int sq_resnet50_prepack_planes(const void* const* tensors, void* packed_w, void* packed_w_lo, float* shifts, float bn_eps, void* stream);
+
 int sq_resnet50_prepack(const void* const* tensors, void* packed_w, float* shifts, float bn_eps, void* stream) {
+    return sq_resnet50_prepack_planes(tensors, packed_w, nullptr, shifts, bn_eps, stream);
+}
+
+int sq_resnet50_prepack_planes(const void* const* tensors, void* packed_w, void* packed_w_lo, float* shifts, float bn_eps, void* stream) {
     const ResNetPlan& p = plan();
     cudaStream_t st = (cudaStream_t)stream;
     for (int i = 0; i < 53; ++i) {
@@ -465,7 +473,7 @@ int sq_resnet50_prepack(const void* const* tensors, void* packed_w, float* shift
         const long long n = (long long)c.cout * (i == 0 ? STEM_K : c.k * c.k * c.cin);
         int blocks = (int)((n + 255) / 256); if (blocks > 4096) blocks = 4096;
         fold_bn_kernel<<<blocks, 256, 0, st>>>(t[0], t[1], t[2], t[3], t[4], bn_eps, c.cout, c.cin, c.k, i == 0 ? STEM_K : 0,
-                                               (bf16*)packed_w + c.w_off, shifts + c.s_off);
+                                               (bf16*)packed_w + c.w_off, shifts + c.s_off, packed_w_lo ? (bf16*)packed_w_lo + c.w_off : nullptr);
     }
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) { set_error("prepack: %s", cudaGetErrorString(err)); return -1; }
@@ -570,6 +578,170 @@ int sq_resnet50_extract(const void* input, int input_kind, int batch, int H, int
     }
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) { set_error("resnet50_extract: %s", cudaGetErrorString(err)); return -1; }
+    return 0;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------ split-precision extraction
+// Opt-in HIGH-PRECISION mode (quantifies what bf16 operands cost): every tensor is carried as fp32 plus bf16 hi / lo planes, every
+// convolution is three tcgen05 MMA groups (hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM) through the generic kernel of gemm.cuh,
+// residuals are added in fp32.  ~1e-5 from the fp64 reference (bf16 operands: 1.4e-3) at about a fifth of the throughput.
+namespace sq {
+
+// im2col of the stem as hi / lo planes: K index = r*24 + s*3 + c (21 taps + 3 zeros per filter row), zeros up to 192
+__global__ void stem_im2col_planes_kernel(const void* __restrict__ in, int kind, int batch, int H, int W, int Ho, int Wo, bf16* __restrict__ col_hi,
+                                          bf16* __restrict__ col_lo) {
+    const long long total = (long long)batch * Ho * Wo * (STEM_K / 8);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int k8 = (int)(i % (STEM_K / 8)) * 8; long long t = i / (STEM_K / 8);
+        const int ow = (int)(t % Wo); t /= Wo; const int oh = (int)(t % Ho); const int img = (int)(t / Ho);
+        __align__(16) bf16 hi[8]; __align__(16) bf16 lo[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int k = k8 + u, r = k / 24, q = k - r * 24;
+            float v = 0.f;
+            if (r < 7 && q < 21) {
+                const int s_ = q / 3, c = q - s_ * 3, ih = oh * 2 - 3 + r, iw = ow * 2 - 3 + s_;
+                if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
+                    if (kind == 0) {
+                        const uint8_t b = reinterpret_cast<const uint8_t*>(in)[(((long long)img * H + ih) * W + iw) * 3 + c];
+                        const float mu = c == 0 ? 0.485f : (c == 1 ? 0.456f : 0.406f), sd = c == 0 ? 0.229f : (c == 1 ? 0.224f : 0.225f);
+                        v = (static_cast<float>(b) / 255.0f - mu) / sd;
+                    } else {
+                        v = reinterpret_cast<const float*>(in)[(((long long)img * 3 + c) * H + ih) * W + iw];
+                    }
+                }
+            }
+            hi[u] = __float2bfloat16_rn(v); lo[u] = __float2bfloat16_rn(v - __bfloat162float(hi[u]));
+        }
+        *reinterpret_cast<uint4*>(col_hi + i * 8) = *reinterpret_cast<const uint4*>(hi);
+        *reinterpret_cast<uint4*>(col_lo + i * 8) = *reinterpret_cast<const uint4*>(lo);
+    }
+}
+
+// 3x3 stride-2 pad-1 max pool on the fp32 map -> fp32 + planes
+__global__ void maxpool3x3s2_f32_kernel(const float* __restrict__ in, float* __restrict__ out, bf16* __restrict__ out_hi, bf16* __restrict__ out_lo,
+                                        int batch, int H, int W, int C) {
+    const int Ho = H / 2, Wo = W / 2;
+    const long long n = (long long)batch * Ho * Wo * C;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C); long long t = i / C;
+        const int ow = (int)(t % Wo); t /= Wo; const int oh = (int)(t % Ho); const int img = (int)(t / Ho);
+        float m = -INFINITY;
+        for (int r = 0; r < 3; ++r) {
+            const int ih = oh * 2 - 1 + r; if (ih < 0 || ih >= H) continue;
+            for (int s_ = 0; s_ < 3; ++s_) {
+                const int iw = ow * 2 - 1 + s_; if (iw < 0 || iw >= W) continue;
+                m = fmaxf(m, in[(((long long)img * H + ih) * W + iw) * C + c]);
+            }
+        }
+        out[i] = m;
+        const bf16 h = __float2bfloat16_rn(m);
+        out_hi[i] = h; out_lo[i] = __float2bfloat16_rn(m - __bfloat162float(h));
+    }
+}
+
+struct HpBuf { float* f; bf16* hi; bf16* lo; };
+struct HpWs { size_t col_hi, col_lo, stem_f, stem_hi, stem_lo, big_f[3], big_hi[3], big_lo[3], small_hi[2], small_lo[2], fmap, total; };
+
+static HpWs hp_layout(int batch, int H, int W) {
+    HpWs w; size_t off = 0;
+    const size_t Ho = H / 2, Wo = W / 2, Hp = H / 4, Wp = W / 4;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
+    w.col_hi = take((size_t)batch * Ho * Wo * STEM_K * 2); w.col_lo = take((size_t)batch * Ho * Wo * STEM_K * 2);
+    w.stem_f = take((size_t)batch * Ho * Wo * 64 * 4); w.stem_hi = take((size_t)batch * Ho * Wo * 64 * 2); w.stem_lo = take((size_t)batch * Ho * Wo * 64 * 2);
+    for (int i = 0; i < 3; ++i) { w.big_f[i] = take((size_t)batch * Hp * Wp * 256 * 4); w.big_hi[i] = take((size_t)batch * Hp * Wp * 256 * 2); w.big_lo[i] = take((size_t)batch * Hp * Wp * 256 * 2); }
+    for (int i = 0; i < 2; ++i) { w.small_hi[i] = take((size_t)batch * Hp * Wp * 128 * 2); w.small_lo[i] = take((size_t)batch * Hp * Wp * 128 * 2); }
+    w.fmap = take((size_t)batch * (H / 32) * (W / 32) * 2048 * 4);
+    w.total = off;
+    return w;
+}
+
+// one split-precision convolution: planes in, fp32 (optional) + planes (optional) out
+static int run_conv_hp(const ConvSpec& c, const bf16* w_hi, const bf16* w_lo, const float* sbase, HpBuf in, int batch, int H, int W, HpBuf out,
+                       const float* res_f32, bool relu, cudaStream_t st, int* Ho_out, int* Wo_out) {
+    const int Ho = (H + 2 * c.pad - c.k) / c.stride + 1, Wo = (W + 2 * c.pad - c.k) / c.stride + 1;
+    GemmArgs g; memset(&g, 0, sizeof(g));
+    g.M = batch * Ho * Wo; g.N = c.cout; g.K = c.k * c.k * c.cin;
+    g.A.hi = in.hi; g.A.lo = in.lo; g.A.ld = c.cin;
+    g.B.hi = w_hi + c.w_off; g.B.lo = w_lo + c.w_off; g.B.ld = g.K;
+    g.nterms = 3;
+    g.conv.enabled = (c.k == 1 && c.stride == 1) ? 0 : 1; g.conv.batch = batch; g.conv.H = H; g.conv.W = W; g.conv.C = c.cin; g.conv.Ho = Ho; g.conv.Wo = Wo;
+    g.conv.R = c.k; g.conv.S = c.k; g.conv.stride = c.stride; g.conv.pad = c.pad;
+    g.e.bias = sbase + c.s_off;
+    g.e.out_f32 = out.f; g.e.ld_f32 = c.cout;
+    g.e.out_hi = out.hi; g.e.out_lo = out.lo; g.e.ld_bf = c.cout;
+    g.e.res_f32 = res_f32; g.e.ld_res = c.cout;
+    g.e.act = relu ? ACT_RELU : ACT_NONE; g.e.alpha = 1.0f; g.e.rowbias_div = 1;
+    *Ho_out = Ho; *Wo_out = Wo;
+    return gemm_launch(g, st);
+}
+
+}  // namespace sq
+
+extern "C" {
+
+size_t sq_resnet50_hp_workspace_bytes(int batch, int H, int W) { return hp_layout(batch, H, W).total; }
+
+int sq_resnet50_extract_hp(const void* input, int input_kind, int batch, int H, int W, const void* packed_w, const void* packed_w_lo,
+                           const float* shifts, float* features, void* workspace, size_t workspace_bytes, void* stream) {
+    if (batch <= 0) return 0;
+    if (H != 256 || W != 256) { set_error("resnet50_extract_hp: the split-precision mode supports 256x256 patches only (got %dx%d)", H, W); return -1; }
+    if (!packed_w_lo) { set_error("resnet50_extract_hp: needs the lo plane of the weights (sq_resnet50_prepack_planes)"); return -1; }
+    const HpWs L = hp_layout(batch, H, W);
+    if (!workspace || workspace_bytes < L.total) { set_error("resnet50_extract_hp: workspace %zu < %zu", workspace_bytes, L.total); return -1; }
+    const ResNetPlan& p = plan();
+    cudaStream_t st = (cudaStream_t)stream;
+    uint8_t* ws = (uint8_t*)workspace;
+    const bf16* wh = (const bf16*)packed_w; const bf16* wl = (const bf16*)packed_w_lo;
+    const int Ho = H / 2, Wo = W / 2;
+    int h = Ho / 2, w = Wo / 2;
+    HpBuf col = {nullptr, (bf16*)(ws + L.col_hi), (bf16*)(ws + L.col_lo)};
+    HpBuf stem = {(float*)(ws + L.stem_f), (bf16*)(ws + L.stem_hi), (bf16*)(ws + L.stem_lo)};
+    HpBuf big[3], small_[2];
+    for (int i = 0; i < 3; ++i) big[i] = HpBuf{(float*)(ws + L.big_f[i]), (bf16*)(ws + L.big_hi[i]), (bf16*)(ws + L.big_lo[i])};
+    for (int i = 0; i < 2; ++i) small_[i] = HpBuf{nullptr, (bf16*)(ws + L.small_hi[i]), (bf16*)(ws + L.small_lo[i])};
+    float* fmap = (float*)(ws + L.fmap);
+    {
+        const long long total = (long long)batch * Ho * Wo * (STEM_K / 8);
+        long long blocks = (total + 255) / 256; if (blocks > 148LL * 64) blocks = 148LL * 64;
+        stem_im2col_planes_kernel<<<(unsigned)blocks, 256, 0, st>>>(input, input_kind, batch, H, W, Ho, Wo, col.hi, col.lo);
+        GemmArgs g; memset(&g, 0, sizeof(g));
+        g.M = batch * Ho * Wo; g.N = 64; g.K = STEM_K;
+        g.A.hi = col.hi; g.A.lo = col.lo; g.A.ld = STEM_K; g.B.hi = wh + p.conv[0].w_off; g.B.lo = wl + p.conv[0].w_off; g.B.ld = STEM_K; g.nterms = 3;
+        g.e.bias = shifts + p.conv[0].s_off; g.e.out_f32 = stem.f; g.e.ld_f32 = 64; g.e.act = ACT_RELU; g.e.alpha = 1.0f; g.e.rowbias_div = 1;
+        if (gemm_launch(g, st)) return -1;
+        const long long n = (long long)batch * h * w * 64;
+        maxpool3x3s2_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(stem.f, big[0].f, big[0].hi, big[0].lo, batch, Ho, Wo, 64);
+    }
+    const int blocks[4] = {3, 4, 6, 3};
+    int ci = 1; int x = 0;
+    for (int stg = 0; stg < 4; ++stg)
+        for (int b = 0; b < blocks[stg]; ++b) {
+            const bool last = (stg == 3 && b == blocks[3] - 1);
+            const bool down = (b == 0);
+            int h1, w1, h2, w2, h3, w3, hd, wd;
+            if (run_conv_hp(p.conv[ci], wh, wl, shifts, big[x], batch, h, w, small_[0], nullptr, true, st, &h1, &w1)) return -1;
+            if (run_conv_hp(p.conv[ci + 1], wh, wl, shifts, small_[0], batch, h1, w1, small_[1], nullptr, true, st, &h2, &w2)) return -1;
+            const float* res = big[x].f;
+            const int y = (x + 1) % 3, d = (x + 2) % 3;
+            if (down) {
+                HpBuf dso = {big[d].f, nullptr, nullptr};
+                if (run_conv_hp(p.conv[ci + 3], wh, wl, shifts, big[x], batch, h, w, dso, nullptr, false, st, &hd, &wd)) return -1;
+                res = big[d].f;
+            }
+            HpBuf o3 = last ? HpBuf{fmap, nullptr, nullptr} : big[y];
+            if (run_conv_hp(p.conv[ci + 2], wh, wl, shifts, small_[1], batch, h2, w2, o3, res, true, st, &h3, &w3)) return -1;
+            x = y; h = h3; w = w3;
+            ci += down ? 4 : 3;
+        }
+    {
+        const long long n = (long long)batch * 2048;
+        avgpool7_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(fmap, features, batch, h, w, 2048);
+    }
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) { set_error("resnet50_extract_hp: %s", cudaGetErrorString(err)); return -1; }
     return 0;
 }
 

@@ -69,6 +69,8 @@ class ResNet(nn.Module):
                 m.bias.data.zero_()
         self._packed = None          # (versions, packed_w, shifts)
         self._workspace = None
+        self._packed_hp = None       # (versions, hi, lo, shifts) for precision="bf16x3"
+        self._workspace_hp = None
         self._lanes = None           # [(stream, workspace)] for extract_many
 
     def _stage(self, planes, blocks, stride):
@@ -112,6 +114,42 @@ class ResNet(nn.Module):
                                          _lib.stream_ptr()))
         self._packed = (key, packed_w, shifts)
         return packed_w, shifts
+
+    def _prepack_planes(self):
+        """hi + lo planes of the folded weights for the split-precision mode (`precision="bf16x3"`)."""
+        tensors = []
+        for conv, bn in self._conv_bn_pairs():
+            tensors += [conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var]
+        key = tuple((t.data_ptr(), t._version) for t in tensors)
+        if self._packed_hp is not None and self._packed_hp[0] == key:
+            return self._packed_hp[1:]
+        dev = self.conv1.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("sequoia_b200 ResNet runs on a B200 only: call .to('cuda') first (no CPU fallback)")
+        L = _lib.lib()
+        hi = torch.empty(L.sq_resnet50_packed_weight_elems(), dtype=torch.bfloat16, device=dev)
+        lo = torch.empty_like(hi)
+        shifts = torch.empty(L.sq_resnet50_shift_elems(), dtype=torch.float32, device=dev)
+        table = (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+        _lib.check(L.sq_resnet50_prepack_planes(table, _lib.ptr(hi), _lib.ptr(lo), _lib.ptr(shifts), C.c_float(self.bn1.eps), _lib.stream_ptr()))
+        self._packed_hp = (key, hi, lo, shifts)
+        return hi, lo, shifts
+
+    def _run_hp(self, inp, kind, batch, H, W, out=None):
+        """Split-precision forward (hi*hi + hi*lo + lo*hi, fp32 residuals): the opt-in mode that brackets the bf16 default."""
+        if self.training:
+            raise RuntimeError("sequoia_b200 ResNet implements eval-mode BatchNorm only; call .eval()")
+        _lib.require_device()
+        hi, lo, shifts = self._prepack_planes()
+        L = _lib.lib()
+        need = L.sq_resnet50_hp_workspace_bytes(batch, H, W)
+        if self._workspace_hp is None or self._workspace_hp.numel() < need or self._workspace_hp.device != inp.device:
+            self._workspace_hp = torch.empty(need, dtype=torch.uint8, device=inp.device)
+        if out is None:
+            out = torch.empty(batch, 2048, dtype=torch.float32, device=inp.device)
+        _lib.check(L.sq_resnet50_extract_hp(_lib.ptr(inp), kind, batch, H, W, _lib.ptr(hi), _lib.ptr(lo), _lib.ptr(shifts), _lib.ptr(out),
+                                            _lib.ptr(self._workspace_hp), self._workspace_hp.numel(), _lib.stream_ptr()))
+        return out
 
     def _run(self, inp, kind, batch, H, W, out=None, workspace=None):
         if self.training:
@@ -183,11 +221,17 @@ class ResNet(nn.Module):
         return self._run(x, 1, x.shape[0], x.shape[2], x.shape[3])
 
     @torch.no_grad()
-    def extract_uint8(self, patches, out=None):
-        """patches: uint8 [B,H,W,3] raw RGB tiles as stored in the patch HDF5 -> float32 [B,2048]."""
+    def extract_uint8(self, patches, out=None, precision="bf16"):
+        """patches: uint8 [B,H,W,3] raw RGB tiles as stored in the patch HDF5 -> float32 [B,2048].
+        precision "bf16" (default): bf16 tensor-core operands, fp32 accumulation (1.4e-3 from the fp64 reference);
+        "bf16x3": opt-in split-precision mode (~1e-5, about a fifth of the throughput, 256-px tiles, batches of <= 64)."""
         if patches.dim() != 4 or patches.shape[3] != 3 or patches.dtype != torch.uint8:
             raise ValueError("extract_uint8 expects uint8 [B,H,W,3]")
         patches = patches.contiguous()
+        if precision == "bf16x3":
+            return self._run_hp(patches, 0, patches.shape[0], patches.shape[1], patches.shape[2], out)
+        if precision != "bf16":
+            raise ValueError("precision must be 'bf16' or 'bf16x3'")
         return self._run(patches, 0, patches.shape[0], patches.shape[1], patches.shape[2], out)
 
     @torch.no_grad()
