@@ -215,6 +215,23 @@ SQ_API int sq_vit_backward(const sq_vit_config* cfg, const float* params, const 
                            int batch, void* act, size_t act_bytes, float* grads, float* dx, void* scratch, size_t scratch_bytes,
                            int stage_hi, int stage_lo, void* stream);
 
+/* Persistent GEMM kernels launch one CTA per SM and fill the register file, so nothing can co-reside with them.  While a
+ * communication kernel has to run beside them (data-parallel backward pass) the caller limits the GEMM grids to `sms` SMs;
+ * 0 restores the full device. */
+SQ_API int sq_set_sm_budget(int sms);
+
+/* ------------------------------------------------------------------ data-parallel gradient exchange
+ * In-place sum all-reduce of grads[begin, begin + count) over NVSwitch multicast (NVLS): `multicast_base` is the MULTICAST address
+ * of the symmetric flat gradient buffer (torch.distributed._symmetric_memory: hdl.multicast_ptr), `peer_flags` a HOST array of
+ * `world` device pointers to each rank's copy of a zero-initialised symmetric flag buffer of sq_multimem_flag_bytes(ctas) bytes
+ * (hdl.buffer_ptrs of that buffer).  `epoch` must grow by 2 per call on a flag buffer (the kernel uses epoch and epoch + 1).
+ * Every rank must enqueue the same sequence of calls.  begin and count in elements, multiples of 4.
+ * Replaces the one `loss.backward()` + DDP-style exchange the reference would need for multi-GPU training (it trains on one GPU,
+ * src/main.py:177). */
+SQ_API size_t sq_multimem_flag_bytes(int max_ctas);
+SQ_API int sq_multimem_allreduce_f32(void* multicast_base, long long begin, long long count, const void* const* peer_flags, int rank,
+                                     int world, unsigned int epoch, int ctas, void* stream);
+
 /* ------------------------------------------------------------------ per-step training metrics
  * Replaces sklearn mean_absolute_error + he2rna.compute_correlations of the training loop (src/vit.py:167-168,
  * src/he2rna.py:140-149) and evaluate()'s smape (src/vit.py:32-33,269).  labels, preds: fp32 [batch, num_outputs] (device).

@@ -65,6 +65,9 @@ SIGNATURES = {
     "sq_gemm_timing_read": (c_int, [C.POINTER(C.c_double), C.POINTER(c_ll), C.POINTER(C.c_double)]),
     "sq_gemm_profile": (c_int, [c_void_p]),
     "sq_side_stream_enable": (c_int, [c_int]),
+    "sq_set_sm_budget": (c_int, [c_int]),
+    "sq_multimem_flag_bytes": (c_size_t, [c_int]),
+    "sq_multimem_allreduce_f32": (c_int, [c_void_p, c_ll, c_ll, C.POINTER(c_void_p), c_int, c_int, C.c_uint, c_int, c_void_p]),
     "sq_split_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_ll, c_int, c_ll, c_ll, c_void_p]),
     "sq_gemm_bf16": (c_int, [C.POINTER(GemmDesc), c_void_p]),
     "sq_conv_bf16": (c_int, [C.POINTER(ConvDesc), c_void_p]),

@@ -16,13 +16,15 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+static int g_sm_budget = 0;         // 0 = all SMs; set by sq_set_sm_budget while communication kernels need room beside the persistent GEMMs
+
 int num_sms() {
     static int n = 0;
     if (n == 0) {
         int dev = 0;
         if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
     }
-    return n;
+    return (g_sm_budget > 0 && g_sm_budget < n) ? g_sm_budget : n;
 }
 
 PFN_encodeTiled get_encode_fn() {
@@ -171,6 +173,8 @@ int sq_gemm_timing_read(double* total_ms, long long* launches, double* mma_flops
 }
 
 int sq_side_stream_enable(int on) { g_side_enabled = on ? 1 : 0; return 0; }
+
+int sq_set_sm_budget(int sms) { g_sm_budget = sms > 0 ? sms : 0; return 0; }
 
 int sq_gemm_profile(void* device_buffer) { g_prof = (unsigned long long*)device_buffer; return 0; }
 

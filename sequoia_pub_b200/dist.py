@@ -51,3 +51,42 @@ def split_batch(batch, rank, world):
         raise ValueError(f"global batch {batch} is not divisible by world size {world}")
     per = batch // world
     return slice(rank * per, (rank + 1) * per)
+
+
+class MultimemAllReduce:
+    """Flat fp32 gradient buffer in symmetric memory with an NVSwitch multicast mapping + the in-place all-reduce over it
+    (`sq_multimem_allreduce_f32`, csrc/comm.cu: one multimem.ld_reduce and one multimem.st per 16 bytes, a handful of CTAs).
+    torch.distributed._symmetric_memory only allocates and exchanges the handles (plumbing); raises RuntimeError when the
+    platform has no multicast support (then the trainer keeps NCCL)."""
+
+    def __init__(self, numel, device, group=None, ctas=8):
+        import torch.distributed._symmetric_memory as symm
+        group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.ctas = int(ctas)
+        self.buf = symm.empty(numel, dtype=torch.float32, device=device)
+        self.buf.zero_()
+        self.hdl = symm.rendezvous(self.buf, group)
+        mc = int(self.hdl.multicast_ptr or 0)
+        if mc == 0:
+            raise RuntimeError("sequoia_b200: no NVSwitch multicast support for symmetric memory on this system")
+        if int(getattr(self.hdl, "offset", 0) or 0) != 0:
+            raise RuntimeError("sequoia_b200: symmetric gradient buffer is not at the start of its multicast allocation")
+        self.mc_ptr = mc
+        nflag = _lib.lib().sq_multimem_flag_bytes(self.ctas) // 4
+        self.flags = symm.empty(nflag, dtype=torch.int32, device=device)
+        self.flags.zero_()
+        self.fhdl = symm.rendezvous(self.flags, group)
+        if int(getattr(self.fhdl, "offset", 0) or 0) != 0:
+            raise RuntimeError("sequoia_b200: symmetric flag buffer is not at the start of its allocation")
+        ptrs = [int(p) for p in self.fhdl.buffer_ptrs]
+        self._peer_flags = (C.c_void_p * self.world)(*ptrs)
+        self.epoch = 1
+        torch.cuda.synchronize(device)
+        dist.barrier(group)                      # every rank's flags are zero before the first kernel signals
+
+    def allreduce(self, begin, end):
+        """Enqueues the all-reduce of buf[begin:end] on the current stream (every rank must issue the same sequence)."""
+        _lib.check(_lib.lib().sq_multimem_allreduce_f32(C.c_void_p(self.mc_ptr), begin, end - begin, self._peer_flags, self.rank, self.world,
+                                                        self.epoch, self.ctas, _lib.stream_ptr(self.buf)))
+        self.epoch += 2
