@@ -28,7 +28,7 @@ struct CgParams {
     int conv, cblocks, S, stride, pad, tiles_per_img, BH, BIMG;
     int tiles_x, Ho, halo_bo;   // halo mode: 8-pixel-wide tiles per output row, output height, descriptor base-offset mode
     const float* bias;   // [N] folded BatchNorm shift
-    int relu, has_res;
+    int relu, has_res;   // relu: activation, 0 none, 1 ReLU, 2 exact GELU
     float* pool_out;     // non-null: instead of storing the tile, add mean over the top-left 7x7 of each 8x8 image map into pool_out[img][N] (src/resnet.py:110,166)
     int batch;
     int l2pf;            // prefetch residual sub-tiles into L2 two tiles ahead
@@ -263,7 +263,7 @@ convgemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         uint8_t* myring = ring + ew * D * Cfg::SUB_BYTES;
         uint64_t* myfull = res_full + ew * D;
         const bool has_res = p.has_res != 0;
-        const float relu_lo = p.relu ? 0.0f : -INFINITY;
+        const float relu_lo = p.relu == 1 ? 0.0f : -INFINITY;
         const int n_items = my_tiles * Cfg::CPH;
         const uint32_t rowoff = (uint32_t)lane * 128u, swz = (uint32_t)(lane & 7);
         // residual prefetch cursor (lane 0): item pf_j = (tile pf_ti, chunk pf_cc), ring slot pf_slot
@@ -344,8 +344,13 @@ convgemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                             f[2 * u + 1] += __uint_as_float(w[u] & 0xffff0000u);
                         }
                     }
+                    if (p.relu == 2) {                       // exact GELU (UNI's fc1, compute_features_hdf5.py:63-66: timm nn.GELU)
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) f[u] = fmaxf(f[u], relu_lo);
+                        for (int u = 0; u < 8; ++u) f[u] = gelu_f(f[u]);
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) f[u] = fmaxf(f[u], relu_lo);
+                    }
                 }
                 if (p.pool_out) {
                     // fused AvgPool2d(7) of the final 8x8 map: a 128-row tile is two images, this warp's 32 rows are image rows
@@ -427,7 +432,7 @@ struct ConvGemmArgs {
     const float* bias;
     const bf16* res;             // [M][N] or null
     bf16* out;                   // [M][N]
-    int relu;
+    int relu;                    // 0 none, 1 ReLU, 2 exact GELU
     ConvGeom conv;
     int block_n;                 // 0 = auto
     int cta_group;               // 0 = auto

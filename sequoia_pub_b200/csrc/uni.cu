@@ -6,7 +6,7 @@
 // accumulation, like the ResNet path); weights pre-cast to bf16 with the LayerScale gammas folded into proj / fc2.
 // Per block: LN -> qkv GEMM(+bias) -> fused softmax attention (mma.sync bf16, one CTA per (image, head)) ->
 // proj GEMM(+bias, +residual) -> LN -> fc1 GEMM(+bias, GELU) -> fc2 GEMM(+bias, +residual).
-#include "gemm.cuh"
+#include "convgemm.cuh"
 #include "../../include/sequoia_b200.h"
 
 namespace sq {
@@ -255,6 +255,13 @@ static void uni_ws_layout(int batch, UniWs* w) {
 
 static int uni_gemm(int M, int N, int K, const bf16* a, const bf16* w, const float* bias, const float* res, float* out_f32, bf16* out_bf, int act,
                     cudaStream_t st) {
+    // bf16 -> bf16 GEMMs with a bias (qkv, fc1 + GELU: 7/12 of the model's FLOPs) run on the CTA-pair kernel with the TMA epilogue
+    static const int use_cg = getenv("SQ_UNI_CONVGEMM") ? atoi(getenv("SQ_UNI_CONVGEMM")) : 1;
+    if (use_cg && out_bf && !out_f32 && !res && bias && (act == ACT_NONE || act == ACT_GELU) && N % 64 == 0 && K % 64 == 0) {
+        ConvGemmArgs c; memset(&c, 0, sizeof(c));
+        c.M = M; c.N = N; c.K = K; c.A = a; c.lda = K; c.W = w; c.bias = bias; c.out = out_bf; c.relu = act == ACT_GELU ? 2 : 0;
+        if (convgemm_supported(c)) return convgemm_launch(c, st);
+    }
     GemmArgs g; memset(&g, 0, sizeof(g));
     g.M = M; g.N = N; g.K = K; g.nterms = 1;
     g.A.hi = a; g.A.ld = K; g.B.hi = w; g.B.ld = K;
