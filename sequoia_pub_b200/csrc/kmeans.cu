@@ -141,8 +141,8 @@ __global__ void __launch_bounds__(256) km_dist_kernel(const float* __restrict__ 
 // threads), and 8 lanes per row (lane = element index mod 8, or mod 4 for the 2-column kernel) add their elements in
 // ascending order.  Block boundaries of KM_NB elements fold the lanes: kind 0: (l + l+4) then (s0+s1)+(s2+s3).
 constexpr int KM_CHUNK = 1024;        // divides KM_NB; multiple of 8
-__device__ void km_gemv_order_block(const float* __restrict__ rows, int T, int n, float* __restrict__ stage /*[T][KM_CHUNK]*/,
-                                    float* __restrict__ pots) {
+__device__ void km_gemv_order_block(const float* rows, int T, int n, float* stage /*[T][KM_CHUNK]*/,
+                                    float* pots) {
     const int tid = threadIdx.x;
     const int t = tid >> 3, l = tid & 7;           // lane-threads: tid < 8*T
     const bool worker = t < T;
@@ -206,11 +206,10 @@ __device__ void km_gemv_order_block(const float* __restrict__ rows, int T, int n
 // sequential float32 cumsum -> next candidates by searchsorted(left) of uniform * pot.
 // step 0: `newc` holds the distances to the first centre (T_in = 1, potential through the sdot order).
 // dynamic shared memory: n floats (closest / cumsum) + KM_MAXT * KM_CHUNK floats (staging)
-__global__ void __launch_bounds__(1024) km_select_kernel(const float* __restrict__ newc, int T_in, int n, int step, int k, int T_next,
-                                                         const double* __restrict__ uniforms, float* __restrict__ closest, int* __restrict__ cand,
-                                                         int* __restrict__ chosen, float* __restrict__ pot_io) {
-    extern __shared__ float cs[];                  // n floats: closest, then its cumsum
-    float* stage = cs + ((n + 31) & ~31);
+__device__ void km_select_body(float* cs /* n floats: closest, then its cumsum */, float* stage /* KM_MAXT * KM_CHUNK floats */,
+                               const float* newc, int T_in, int n, int step, int k, int T_next,
+                               const double* __restrict__ uniforms, float* closest, int* cand,
+                               int* chosen, float* pot_io) {
     __shared__ float pots[KM_MAXT];
     __shared__ float acc16[64];
     __shared__ int s_best;
@@ -262,17 +261,26 @@ __global__ void __launch_bounds__(1024) km_select_kernel(const float* __restrict
     if (tid < KM_MAXT) counts[tid] = 0;
     __syncthreads();
     if (step + 1 >= k) return;
-    if (tid == 0) {                                  // np.cumsum(float32): strictly sequential
+    if (tid == 0) {                                  // np.cumsum(float32): strictly sequential adds; the loads run 16 elements ahead
         float a = 0.f;
         int i = 0;
-        for (; i + 8 <= n; i += 8) {
-            float v[8];
+        float4 nx[4];
+        if (n >= 16) {
 #pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = cs[i + u];
+            for (int u = 0; u < 4; ++u) nx[u] = *reinterpret_cast<const float4*>(cs + 4 * u);
+        }
+        for (; i + 16 <= n; i += 16) {
+            float v[16];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) { a = __fadd_rn(a, v[u]); v[u] = a; }
+            for (int u = 0; u < 4; ++u) { v[4 * u] = nx[u].x; v[4 * u + 1] = nx[u].y; v[4 * u + 2] = nx[u].z; v[4 * u + 3] = nx[u].w; }
+            if (i + 32 <= n) {
 #pragma unroll
-            for (int u = 0; u < 8; ++u) cs[i + u] = v[u];
+                for (int u = 0; u < 4; ++u) nx[u] = *reinterpret_cast<const float4*>(cs + i + 16 + 4 * u);
+            }
+#pragma unroll
+            for (int u = 0; u < 16; ++u) { a = __fadd_rn(a, v[u]); v[u] = a; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) *reinterpret_cast<float4*>(cs + i + 4 * u) = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
         }
         for (; i < n; ++i) { a = __fadd_rn(a, cs[i]); cs[i] = a; }
     }
@@ -288,6 +296,129 @@ __global__ void __launch_bounds__(1024) km_select_kernel(const float* __restrict
     __syncthreads();
     if (tid < T_next) cand[tid] = min(counts[tid], n - 1);
 }
+
+__global__ void __launch_bounds__(1024) km_select_kernel(const float* __restrict__ newc, int T_in, int n, int step, int k, int T_next,
+                                                         const double* __restrict__ uniforms, float* __restrict__ closest, int* __restrict__ cand,
+                                                         int* __restrict__ chosen, float* __restrict__ pot_io) {
+    extern __shared__ float km_sel_smem[];
+    km_select_body(km_sel_smem, km_sel_smem + ((n + 31) & ~31), newc, T_in, n, step, k, T_next, uniforms, closest, cand, chosen, pot_io);
+}
+
+// ---------------------------------------------------------------- selection step, second version (steps >= 1)
+// The T candidate rows are staged in shared memory ONCE (the first version re-staged them chunk by chunk for the BLAS-order sums and
+// then copied and accumulated the winner); the BLAS-order potentials (threads 0 .. 8T-1) run BESIDE the T sequential float32 cumsums
+// (lanes 0 .. T-1 of one warp in lockstep, one row each, loads 16 elements ahead of the add chain, results streamed to global memory),
+// so the serial part of a step is ONE 4096-add chain instead of potentials + copy + cumsum.  Same arithmetic, same orders.
+__device__ void km_gemv_order_smem(const float* rows, int T, int n, int ns, float* pots) {
+    const int tid = threadIdx.x;
+    const int t = tid >> 3, l = tid & 7;
+    const bool worker = t < T;
+    const unsigned wmask = __ballot_sync(0xffffffffu, worker);      // called by whole warps
+    if (!worker) return;
+    const int rem = T & 3;
+    int kind = 0;
+    if (t >= T - rem) { const int rr = t - (T - rem); kind = ((rem & 2) && rr < 2) ? 1 : 0; }
+    const int m1 = n - (n & 3);
+    const float* a = rows + (size_t)t * ns;
+    float y = 0.f;
+    for (int b0 = 0; b0 < m1; b0 += KM_NB) {
+        const int len = min(KM_NB, m1 - b0);
+        float acc = 0.f;
+        const int lead = (len & 4) ? 4 : 0;
+        if (lead && l < 4) acc = a[b0 + l];
+        if (kind == 0) {
+#pragma unroll 8
+            for (int i = lead; i < len; i += 8) acc = __fadd_rn(acc, a[b0 + i + l]);
+        } else if (l < 4) {
+#pragma unroll 8
+            for (int i = lead; i < len; i += 4) acc = __fadd_rn(acc, a[b0 + i + l]);
+        }
+        const int base = (tid & 31) & ~7;
+        const float other = __shfl_sync(wmask, acc, base + ((l + 4) & 7));
+        const float sfold = kind == 0 ? __fadd_rn(acc, other) : acc;
+        const float p01 = __fadd_rn(__shfl_sync(wmask, sfold, base + 0), __shfl_sync(wmask, sfold, base + 1));
+        const float p23 = __fadd_rn(__shfl_sync(wmask, sfold, base + 2), __shfl_sync(wmask, sfold, base + 3));
+        y = __fadd_rn(y, __fadd_rn(p01, p23));
+    }
+    if (l == 0) {
+        if (n & 3) {
+            float tt = a[m1];
+            for (int i = m1 + 1; i < n; ++i) tt = __fadd_rn(tt, a[i]);
+            y = __fadd_rn(y, tt);
+        }
+        pots[t] = y;
+    }
+}
+
+__global__ void __launch_bounds__(1024) km_select2_kernel(const float* __restrict__ newc, int T, int n, int step, int k, const double* __restrict__ uniforms,
+                                                          float* __restrict__ closest, float* cum /* [T][n4], n4 = n rounded up to 4 */,
+                                                          int* __restrict__ cand, int* __restrict__ chosen, float* __restrict__ pot_io) {
+    extern __shared__ __align__(16) float rows_s[];        // [T][ns], ns = n rounded up to 4, plus 4: 16-byte aligned rows, 4 banks apart
+    __shared__ float pots[KM_MAXT];
+    __shared__ int s_best;
+    __shared__ float s_pot;
+    __shared__ int counts[KM_MAXT];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n4 = (n + 3) & ~3, ns = n4 + 4;
+    for (int e = tid; e < T * n; e += blockDim.x) { const int t = e / n, i = e - t * n; rows_s[(size_t)t * ns + i] = newc[e]; }
+    if (tid < KM_MAXT) counts[tid] = 0;
+    __syncthreads();
+    const int pot_warps = (8 * T + 31) / 32;
+    if (warp < pot_warps) {
+        km_gemv_order_smem(rows_s, T, n, ns, pots);
+    } else if (warp == pot_warps && lane < T && step + 1 < k) {
+        const float* a = rows_s + (size_t)lane * ns;
+        float* o = cum + (size_t)lane * n4;
+        float run = 0.f;
+        int i = 0;
+        float4 nx[4];
+        if (n >= 16) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) nx[u] = *reinterpret_cast<const float4*>(a + 4 * u);
+        }
+        for (; i + 16 <= n; i += 16) {
+            float cur[16];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { cur[4 * u] = nx[u].x; cur[4 * u + 1] = nx[u].y; cur[4 * u + 2] = nx[u].z; cur[4 * u + 3] = nx[u].w; }
+            if (i + 32 <= n) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) nx[u] = *reinterpret_cast<const float4*>(a + i + 16 + 4 * u);
+            }
+#pragma unroll
+            for (int u = 0; u < 16; ++u) { run = __fadd_rn(run, cur[u]); cur[u] = run; }
+#pragma unroll
+            for (int u = 0; u < 16; u += 4) *reinterpret_cast<float4*>(o + i + u) = make_float4(cur[u], cur[u + 1], cur[u + 2], cur[u + 3]);
+        }
+        for (; i < n; ++i) { run = __fadd_rn(run, a[i]); o[i] = run; }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int best = 0;
+        for (int t2 = 1; t2 < T; ++t2) if (pots[t2] < pots[best]) best = t2;      // np.argmin: first minimum
+        s_best = best; s_pot = pots[best];
+        chosen[step] = cand[best]; *pot_io = pots[best];
+    }
+    __syncthreads();
+    const int best = s_best;
+    const float pot = s_pot;
+    for (int i = tid; i < n; i += blockDim.x) closest[i] = rows_s[(size_t)best * ns + i];
+    if (step + 1 >= k) return;
+    const float* cb = cum + (size_t)best * n4;
+    for (int t = 0; t < T; ++t) {
+        const double rv = __dmul_rn(uniforms[(size_t)step * T + t], (double)pot);
+        int c = 0;
+        for (int i = tid; i < n; i += blockDim.x) c += ((double)cb[i] < rv) ? 1 : 0;     // searchsorted side='left'
+#pragma unroll
+        for (int o2 = 16; o2 > 0; o2 >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o2);
+        if ((tid & 31) == 0 && c) atomicAdd(&counts[t], c);
+    }
+    __syncthreads();
+    if (tid < T) cand[tid] = min(counts[tid], n - 1);
+}
+
+// (Measured and dropped in round 2: a distance kernel with the candidate rows staged as doubles in shared memory and four sample rows
+//  per warp - 7.89 vs 7.74 ms per slide, no gain, the kernel is L2-latency bound - and a persistent cooperative kernel running all k
+//  seeding steps with grid barriers - 9.4 ms, its selection step then runs on one 256-thread CTA.)
 
 // ---------------------------------------------------------------- Lloyd iterations
 __global__ void km_gather_centers_kernel(const float* __restrict__ Xc, const int* __restrict__ chosen, int k, int d, float* __restrict__ centers) {
@@ -567,11 +698,12 @@ __global__ void km_converge_kernel(const float* __restrict__ shift_part, int k, 
     if (done && cond_handle) cudaGraphSetConditional((cudaGraphConditionalHandle)cond_handle, 0);
 }
 
-struct KmWs { size_t xc, xx64, mean, var, closest, newc, cand, chosen, pot, cA, cB, csq, labels, labels_old, offsets, members, shift, flags, rdist, empty_ids, far, n_iter, total; };
+struct KmWs { size_t cum, xc, xx64, mean, var, closest, newc, cand, chosen, pot, cA, cB, csq, labels, labels_old, offsets, members, shift, flags, rdist, empty_ids, far, n_iter, total; };
 
 static void km_ws_layout(int n, int d, int k, KmWs* w) {
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) / 256 * 256; return o; };
+    w->cum = take((size_t)KM_MAXT * ((n + 3) & ~3) * 4);
     w->xc = take((size_t)n * d * 4); w->xx64 = take((size_t)n * 8); w->mean = take((size_t)d * 4); w->var = take((size_t)d * 4);
     w->closest = take((size_t)n * 4); w->newc = take((size_t)KM_MAXT * n * 4); w->cand = take(KM_MAXT * 4); w->chosen = take((size_t)k * 4);
     w->pot = take(4); w->cA = take((size_t)k * d * 4); w->cB = take((size_t)k * d * 4); w->csq = take((size_t)k * 4);
@@ -711,6 +843,12 @@ int sq_kmeans_fit(const float* features, int n, int d, int k, int trials, int fi
     } else {
         // ---- k-means++ (L180-279)
         cudaMemcpyAsync(cand, &first_center, sizeof(int), cudaMemcpyHostToDevice, st);
+        static const int sel2_on = getenv("SQ_KMEANS_SELECT_V2") ? atoi(getenv("SQ_KMEANS_SELECT_V2")) : 1;
+        const size_t sel2_smem = (size_t)trials * (((n + 3) & ~3) + 4) * sizeof(float);
+        const bool sel2 = sel2_on && sel2_smem <= 200 * 1024;
+        float* cum = (float*)(ws + L.cum);
+        static bool sel2_attr = false;
+        if (sel2 && !sel2_attr) { cudaFuncSetAttribute(km_select2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); sel2_attr = true; }
         launch_dist<1>(Xc, xx64, cand, nullptr, n, d, newc, st);
         km_select_kernel<<<1, 1024, sel_smem, st>>>(newc, 1, n, 0, k, trials, uniforms, closest, cand, chosen, pot);
         for (int c = 1; c < k; ++c) {
@@ -725,7 +863,8 @@ int sq_kmeans_fit(const float* features, int n, int d, int k, int trials, int fi
                 case 9: launch_dist<9>(Xc, xx64, cand, closest, n, d, newc, st); break;
                 default: launch_dist<10>(Xc, xx64, cand, closest, n, d, newc, st); break;
             }
-            km_select_kernel<<<1, 1024, sel_smem, st>>>(newc, trials, n, c, k, trials, uniforms, closest, cand, chosen, pot);
+            if (sel2) km_select2_kernel<<<1, 1024, sel2_smem, st>>>(newc, trials, n, c, k, uniforms, closest, cum, cand, chosen, pot);
+            else km_select_kernel<<<1, 1024, sel_smem, st>>>(newc, trials, n, c, k, trials, uniforms, closest, cand, chosen, pot);
         }
     }
     km_gather_centers_kernel<<<k, 256, 0, st>>>(Xc, chosen, k, d, P.cA);
