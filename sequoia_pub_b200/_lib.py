@@ -163,6 +163,24 @@ def on_device(t):
     return torch.cuda.device(t.device if getattr(t, "is_cuda", False) else torch.cuda.current_device())
 
 
+def with_device_of(pick):
+    """Decorator: runs the wrapped method with the CUDA device of `pick(*args, **kwargs)` (a tensor) current, so that every
+    `stream_ptr()` / `require_device()` inside refers to the device that holds the operands (a model built with device='cuda:1' in a
+    process whose current device is 0 must not enqueue on device 0's stream)."""
+    import functools
+
+    def deco(fn):
+        @functools.wraps(fn)
+        def wrapper(*args, **kwargs):
+            t = pick(*args, **kwargs)
+            if t is None or not getattr(t, "is_cuda", False):
+                return fn(*args, **kwargs)
+            with on_device(t):
+                return fn(*args, **kwargs)
+        return wrapper
+    return deco
+
+
 _device_checked = set()
 
 

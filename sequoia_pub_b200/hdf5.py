@@ -215,6 +215,10 @@ class File:
         if sb[13] != 8 or sb[14] != 8:
             raise HDF5Error("only 8-byte offsets and lengths are supported")
         self._sb_at = base
+        # node sizes of the group structures are file properties: an 'r+' rewrite of the root group must keep them
+        self._leaf_k, self._internal_k = struct.unpack_from("<HH", sb, 16)
+        if self._leaf_k < 1 or self._internal_k < 1:
+            raise HDF5Error("bad group node K values in the superblock")
         p = 24 + (4 if ver == 1 else 0)
         self._base, _, self._eof, _ = struct.unpack_from("<4Q", sb, p)
         self._eof_at = p + 16
@@ -421,7 +425,7 @@ class File:
         os.pwrite(self._fd, struct.pack("<Q", heap_addr + 32), self._base + heap_addr + 24)
         self._append(bytes(seg))
         # symbol table nodes, 2K entries each, then B-tree levels bottom-up
-        per = 2 * _LEAF_K
+        per = 2 * getattr(self, "_leaf_k", _LEAF_K)
         level_nodes = []                                   # (address, heap offset of the largest name below)
         for i in range(0, len(names), per):
             chunk = names[i:i + per]
@@ -431,7 +435,7 @@ class File:
             blob += b"\0" * (8 + per * 40 - len(blob))
             level_nodes.append((self._append(blob), offs[chunk[-1]]))
         level = 0
-        fan = 2 * _INTERNAL_K
+        fan = 2 * getattr(self, "_internal_k", _INTERNAL_K)
         node_size = 24 + (2 * fan + 1) * 8
         while True:
             groups = [level_nodes[i:i + fan] for i in range(0, len(level_nodes), fan)] or [[]]   # empty group: 0 entries

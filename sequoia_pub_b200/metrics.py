@@ -24,8 +24,9 @@ def step_metrics(labels, preds):
     L = _lib.lib()
     scratch = torch.empty(L.sq_step_metrics_scratch_bytes(G), dtype=torch.uint8, device=labels.device)
     out = torch.empty(4, dtype=torch.float32, device=labels.device)
-    _lib.check(L.sq_step_metrics(_lib.ptr(labels), _lib.ptr(preds), B, G, _lib.ptr(out), _lib.ptr(scratch), scratch.numel(),
-                                 _lib.stream_ptr()))
+    with _lib.on_device(labels):
+        _lib.check(L.sq_step_metrics(_lib.ptr(labels), _lib.ptr(preds), B, G, _lib.ptr(out), _lib.ptr(scratch), scratch.numel(),
+                                     _lib.stream_ptr(labels)))
     return out
 
 

@@ -93,6 +93,7 @@ class ResNet(nn.Module):
                     pairs.append((blk.downsample[0], blk.downsample[1]))
         return pairs
 
+    @_lib.with_device_of(lambda self: self.conv1.weight)
     def _prepack(self):
         tensors = []
         for conv, bn in self._conv_bn_pairs():
@@ -115,6 +116,7 @@ class ResNet(nn.Module):
         self._packed = (key, packed_w, shifts)
         return packed_w, shifts
 
+    @_lib.with_device_of(lambda self: self.conv1.weight)
     def _prepack_planes(self):
         """hi + lo planes of the folded weights for the split-precision mode (`precision="bf16x3"`)."""
         tensors = []
@@ -135,6 +137,7 @@ class ResNet(nn.Module):
         self._packed_hp = (key, hi, lo, shifts)
         return hi, lo, shifts
 
+    @_lib.with_device_of(lambda self, inp, *a, **k: inp)
     def _run_hp(self, inp, kind, batch, H, W, out=None):
         """Split-precision forward (hi*hi + hi*lo + lo*hi, fp32 residuals): the opt-in mode that brackets the bf16 default."""
         if self.training:
@@ -151,6 +154,7 @@ class ResNet(nn.Module):
                                             _lib.ptr(self._workspace_hp), self._workspace_hp.numel(), _lib.stream_ptr()))
         return out
 
+    @_lib.with_device_of(lambda self, inp, *a, **k: inp)
     def _run(self, inp, kind, batch, H, W, out=None, workspace=None):
         if self.training:
             raise RuntimeError("sequoia_b200 ResNet implements eval-mode BatchNorm only; call .eval() "

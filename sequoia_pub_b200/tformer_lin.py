@@ -229,6 +229,7 @@ class _FlatAggregator:
     def _version_key(self):
         return sum(p._version for p in self._params)
 
+    @_lib.with_device_of(lambda self: self._flat)
     def _refresh_planes(self):
         key = self._version_key()
         if key != self._planes_key:
@@ -241,6 +242,7 @@ class _FlatAggregator:
         self._planes_key = self._version_key()
 
     # ------------------------------------------------------------------ compute
+    @_lib.with_device_of(lambda self, x, *a, **k: x)
     def _forward_impl(self, x, keep):
         self._ensure_flat()
         cfg = self._cfg
@@ -285,6 +287,7 @@ class _FlatAggregator:
             self._scratch = torch.empty(need, dtype=torch.uint8, device=self._flat.device)
         return self._scratch
 
+    @_lib.with_device_of(lambda self, act, *a, **k: act if act is not None else self._flat)
     def _backward_impl(self, act, dpred, B, need_dx, gbuf=None, stage_hi=None, stage_lo=0):
         cfg = self._cfg
         if gbuf is None:

@@ -81,6 +81,7 @@ class FusedTrainer:
                     self.step_count = 0                  # a different architecture: nothing carries over, bias correction restarts
         return m
 
+    @_lib.with_device_of(lambda self, x, *a, **k: x)
     def step(self, x, y):
         """x: float32 [B, N, D], y: float32 [B, G] on the model's device -> loss (1-element device tensor, this rank's shard)."""
         m = self._bind()

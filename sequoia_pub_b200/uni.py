@@ -90,6 +90,7 @@ class VisionTransformer(nn.Module):
                   b.norm2.weight, b.norm2.bias, b.mlp.fc1.weight, b.mlp.fc1.bias, b.mlp.fc2.weight, b.mlp.fc2.bias, b.ls2.gamma]
         return t + [self.norm.weight, self.norm.bias]
 
+    @_lib.with_device_of(lambda self: self.cls_token)
     def _prepack(self):
         tensors = self._tensors()
         key = (sum(t._version for t in tensors), tensors[0].data_ptr(), tensors[-1].data_ptr())
@@ -109,6 +110,7 @@ class VisionTransformer(nn.Module):
         self._packed = (key, pw, pv)
         return pw, pv
 
+    @_lib.with_device_of(lambda self, inp, *a, **k: inp)
     def _run(self, inp, kind, batch, out=None, workspace=None):
         if self.training:
             raise RuntimeError("inference only: call .eval() (compute_features_hdf5.py:68)")
