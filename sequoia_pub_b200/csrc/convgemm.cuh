@@ -64,7 +64,7 @@ template <int BN, int CG, int D, int HALO = 0> struct CgCfg {
     static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
 };
 
-template <int BN, int CG, int D, int HALO>
+template <int BN, int CG, int D, int HALO, int GELU = 0>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 convgemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                 const __grid_constant__ CUtensorMap mapR, const __grid_constant__ CUtensorMap mapO, const CgParams p) {
@@ -344,13 +344,12 @@ convgemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                             f[2 * u + 1] += __uint_as_float(w[u] & 0xffff0000u);
                         }
                     }
-                    if (p.relu == 2) {                       // exact GELU (UNI's fc1, compute_features_hdf5.py:63-66: timm nn.GELU)
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) f[u] = gelu_f(f[u]);
-                    } else {
+                    for (int u = 0; u < 8; ++u) f[u] = fmaxf(f[u], relu_lo);
+                }
+                if constexpr (GELU) {                        // exact GELU (UNI's fc1: timm nn.GELU): its own instantiation, the ReLU kernels carry no erff code
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) f[u] = fmaxf(f[u], relu_lo);
-                    }
+                    for (int u = 0; u < 64; ++u) v[u] = gelu_f(v[u]);
                 }
                 if (p.pool_out) {
                     // fused AvgPool2d(7) of the final 8x8 map: a 128-row tile is two images, this warp's 32 rows are image rows
@@ -440,12 +439,12 @@ struct ConvGemmArgs {
     bf16* scratch; size_t scratch_bytes;   // im2col buffer for geometries neither TMA mode tiles (strided convolutions on odd-sized maps)
 };
 
-template <int BN, int CG, int D, int HALO>
+template <int BN, int CG, int D, int HALO, int GELU = 0>
 int convgemm_launch_inst(const CUtensorMap* maps, const CgParams& kp, int grid, cudaStream_t st) {
     using Cfg = CgCfg<BN, CG, D, HALO>;
     static bool configured = false;
     if (!configured) {
-        cudaError_t err = cudaFuncSetAttribute(convgemm_kernel<BN, CG, D, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        cudaError_t err = cudaFuncSetAttribute(convgemm_kernel<BN, CG, D, HALO, GELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
         if (err != cudaSuccess) { set_error("convgemm: cudaFuncSetAttribute: %s", cudaGetErrorString(err)); return -1; }
         configured = true;
     }
@@ -458,7 +457,7 @@ int convgemm_launch_inst(const CUtensorMap* maps, const CgParams& kp, int grid, 
     if (CG == 2) { attr[na].id = cudaLaunchAttributeClusterDimension; attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1; ++na; }
     if (pdl) { attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[na].val.programmaticStreamSerializationAllowed = 1; ++na; }
     cfg.attrs = attr; cfg.numAttrs = na;
-    cudaError_t err = cudaLaunchKernelEx(&cfg, convgemm_kernel<BN, CG, D, HALO>, maps[0], maps[1], maps[2], maps[3], kp);
+    cudaError_t err = cudaLaunchKernelEx(&cfg, convgemm_kernel<BN, CG, D, HALO, GELU>, maps[0], maps[1], maps[2], maps[3], kp);
     if (err == cudaSuccess) err = cudaGetLastError();
     if (err != cudaSuccess) { set_error("convgemm launch: %s", cudaGetErrorString(err)); return -1; }
     return 0;
@@ -506,6 +505,7 @@ inline int convgemm_launch(const ConvGemmArgs& g, cudaStream_t st) {
         if (bn == 0) bn = 64;
     }
     if (cg == 1 && bn == 256) bn = 128;                     // a single CTA has no room for 256-wide stages beside the ring
+    if (g.relu == 2) { bn = 256; cg = 2; if (g.N % 256 != 0 || g.conv.enabled) { set_error("convgemm: the GELU epilogue is built for plain GEMMs with N %% 256 == 0"); return -1; } }
     if (g.N % bn != 0) bn = 64;
     kp.M = g.M; kp.N = g.N;
     const int num_m = (g.M + GEMM_BM - 1) / GEMM_BM;

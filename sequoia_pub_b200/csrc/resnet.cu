@@ -385,6 +385,7 @@ static ResNetWs ws_layout(int batch, int H, int W) {
 
 // one instantiation per (tile width, CTA group); ring depth 3
 int convgemm_dispatch(int bn, int cg, int halo, const CUtensorMap* maps, const CgParams& kp, int grid, cudaStream_t st) {
+    if (kp.relu == 2) return convgemm_launch_inst<256, 2, 3, 0, 1>(maps, kp, grid, st);       // GELU epilogue (UNI fc1): one instantiation
 #define SQ_CG_CASE(BN, CG) if (bn == BN && cg == CG && !halo) return convgemm_launch_inst<BN, CG, 3, 0>(maps, kp, grid, st);
 #define SQ_CG_HALO(BN, CG, D) if (bn == BN && cg == CG && halo) return convgemm_launch_inst<BN, CG, D, 1>(maps, kp, grid, st);
     SQ_CG_CASE(64, 2) SQ_CG_CASE(128, 2) SQ_CG_CASE(256, 2) SQ_CG_CASE(64, 1) SQ_CG_CASE(128, 1)

@@ -257,7 +257,7 @@ static int uni_gemm(int M, int N, int K, const bf16* a, const bf16* w, const flo
                     cudaStream_t st) {
     // bf16 -> bf16 GEMMs with a bias (qkv, fc1 + GELU: 7/12 of the model's FLOPs) run on the CTA-pair kernel with the TMA epilogue
     static const int use_cg = getenv("SQ_UNI_CONVGEMM") ? atoi(getenv("SQ_UNI_CONVGEMM")) : 1;
-    if (use_cg && out_bf && !out_f32 && !res && bias && (act == ACT_NONE || act == ACT_GELU) && N % 64 == 0 && K % 64 == 0) {
+    if (use_cg && out_bf && !out_f32 && !res && bias && (act == ACT_NONE || (act == ACT_GELU && N % 256 == 0)) && N % 64 == 0 && K % 64 == 0) {
         ConvGemmArgs c; memset(&c, 0, sizeof(c));
         c.M = M; c.N = N; c.K = K; c.A = a; c.lda = K; c.W = w; c.bias = bias; c.out = out_bf; c.relu = act == ACT_GELU ? 2 : 0;
         if (convgemm_supported(c)) return convgemm_launch(c, st);
