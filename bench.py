@@ -620,8 +620,8 @@ def main():
                 "launches": n, "avg_launch_us": tms * 1e3 / max(n, 1),
                 "step_frac": value / world * FLOP_PER_PATCH / 1e12 / pk["bf16_sustained"],
                 "kernel_share_of_step": tms / ser_ms, "serialized_step_ms": ser_ms,
-                "timing_note": "kernel durations and share measured on one stream (no inter-batch overlap); the per-launch event brackets serialise launches that "
-                               "overlap through programmatic dependent launch in the untimed step, so the share can read slightly above 1 and `achieved` is conservative",
+                "timing_note": "one CUDA-event pair around the 52 back-to-back convolution launches of every batch, on one stream (no inter-batch overlap): "
+                               "avg_launch_us = chain duration / 52, launches overlap through programmatic dependent launch as in the untimed step",
                 "issued_mma_tflops": fl / (tms * 1e-3) / 1e12}
         if roof["traffic"]:
             # secondary bound: DRAM bytes the same launches moved (ncu) over their live duration

@@ -36,9 +36,11 @@ SQ_API const char* sq_last_error(void);
 /* 0 when the current device is an sm_100 part; the product path refuses to run otherwise. */
 SQ_API int sq_device_ok(void);
 
-/* Measurement aid for bench.py: when enabled, every launch of the tcgen05 GEMM/conv kernel is bracketed by CUDA
- * events on its stream.  _read (after a stream synchronise) returns the summed kernel time, the launch count and
- * the tensor-core FLOPs those launches issued, then resets the counters. */
+/* Measurement aid for bench.py: when enabled, launches of the tcgen05 GEMM/conv kernels are bracketed by CUDA events on
+ * their stream - one pair per launch, except inside sq_resnet50_extract, where ONE pair brackets the chain of 52 back-to-back
+ * convolution launches of a batch (so they overlap through programmatic dependent launch as in an untimed run; the chain counts
+ * as 52 launches).  _read (after a stream synchronise) returns the summed time, the launch count and the tensor-core FLOPs those
+ * launches issued, then resets the counters. */
 SQ_API int sq_gemm_timing_enable(int on);
 SQ_API int sq_gemm_timing_read(double* total_ms, long long* launches, double* mma_flops);
 

@@ -926,6 +926,8 @@ int split_planes(const float* x, bf16* hi, bf16* lo, long long rows, int cols, l
 // optional per-launch CUDA-event timing of the GEMM kernel (bench.py's roofline leg); no-ops unless enabled
 void gemm_timing_begin(cudaStream_t st, double flops);
 void gemm_timing_end(cudaStream_t st);
+void gemm_timing_chain_begin(cudaStream_t st);   // one event pair around a chain of launches (per-launch events suppressed inside)
+void gemm_timing_chain_end(cudaStream_t st);
 unsigned long long* gemm_prof_buffer();
 struct SideStream { cudaStream_t s; cudaEvent_t fork, join; bool ok; };
 SideStream* side_stream();                                   // null when disabled (SQ_SIDE_STREAM=0) or unavailable

@@ -329,6 +329,305 @@ static int launch_stem_fused(const void* input, int kind, int batch, int H, int 
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------- tcgen05 stem (256 x 256 tiles)
+// conv1 7x7/2 + BN shift + ReLU + 3x3/2 max-pool on the 5th-generation tensor cores, warp-specialised (no block-wide barrier in
+// the steady state).  One MMA tile = ONE ROW of the conv map (128 pixels x 64 channels).  The K dimension is organised by INPUT
+// ROW, not by filter row: k-block P_j ("pair j") holds, for every pixel of the row, the 24 (s, c) taps of input row 2j-1 in
+// columns 0..23 and those of input row 2j in columns 32..55 (columns 24..31 / 56..63 are zero).  The taps of a pixel in one input
+// row are 24 CONTIGUOUS values of the normalised row (6*ox values in; the last 3 meet zero weights), so a pair is built from two
+// staged rows with 32-bit shared-memory loads and six 16-byte stores per pixel.  Conv row cy = P_{cy-1} x W[r0 r1] + P_cy x
+// W[r2 r3] + P_{cy+1} x W[r4 r5] + (first half of) P_{cy+2} x W[r6]: every pair is built ONCE and used by four conv rows, i.e. the
+// im2col work per conv row is one pair (16 KB written) instead of the whole 128 x 192 tile (48 KB).
+//   warps 0-7   epilogue: tcgen05.ld (32 lanes x 32 channels each), + shift, ReLU, bf16; the VERTICAL 3-max of the pool lives in
+//               registers (a TMEM lane is a pixel column, the same thread sees it in every conv row); every second conv row the
+//               vertical maxima go to shared memory and the horizontal stride-2 3-max writes the pooled row (8 KB, contiguous)
+//   warps 8-15  two builder groups (alternate pairs): uint8 rows -> (word loads, prefetched one pair ahead) -> 3x256 table ->
+//               staged bf16 rows -> 128B-swizzled K-major pair in a ring of 8 -> fence.proxy.async -> mbarrier
+//   warp 16     one elected thread issues 14 tcgen05.mma (M 128, N 64, K 16) per conv row into a double-buffered TMEM accumulator;
+//               tcgen05.commit releases the oldest pair and publishes the accumulator
+// A CTA walks bands of 4 pooled rows (9 conv rows, 12 pairs) of one image.
+constexpr int S2_THREADS = 17 * 32;
+constexpr int S2_P = 4;                          // pooled rows per band
+constexpr int S2_R = 8;                          // pair ring slots
+constexpr int S2_PAIR_BYTES = 16384;             // [128 pixels][64 k] bf16
+constexpr int S2_B_BYTES = 4 * 8192;             // weights: 4 k-blocks x [64 channels][64 k]
+constexpr int S2_STG_LD = 800;                   // staged row: 3 zero pixels + 256 pixels + 3 zero pixels = 786 values (+ pad)
+constexpr int S2_V_LD = 144;                     // vertical-max row: 128 pixels x 64 bf16, row pitch 144 B (conflict-free 16-byte accesses)
+constexpr int S2_V_BYTES = 128 * S2_V_LD;
+constexpr size_t S2_SMEM = (size_t)S2_R * S2_PAIR_BYTES + S2_B_BYTES + 2 * S2_V_BYTES + 2 * 2 * 2 * S2_STG_LD * 2 + 3 * 256 * 2 + 64 * 4 + 256;
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+struct S2Item { int img, py0, cyb, nrows; };
+__device__ __forceinline__ S2Item s2_item(int item) {
+    S2Item t; t.img = item / (64 / S2_P); t.py0 = (item - t.img * (64 / S2_P)) * S2_P;
+    t.cyb = t.py0 == 0 ? 0 : 2 * t.py0 - 1; t.nrows = 2 * t.py0 + 2 * S2_P - t.cyb;
+    return t;
+}
+
+__global__ void __launch_bounds__(S2_THREADS, 1) stem_tc_kernel(const void* __restrict__ in, int kind, int batch, const bf16* __restrict__ wpk,
+                                                                const float* __restrict__ shift, bf16* __restrict__ out) {
+    constexpr int H = 256, W = 256, HP = 64;
+    extern __shared__ __align__(1024) uint8_t s2_smem[];
+    uint8_t* sA = s2_smem;                                              // [R][128][128 B], 128B swizzle
+    uint8_t* sB = sA + S2_R * S2_PAIR_BYTES;                            // [4][64][128 B], 128B swizzle
+    uint8_t* sV = sB + S2_B_BYTES;                                      // [2][128][144 B]
+    bf16* sStg = reinterpret_cast<bf16*>(sV + 2 * S2_V_BYTES);          // [group][buffer][row][S2_STG_LD]
+    bf16* sLut = sStg + 2 * 2 * 2 * S2_STG_LD;                          // [3][256]
+    float* sShift = reinterpret_cast<float*>(sLut + 3 * 256);           // [64]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sShift + 64);
+    uint64_t* pair_full = bars;                                         // [R] 128 builder arrivals
+    uint64_t* pair_free = bars + S2_R;                                  // [R] tcgen05.commit
+    uint64_t* tmem_full = bars + 2 * S2_R;                              // [2]
+    uint64_t* tmem_empty = tmem_full + 2;                               // [2] 8 epilogue warps
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nitems = batch * (HP / S2_P);
+
+    for (int i = tid; i < 3 * 256; i += S2_THREADS) {
+        const int c = i >> 8;
+        const float mu = c == 0 ? 0.485f : (c == 1 ? 0.456f : 0.406f), sd = c == 0 ? 0.229f : (c == 1 ? 0.224f : 0.225f);
+        sLut[i] = __float2bfloat16_rn((static_cast<float>(i & 255) / 255.0f - mu) / sd);
+    }
+    if (tid < 64) sShift[tid] = shift[tid];
+    // weights [64][7 x 24] -> four K-major 128B-swizzled k-blocks [r0 r1] [r2 r3] [r4 r5] [r6 0], each filter row padded to 32 columns
+    for (int i = tid; i < 4 * 64 * 8; i += S2_THREADS) {
+        const int ch = i & 7, n = (i >> 3) & 63, b = i >> 9, r = 2 * b + (ch >> 2), part = ch & 3;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (r < 7 && part < 3) v = *reinterpret_cast<const uint4*>(wpk + n * STEM_K + r * 24 + part * 8);
+        *reinterpret_cast<uint4*>(sB + b * 8192 + n * 128 + ((ch ^ (n & 7)) << 4)) = v;
+    }
+    // the zero columns of the pairs and the zero pixels left / right of a staged row are written here once and never again
+    for (int i = tid; i < S2_R * S2_PAIR_BYTES / 16; i += S2_THREADS) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < 2 * 2 * 2 * S2_STG_LD; i += S2_THREADS) sStg[i] = __float2bfloat16_rn(0.f);
+    if (tid == 0) {
+        for (int i = 0; i < S2_R; ++i) { mbar_init(&pair_full[i], 128); mbar_init(&pair_free[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 8); }
+        mbar_fence_init();
+    }
+    if (warp == 16) tmem_alloc(tmem_ptr, 128);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp < 8) {
+        // ================================================================ epilogue + max-pool
+        const int q = warp & 3, h = warp >> 2, m = q * 32 + lane, et = tid;          // et: 0..255
+        const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + h * 32;
+        const float4* sh4 = reinterpret_cast<const float4*>(sShift + h * 32);
+        int n = 0, vb = 0;
+        for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+            const S2Item it = s2_item(item);
+            __nv_bfloat162 acc[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) acc[k] = __floats2bfloat162_rn(0.f, 0.f);           // ReLU outputs are >= 0: 0 is the identity of the max
+            for (int c = 0; c < it.nrows; ++c, ++n) {
+                const int cy = it.cyb + c, ab = n & 1;
+                mbar_wait(&tmem_full[ab], (n >> 1) & 1);
+                tc_fence_after();
+                float v[32];
+                tmem_ld32(trow + ab * 64, v);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[ab]);
+                __nv_bfloat162 p[16];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float4 s4 = sh4[k];
+                    p[2 * k] = __floats2bfloat162_rn(fmaxf(v[4 * k] + s4.x, 0.f), fmaxf(v[4 * k + 1] + s4.y, 0.f));
+                    p[2 * k + 1] = __floats2bfloat162_rn(fmaxf(v[4 * k + 2] + s4.z, 0.f), fmaxf(v[4 * k + 3] + s4.w, 0.f));
+                }
+                if (cy & 1) {
+                    const int py = (cy - 1) >> 1;                    // conv rows 2py-1, 2py, 2py+1 are complete
+                    if (py >= it.py0) {
+                        uint8_t* vrow = sV + (vb & 1) * S2_V_BYTES + m * S2_V_LD + h * 64;
+#pragma unroll
+                        for (int k4 = 0; k4 < 4; ++k4) {
+                            __nv_bfloat162 o[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) o[u] = __hmax2(acc[4 * k4 + u], p[4 * k4 + u]);
+                            *reinterpret_cast<uint4*>(vrow + 16 * k4) = *reinterpret_cast<const uint4*>(o);
+                        }
+                        named_bar_sync(1, 256);
+                        const uint8_t* vbuf = sV + (vb & 1) * S2_V_BYTES;
+                        bf16* orow = out + (((size_t)it.img * HP + py) * HP) * 64;
+#pragma unroll
+                        for (int rep = 0; rep < 2; ++rep) {
+                            const int idx = et + rep * 256, c8 = idx & 7, px = idx >> 3;
+                            uint4 t1 = *reinterpret_cast<const uint4*>(vbuf + (2 * px) * S2_V_LD + c8 * 16);
+                            const uint4 t2 = *reinterpret_cast<const uint4*>(vbuf + (2 * px + 1) * S2_V_LD + c8 * 16);
+                            uint4 t0 = t1;
+                            if (px > 0) t0 = *reinterpret_cast<const uint4*>(vbuf + (2 * px - 1) * S2_V_LD + c8 * 16);
+                            __nv_bfloat162* a = reinterpret_cast<__nv_bfloat162*>(&t1);
+                            const __nv_bfloat162* b0 = reinterpret_cast<const __nv_bfloat162*>(&t0);
+                            const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&t2);
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) a[u] = __hmax2(__hmax2(a[u], b0[u]), b2[u]);
+                            *reinterpret_cast<uint4*>(orow + px * 64 + c8 * 8) = t1;
+                        }
+                        ++vb;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) acc[k] = p[k];
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) acc[k] = __hmax2(acc[k], p[k]);
+                }
+            }
+        }
+    } else if (warp < 16) {
+        // ================================================================ pair builders (two groups of 128 threads, alternate pairs)
+        const int g = (warp - 8) >> 2, t = tid - 256 - g * 128;                  // t: pixel column of this thread, 0..127
+        bf16* stg_base = sStg + g * (2 * 2 * S2_STG_LD);
+        struct Cur { int item, i, np, j0, img; int seq; };
+        auto decode = [&](Cur& c) { const S2Item it = s2_item(c.item); c.np = it.nrows + 3; c.j0 = it.cyb - 1; c.img = it.img; };
+        auto advance = [&](Cur& c) {
+            ++c.seq;
+            if (++c.i == c.np) { c.item += gridDim.x; c.i = 0; if (c.item < nitems) decode(c); }
+        };
+        // the three 32-bit words of this thread among the 2 x 192 words of the pair's two uint8 rows
+        auto load_words = [&](const Cur& c, uint32_t (&w)[3]) {
+            const int j = c.j0 + c.i;
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+                const int wi = t + 128 * u, row = wi >= 192 ? 1 : 0, cw = wi - row * 192, iy = 2 * j - 1 + row;
+                w[u] = 0u;
+                if (iy >= 0 && iy < H) w[u] = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(in) + ((size_t)c.img * H + iy) * (W * 3))[cw];
+            }
+        };
+        Cur cur; cur.item = blockIdx.x; cur.i = 0; cur.seq = 0; cur.np = 0; cur.j0 = 0; cur.img = 0;
+        if (cur.item < nitems) decode(cur);
+        if (g == 1 && cur.item < nitems) advance(cur);
+        uint32_t w[3] = {0u, 0u, 0u}, wn[3] = {0u, 0u, 0u};
+        if (kind == 2 && cur.item < nitems) load_words(cur, w);
+        int itn = 0;
+        while (cur.item < nitems) {
+            Cur nx = cur; advance(nx); if (nx.item < nitems) advance(nx);
+            if (kind == 2 && nx.item < nitems) load_words(nx, wn);                // in flight while this pair is staged and built
+            bf16* stg = stg_base + (itn & 1) * (2 * S2_STG_LD);
+            const int j = cur.j0 + cur.i;
+            if (kind == 2) {
+#pragma unroll
+                for (int u = 0; u < 3; ++u) {
+                    const int wi = t + 128 * u, row = wi >= 192 ? 1 : 0, cw = wi - row * 192, iy = 2 * j - 1 + row;
+                    const bool valid = iy >= 0 && iy < H;
+                    const int b0 = cw * 4; int c = b0 % 3;
+                    bf16* dst = stg + row * S2_STG_LD + 9 + b0;
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        dst[b] = valid ? sLut[(c << 8) + ((w[u] >> (8 * b)) & 255u)] : __float2bfloat16_rn(0.f);
+                        c = c == 2 ? 0 : c + 1;
+                    }
+                }
+            } else if (kind == 0) {
+                // uint8 tiles whose base is not 4-byte aligned: byte loads, same table, same staged values
+                const uint8_t* src = reinterpret_cast<const uint8_t*>(in) + (size_t)cur.img * H * (W * 3);
+                for (int i = t; i < 2 * 3 * W; i += 128) {
+                    const int row = i / (3 * W), e = i - row * (3 * W), iy = 2 * j - 1 + row;
+                    stg[row * S2_STG_LD + 9 + e] = (iy >= 0 && iy < H) ? sLut[((e % 3) << 8) + src[(size_t)iy * (W * 3) + e]] : __float2bfloat16_rn(0.f);
+                }
+            } else {
+                // fp32 NCHW, already normalised (the tensor the reference hands to forward_extract)
+                const float* src = reinterpret_cast<const float*>(in);
+                for (int i = t; i < 2 * 3 * W; i += 128) {
+                    const int row = i / (3 * W), e = i - row * (3 * W), c = e / W, x = e - c * W, iy = 2 * j - 1 + row;
+                    float v = 0.f;
+                    if (iy >= 0 && iy < H) v = src[(((size_t)cur.img * 3 + c) * H + iy) * W + x];
+                    stg[row * S2_STG_LD + 9 + x * 3 + c] = __float2bfloat16_rn(v);
+                }
+            }
+            named_bar_sync(2 + g, 128);
+            const int slot = cur.seq % S2_R;
+            mbar_wait(&pair_free[slot], ((cur.seq / S2_R) & 1) ^ 1);
+            {
+                uint8_t* arow = sA + slot * S2_PAIR_BYTES + t * 128;
+                const uint32_t* s32 = reinterpret_cast<const uint32_t*>(stg);
+#pragma unroll
+                for (int row = 0; row < 2; ++row)
+#pragma unroll
+                    for (int part = 0; part < 3; ++part) {
+                        const int w0 = (row * S2_STG_LD + 6 * t + 8 * part) >> 1;                 // 32-bit word index (6t + 8 part is even)
+                        const uint4 val = make_uint4(s32[w0], s32[w0 + 1], s32[w0 + 2], s32[w0 + 3]);
+                        *reinterpret_cast<uint4*>(arow + (((row * 4 + part) ^ (t & 7)) << 4)) = val;
+                    }
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(&pair_full[slot]);
+            cur = nx;
+#pragma unroll
+            for (int u = 0; u < 3; ++u) w[u] = wn[u];
+            ++itn;
+        }
+    } else {
+        // ================================================================ MMA issuer
+        const uint32_t idesc = make_idesc_bf16(64, 0, 0, 128);
+        const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+        int n = 0, seq0 = 0, next_wait = 0;
+        for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+            const S2Item it = s2_item(item);
+            for (int c = 0; c < it.nrows; ++c, ++n) {
+                const int ab = n & 1;
+                mbar_wait(&tmem_empty[ab], ((n >> 1) & 1) ^ 1);
+                while (next_wait <= seq0 + c + 3) { mbar_wait(&pair_full[next_wait % S2_R], (next_wait / S2_R) & 1); ++next_wait; }
+                tc_fence_after();
+                if (elect_one()) {
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const uint32_t abase = a0 + ((seq0 + c + b) % S2_R) * S2_PAIR_BYTES;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            if (b == 3 && k >= 2) break;
+                            umma_bf16(tmem_base + ab * 64, make_smem_desc(abase + k * 32, 1024, 0), make_smem_desc(b0 + b * 8192 + k * 32, 1024, 0),
+                                      idesc, (b | k) ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(&tmem_full[ab]);
+                    umma_commit(&pair_free[(seq0 + c) % S2_R]);
+                    if (c == it.nrows - 1)
+                        for (int b = 1; b < 4; ++b) umma_commit(&pair_free[(seq0 + c + b) % S2_R]);
+                }
+                __syncwarp();
+            }
+            seq0 += it.nrows + 3;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 16) tmem_dealloc(tmem_base, 128);
+}
+
+static int stem_tc_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SQ_STEM_TC"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v;
+}
+
+// 256 x 256 tiles (uint8 NHWC or normalised fp32 NCHW); other sizes keep stem_fused_kernel
+static bool stem_tc_supported(const void* input, int kind, int H, int W) {
+    (void)input;
+    return H == 256 && W == 256 && (kind == 0 || kind == 1);
+}
+
+static int launch_stem_tc(const void* input, int kind, int batch, const bf16* wpk, const float* shift, bf16* out, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S2_SMEM) != cudaSuccess) {
+            set_error("stem_tc: cannot raise the dynamic shared memory limit"); (void)cudaGetLastError(); return -1;
+        }
+        attr_set = true;
+    }
+    const int nitems = batch * (64 / S2_P);
+    int grid = num_sms(); if (grid > nitems) grid = nitems;
+    if (kind == 0 && (reinterpret_cast<uintptr_t>(input) & 3) == 0) kind = 2;      // word loads: every row is 768 B
+    stem_tc_kernel<<<grid, S2_THREADS, S2_SMEM, st>>>(input, kind, batch, wpk, shift, out);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) { set_error("stem_tc: %s", cudaGetErrorString(err)); return -1; }
+    return 0;
+}
+
 // AvgPool2d(7) on an HfxWf map with Hf,Wf in [7,13]: mean of the top-left 7x7 window (src/resnet.py:110,166; fact 4)
 __global__ void avgpool7_kernel(const float* __restrict__ in, float* __restrict__ out, int batch, int Hf, int Wf, int C) {
     const long long n = (long long)batch * C;
@@ -528,7 +827,9 @@ int sq_resnet50_extract(const void* input, int input_kind, int batch, int H, int
     int h = conv_out(Ho, 3, 2, 1), w = conv_out(Wo, 3, 2, 1);
     bf16* im2col = (bf16*)(ws + L.im2col);
     const size_t im2col_bytes = L.total - L.im2col;
-    if (stem_fused_enabled()) {
+    if (stem_fused_enabled() && stem_tc_enabled() && stem_tc_supported(input, input_kind, H, W)) {
+        if (launch_stem_tc(input, input_kind, batch, wp + p.conv[0].w_off, shifts + p.conv[0].s_off, big[0], st)) return -1;
+    } else if (stem_fused_enabled()) {
         if (launch_stem_fused(input, input_kind, batch, H, W, wp + p.conv[0].w_off, shifts + p.conv[0].s_off, big[0], st)) return -1;
     } else {
     stem_im2col_kernel<<<batch * Ho * (Wo / 32), 256, 0, st>>>(input, input_kind, H, W, Ho, Wo, col);
@@ -544,7 +845,8 @@ int sq_resnet50_extract(const void* input, int input_kind, int batch, int H, int
         maxpool3x3s2_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(stem, big[0], batch, Ho, Wo, 64);
     }
     }
-    // ---- 16 bottlenecks
+    // ---- 16 bottlenecks (when bench.py times the kernels: ONE event pair around the chain, so the launches overlap as they do untimed)
+    gemm_timing_chain_begin(st);
     const int blocks[4] = {3, 4, 6, 3};
     bool pooled = false;
     int ci = 1; int x = 0;   // big[x] holds the block input
@@ -573,6 +875,7 @@ int sq_resnet50_extract(const void* input, int input_kind, int batch, int H, int
             x = y; h = h3; w = w3;
             ci += down ? 4 : 3;
         }
+    gemm_timing_chain_end(st);
     if (!pooled) {
         const long long n = (long long)batch * 2048;
         avgpool7_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(fmap, features, batch, h, w, 2048);
