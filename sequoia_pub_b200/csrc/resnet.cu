@@ -333,30 +333,73 @@ static int launch_stem_fused(const void* input, int kind, int batch, int H, int 
 // conv1 7x7/2 + BN shift + ReLU + 3x3/2 max-pool on the 5th-generation tensor cores, warp-specialised (no block-wide barrier in
 // the steady state).  One MMA tile = ONE ROW of the conv map (128 pixels x 64 channels).  The K dimension is organised by INPUT
 // ROW, not by filter row: k-block P_j ("pair j") holds, for every pixel of the row, the 24 (s, c) taps of input row 2j-1 in
-// columns 0..23 and those of input row 2j in columns 32..55 (columns 24..31 / 56..63 are zero).  The taps of a pixel in one input
-// row are 24 CONTIGUOUS values of the normalised row (6*ox values in; the last 3 meet zero weights), so a pair is built from two
-// staged rows with 32-bit shared-memory loads and six 16-byte stores per pixel.  Conv row cy = P_{cy-1} x W[r0 r1] + P_cy x
-// W[r2 r3] + P_{cy+1} x W[r4 r5] + (first half of) P_{cy+2} x W[r6]: every pair is built ONCE and used by four conv rows, i.e. the
-// im2col work per conv row is one pair (16 KB written) instead of the whole 128 x 192 tile (48 KB).
-//   warps 0-7   epilogue: tcgen05.ld (32 lanes x 32 channels each), + shift, ReLU, bf16; the VERTICAL 3-max of the pool lives in
+// columns 0..23 and those of input row 2j in columns 32..55.  The taps of a pixel in one input row are 24 CONTIGUOUS values of
+// the normalised row (6*ox values in; the last 3 meet zero weights), i.e. twelve 32-bit shared-memory loads per row.
+// Conv row cy = P_{cy-1} x W[r0 r1] + P_cy x W[r2 r3] + P_{cy+1} x W[r4 r5] + (first half of) P_{cy+2} x W[r6]: every pair is
+// built ONCE and used by four conv rows.
+//  * The pairs live in TENSOR MEMORY (the A operand of tcgen05.mma is read from TMEM): a builder thread is a pixel = a TMEM lane,
+//    its 2 x 12 words go to the pair's 32 columns with tcgen05.st; shared memory only feeds the 64-channel weight tile (2 KB per
+//    MMA instead of 6 KB - with A in a shared-memory ring, the first version, the kernel was bound by shared-memory bandwidth).
+//  * The BN shift rides in the MMA: columns 24, 25 of every pair are 1.0 and the weight block of filter row r6 carries
+//    bf16 hi / lo of the shift there (the other blocks have zeros), so the epilogue is one cvt.rn.relu.bf16x2 per two values.
+//  * Normalisation (byte / 255 - mean) / std is ONE fma per value with constants that reproduce the bf16 result of the reference
+//    formula for all 256 byte values (exhaustive check; the byte-wise path keeps the table and the tests compare the bits).
+//   warps 0-7   epilogue: tcgen05.ld (32 lanes x 32 channels each), ReLU + bf16 pack; the VERTICAL 3-max of the pool lives in
 //               registers (a TMEM lane is a pixel column, the same thread sees it in every conv row); every second conv row the
 //               vertical maxima go to shared memory and the horizontal stride-2 3-max writes the pooled row (8 KB, contiguous)
-//   warps 8-15  two builder groups (alternate pairs): uint8 rows -> (word loads, prefetched one pair ahead) -> 3x256 table ->
-//               staged bf16 rows -> 128B-swizzled K-major pair in a ring of 8 -> fence.proxy.async -> mbarrier
+//   warps 8-15  two builder groups (alternate pairs): uint8 rows -> cp.async into a 4-deep ring (three pairs ahead) -> staged
+//               normalised bf16 rows -> registers -> tcgen05.st -> mbarrier
 //   warp 16     one elected thread issues 14 tcgen05.mma (M 128, N 64, K 16) per conv row into a double-buffered TMEM accumulator;
 //               tcgen05.commit releases the oldest pair and publishes the accumulator
 // A CTA walks bands of 4 pooled rows (9 conv rows, 12 pairs) of one image.
 constexpr int S2_THREADS = 17 * 32;
 constexpr int S2_P = 4;                          // pooled rows per band
-constexpr int S2_R = 8;                          // pair ring slots
-constexpr int S2_PAIR_BYTES = 16384;             // [128 pixels][64 k] bf16
+constexpr int S2_R = 8;                          // pair ring slots (32 TMEM columns each)
+constexpr int S2_D = 4;                          // raw-row ring depth per builder group (pairs in flight from global memory)
 constexpr int S2_B_BYTES = 4 * 8192;             // weights: 4 k-blocks x [64 channels][64 k]
 constexpr int S2_STG_LD = 800;                   // staged row: 3 zero pixels + 256 pixels + 3 zero pixels = 786 values (+ pad)
 constexpr int S2_V_LD = 144;                     // vertical-max row: 128 pixels x 64 bf16, row pitch 144 B (conflict-free 16-byte accesses)
 constexpr int S2_V_BYTES = 128 * S2_V_LD;
-constexpr size_t S2_SMEM = (size_t)S2_R * S2_PAIR_BYTES + S2_B_BYTES + 2 * S2_V_BYTES + 2 * 2 * 2 * S2_STG_LD * 2 + 3 * 256 * 2 + 64 * 4 + 256;
+constexpr int S2_RAW_BYTES = 2 * 768;            // the two uint8 rows of a pair
+constexpr uint32_t S2_TMEM_COLS = 512;           // 2 x 64 accumulator columns + 8 pairs x 32 columns = 384 -> 512
+constexpr size_t S2_SMEM = (size_t)S2_B_BYTES + 2 * S2_V_BYTES + 2 * 2 * 2 * S2_STG_LD * 2 + 2 * S2_D * S2_RAW_BYTES + 3 * 256 * 2 + 256;
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// 32 lanes x 16 columns: thread t of the warp writes its 16 registers to lane (base_lane + t), columns [col, col + 16)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem]: A is read from tensor memory (lane = row, one 32-bit column = two consecutive k)
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// {lo, hi} -> bf16x2 with ReLU fused into the conversion
+__device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+__device__ __forceinline__ uint32_t hmax2_u32(uint32_t a, uint32_t b) {
+    __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+    return *reinterpret_cast<uint32_t*>(&r);
+}
 
 struct S2Item { int img, py0, cyb, nrows; };
 __device__ __forceinline__ S2Item s2_item(int item) {
@@ -365,18 +408,19 @@ __device__ __forceinline__ S2Item s2_item(int item) {
     return t;
 }
 
+// kind 0: uint8 NHWC (any alignment, byte loads); 1: fp32 NCHW normalised; 2: uint8 NHWC with a 16-byte aligned base (cp.async)
 __global__ void __launch_bounds__(S2_THREADS, 1) stem_tc_kernel(const void* __restrict__ in, int kind, int batch, const bf16* __restrict__ wpk,
-                                                                const float* __restrict__ shift, bf16* __restrict__ out) {
+                                                                const float* __restrict__ shift, bf16* __restrict__ out, int prof) {
     constexpr int H = 256, W = 256, HP = 64;
+    long long pc[6] = {0, 0, 0, 0, 0, 0}; const long long pt0 = clock64();          // SQ_STEM_PROF=1: cycles each role of block 0 spends waiting
     extern __shared__ __align__(1024) uint8_t s2_smem[];
-    uint8_t* sA = s2_smem;                                              // [R][128][128 B], 128B swizzle
-    uint8_t* sB = sA + S2_R * S2_PAIR_BYTES;                            // [4][64][128 B], 128B swizzle
+    uint8_t* sB = s2_smem;                                              // [4][64][128 B], 128B swizzle
     uint8_t* sV = sB + S2_B_BYTES;                                      // [2][128][144 B]
     bf16* sStg = reinterpret_cast<bf16*>(sV + 2 * S2_V_BYTES);          // [group][buffer][row][S2_STG_LD]
-    bf16* sLut = sStg + 2 * 2 * 2 * S2_STG_LD;                          // [3][256]
-    float* sShift = reinterpret_cast<float*>(sLut + 3 * 256);           // [64]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sShift + 64);
-    uint64_t* pair_full = bars;                                         // [R] 128 builder arrivals
+    uint8_t* sRaw = reinterpret_cast<uint8_t*>(sStg + 2 * 2 * 2 * S2_STG_LD);   // [group][S2_D][2 x 768 B]
+    bf16* sLut = reinterpret_cast<bf16*>(sRaw + 2 * S2_D * S2_RAW_BYTES);       // [3][256] (byte-wise path only)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sLut + 3 * 256);
+    uint64_t* pair_full = bars;                                         // [R] 4 builder warps
     uint64_t* pair_free = bars + S2_R;                                  // [R] tcgen05.commit
     uint64_t* tmem_full = bars + 2 * S2_R;                              // [2]
     uint64_t* tmem_empty = tmem_full + 2;                               // [2] 8 epilogue warps
@@ -384,28 +428,33 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem_tc_kernel(const void* __re
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nitems = batch * (HP / S2_P);
 
-    for (int i = tid; i < 3 * 256; i += S2_THREADS) {
-        const int c = i >> 8;
-        const float mu = c == 0 ? 0.485f : (c == 1 ? 0.456f : 0.406f), sd = c == 0 ? 0.229f : (c == 1 ? 0.224f : 0.225f);
-        sLut[i] = __float2bfloat16_rn((static_cast<float>(i & 255) / 255.0f - mu) / sd);
-    }
-    if (tid < 64) sShift[tid] = shift[tid];
-    // weights [64][7 x 24] -> four K-major 128B-swizzled k-blocks [r0 r1] [r2 r3] [r4 r5] [r6 0], each filter row padded to 32 columns
+    if (kind == 0)
+        for (int i = tid; i < 3 * 256; i += S2_THREADS) {
+            const int c = i >> 8;
+            const float mu = c == 0 ? 0.485f : (c == 1 ? 0.456f : 0.406f), sd = c == 0 ? 0.229f : (c == 1 ? 0.224f : 0.225f);
+            sLut[i] = __float2bfloat16_rn((static_cast<float>(i & 255) / 255.0f - mu) / sd);
+        }
+    // weights [64][7 x 24] -> four K-major 128B-swizzled k-blocks [r0 r1] [r2 r3] [r4 r5] [r6 0], each filter row padded to 32 columns;
+    // columns 24, 25 of the r6 block: bf16 hi / lo of the BN shift (they meet the 1.0 columns of the pairs)
     for (int i = tid; i < 4 * 64 * 8; i += S2_THREADS) {
         const int ch = i & 7, n = (i >> 3) & 63, b = i >> 9, r = 2 * b + (ch >> 2), part = ch & 3;
         uint4 v = make_uint4(0u, 0u, 0u, 0u);
         if (r < 7 && part < 3) v = *reinterpret_cast<const uint4*>(wpk + n * STEM_K + r * 24 + part * 8);
+        if (r == 6 && part == 3) {
+            const float sh = shift[n];
+            const bf16 hi = __float2bfloat16_rn(sh), lo = __float2bfloat16_rn(sh - __bfloat162float(hi));
+            v.x = (uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(lo) << 16);
+        }
         *reinterpret_cast<uint4*>(sB + b * 8192 + n * 128 + ((ch ^ (n & 7)) << 4)) = v;
     }
-    // the zero columns of the pairs and the zero pixels left / right of a staged row are written here once and never again
-    for (int i = tid; i < S2_R * S2_PAIR_BYTES / 16; i += S2_THREADS) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0u, 0u, 0u, 0u);
+    // the zero pixels left / right of a staged row are written here once and never again
     for (int i = tid; i < 2 * 2 * 2 * S2_STG_LD; i += S2_THREADS) sStg[i] = __float2bfloat16_rn(0.f);
     if (tid == 0) {
-        for (int i = 0; i < S2_R; ++i) { mbar_init(&pair_full[i], 128); mbar_init(&pair_free[i], 1); }
+        for (int i = 0; i < S2_R; ++i) { mbar_init(&pair_full[i], 4); mbar_init(&pair_free[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 8); }
         mbar_fence_init();
     }
-    if (warp == 16) tmem_alloc(tmem_ptr, 128);
+    if (warp == 16) tmem_alloc(tmem_ptr, S2_TMEM_COLS);
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -416,16 +465,16 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem_tc_kernel(const void* __re
         // ================================================================ epilogue + max-pool
         const int q = warp & 3, h = warp >> 2, m = q * 32 + lane, et = tid;          // et: 0..255
         const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + h * 32;
-        const float4* sh4 = reinterpret_cast<const float4*>(sShift + h * 32);
         int n = 0, vb = 0;
         for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
             const S2Item it = s2_item(item);
-            __nv_bfloat162 acc[16];
+            uint32_t acc[16];
 #pragma unroll
-            for (int k = 0; k < 16; ++k) acc[k] = __floats2bfloat162_rn(0.f, 0.f);           // ReLU outputs are >= 0: 0 is the identity of the max
+            for (int k = 0; k < 16; ++k) acc[k] = 0u;                        // ReLU outputs are >= 0: 0 is the identity of the max
             for (int c = 0; c < it.nrows; ++c, ++n) {
                 const int cy = it.cyb + c, ab = n & 1;
-                mbar_wait(&tmem_full[ab], (n >> 1) & 1);
+                if (prof) { const long long w0 = clock64(); mbar_wait(&tmem_full[ab], (n >> 1) & 1); pc[0] += clock64() - w0; }
+                else mbar_wait(&tmem_full[ab], (n >> 1) & 1);
                 tc_fence_after();
                 float v[32];
                 tmem_ld32(trow + ab * 64, v);
@@ -433,25 +482,19 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem_tc_kernel(const void* __re
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tmem_empty[ab]);
-                __nv_bfloat162 p[16];
+                uint32_t p[16];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const float4 s4 = sh4[k];
-                    p[2 * k] = __floats2bfloat162_rn(fmaxf(v[4 * k] + s4.x, 0.f), fmaxf(v[4 * k + 1] + s4.y, 0.f));
-                    p[2 * k + 1] = __floats2bfloat162_rn(fmaxf(v[4 * k + 2] + s4.z, 0.f), fmaxf(v[4 * k + 3] + s4.w, 0.f));
-                }
+                for (int k = 0; k < 16; ++k) p[k] = pack_relu_bf16x2(v[2 * k], v[2 * k + 1]);
                 if (cy & 1) {
                     const int py = (cy - 1) >> 1;                    // conv rows 2py-1, 2py, 2py+1 are complete
                     if (py >= it.py0) {
                         uint8_t* vrow = sV + (vb & 1) * S2_V_BYTES + m * S2_V_LD + h * 64;
 #pragma unroll
-                        for (int k4 = 0; k4 < 4; ++k4) {
-                            __nv_bfloat162 o[4];
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) o[u] = __hmax2(acc[4 * k4 + u], p[4 * k4 + u]);
-                            *reinterpret_cast<uint4*>(vrow + 16 * k4) = *reinterpret_cast<const uint4*>(o);
-                        }
-                        named_bar_sync(1, 256);
+                        for (int k4 = 0; k4 < 4; ++k4)
+                            *reinterpret_cast<uint4*>(vrow + 16 * k4) = make_uint4(hmax2_u32(acc[4 * k4], p[4 * k4]), hmax2_u32(acc[4 * k4 + 1], p[4 * k4 + 1]),
+                                                                                   hmax2_u32(acc[4 * k4 + 2], p[4 * k4 + 2]), hmax2_u32(acc[4 * k4 + 3], p[4 * k4 + 3]));
+                        if (prof) { const long long w0 = clock64(); named_bar_sync(1, 256); pc[1] += clock64() - w0; }
+                        else named_bar_sync(1, 256);
                         const uint8_t* vbuf = sV + (vb & 1) * S2_V_BYTES;
                         bf16* orow = out + (((size_t)it.img * HP + py) * HP) * 64;
 #pragma unroll
@@ -461,11 +504,8 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem_tc_kernel(const void* __re
                             const uint4 t2 = *reinterpret_cast<const uint4*>(vbuf + (2 * px + 1) * S2_V_LD + c8 * 16);
                             uint4 t0 = t1;
                             if (px > 0) t0 = *reinterpret_cast<const uint4*>(vbuf + (2 * px - 1) * S2_V_LD + c8 * 16);
-                            __nv_bfloat162* a = reinterpret_cast<__nv_bfloat162*>(&t1);
-                            const __nv_bfloat162* b0 = reinterpret_cast<const __nv_bfloat162*>(&t0);
-                            const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&t2);
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) a[u] = __hmax2(__hmax2(a[u], b0[u]), b2[u]);
+                            t1.x = hmax2_u32(hmax2_u32(t1.x, t0.x), t2.x); t1.y = hmax2_u32(hmax2_u32(t1.y, t0.y), t2.y);
+                            t1.z = hmax2_u32(hmax2_u32(t1.z, t0.z), t2.z); t1.w = hmax2_u32(hmax2_u32(t1.w, t0.w), t2.w);
                             *reinterpret_cast<uint4*>(orow + px * 64 + c8 * 8) = t1;
                         }
                         ++vb;
@@ -474,56 +514,82 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem_tc_kernel(const void* __re
                     for (int k = 0; k < 16; ++k) acc[k] = p[k];
                 } else {
 #pragma unroll
-                    for (int k = 0; k < 16; ++k) acc[k] = __hmax2(acc[k], p[k]);
+                    for (int k = 0; k < 16; ++k) acc[k] = hmax2_u32(acc[k], p[k]);
                 }
             }
         }
     } else if (warp < 16) {
         // ================================================================ pair builders (two groups of 128 threads, alternate pairs)
-        const int g = (warp - 8) >> 2, t = tid - 256 - g * 128;                  // t: pixel column of this thread, 0..127
+        const int g = (warp - 8) >> 2, t = tid - 256 - g * 128;                  // t: pixel column of this thread = TMEM lane, 0..127
         bf16* stg_base = sStg + g * (2 * 2 * S2_STG_LD);
+        uint8_t* raw_base = sRaw + g * (S2_D * S2_RAW_BYTES);
         struct Cur { int item, i, np, j0, img; int seq; };
         auto decode = [&](Cur& c) { const S2Item it = s2_item(c.item); c.np = it.nrows + 3; c.j0 = it.cyb - 1; c.img = it.img; };
         auto advance = [&](Cur& c) {
             ++c.seq;
             if (++c.i == c.np) { c.item += gridDim.x; c.i = 0; if (c.item < nitems) decode(c); }
         };
-        // the three 32-bit words of this thread among the 2 x 192 words of the pair's two uint8 rows
-        auto load_words = [&](const Cur& c, uint32_t (&w)[3]) {
-            const int j = c.j0 + c.i;
-#pragma unroll
-            for (int u = 0; u < 3; ++u) {
-                const int wi = t + 128 * u, row = wi >= 192 ? 1 : 0, cw = wi - row * 192, iy = 2 * j - 1 + row;
-                w[u] = 0u;
-                if (iy >= 0 && iy < H) w[u] = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(in) + ((size_t)c.img * H + iy) * (W * 3))[cw];
-            }
+        auto advance2 = [&](Cur& c) { advance(c); if (c.item < nitems) advance(c); };
+        // cp.async: thread t < 96 copies 16-byte chunk t of the pair's 2 x 768 raw bytes
+        const int my_row = t >= 48 ? 1 : 0, my_chunk = t - my_row * 48;
+        auto issue_copy = [&](const Cur& c, int rslot) {
+            const int iy = 2 * (c.j0 + c.i) - 1 + my_row;
+            if (t < 96 && iy >= 0 && iy < H)
+                cp_async16(raw_base + rslot * S2_RAW_BYTES + t * 16, reinterpret_cast<const uint8_t*>(in) + ((size_t)c.img * H + iy) * (W * 3) + my_chunk * 16);
         };
+        // (byte / 255 - mean) / std as ONE fma per value: for these three (a, b) pairs bf16(fma(byte, a, b)) equals bf16 of the
+        // reference formula for all 256 byte values (checked exhaustively; the byte-wise path below keeps the table, and
+        // tests/test_resnet_gpu.py asserts both paths give the same bits)
+        const float na0 = __uint_as_float(0x3c8c48f6u), nb0 = __uint_as_float(0xc0078b9cu);
+        const float na1 = __uint_as_float(0x3c8f6a98u), nb1 = __uint_as_float(0xc00248eeu);
+        const float na2 = __uint_as_float(0x3c8ec798u), nb2 = __uint_as_float(0xbfe6f7ddu);
         Cur cur; cur.item = blockIdx.x; cur.i = 0; cur.seq = 0; cur.np = 0; cur.j0 = 0; cur.img = 0;
         if (cur.item < nitems) decode(cur);
         if (g == 1 && cur.item < nitems) advance(cur);
-        uint32_t w[3] = {0u, 0u, 0u}, wn[3] = {0u, 0u, 0u};
-        if (kind == 2 && cur.item < nitems) load_words(cur, w);
+        Cur pf = cur;
+        if (kind == 2) {
+#pragma unroll
+            for (int d = 0; d < S2_D - 1; ++d) {
+                if (pf.item < nitems) { issue_copy(pf, d); advance2(pf); }
+                cp_async_commit();
+            }
+            cp_async_wait<S2_D - 2>();                     // this thread's chunk of the first pair has landed ...
+            named_bar_sync(2 + g, 128);                    // ... and so have the other threads' chunks
+        }
         int itn = 0;
         while (cur.item < nitems) {
-            Cur nx = cur; advance(nx); if (nx.item < nitems) advance(nx);
-            if (kind == 2 && nx.item < nitems) load_words(nx, wn);                // in flight while this pair is staged and built
             bf16* stg = stg_base + (itn & 1) * (2 * S2_STG_LD);
             const int j = cur.j0 + cur.i;
+            const long long tb0 = prof ? clock64() : 0;
             if (kind == 2) {
+                if (pf.item < nitems) { issue_copy(pf, (itn + S2_D - 1) % S2_D); advance2(pf); }
+                cp_async_commit();
+                // thread t converts bytes 6t+1 .. 6t+6 of both rows: three aligned bf16 pairs per row (staged index = byte + 9), channels
+                // (1,2) (0,1) (2,0) whatever t is; consecutive threads write words 3 apart (conflict-free)
+                const uint8_t* rp = raw_base + (itn % S2_D) * S2_RAW_BYTES + 6 * t;
+                uint32_t* sw = reinterpret_cast<uint32_t*>(stg) + 5 + 3 * t;
 #pragma unroll
-                for (int u = 0; u < 3; ++u) {
-                    const int wi = t + 128 * u, row = wi >= 192 ? 1 : 0, cw = wi - row * 192, iy = 2 * j - 1 + row;
-                    const bool valid = iy >= 0 && iy < H;
-                    const int b0 = cw * 4; int c = b0 % 3;
-                    bf16* dst = stg + row * S2_STG_LD + 9 + b0;
-#pragma unroll
-                    for (int b = 0; b < 4; ++b) {
-                        dst[b] = valid ? sLut[(c << 8) + ((w[u] >> (8 * b)) & 255u)] : __float2bfloat16_rn(0.f);
-                        c = c == 2 ? 0 : c + 1;
+                for (int row = 0; row < 2; ++row) {
+                    const int iy = 2 * j - 1 + row;
+                    uint32_t w0 = 0u, w1 = 0u, w2 = 0u, we = 0u;
+                    if (iy >= 0 && iy < H) {
+                        const uint8_t* r8 = rp + row * 768;
+                        const uint32_t b1 = r8[1], h2 = *reinterpret_cast<const uint16_t*>(r8 + 2), h4 = *reinterpret_cast<const uint16_t*>(r8 + 4), b6 = r8[6];
+                        __nv_bfloat162 q0 = __floats2bfloat162_rn(fmaf((float)b1, na1, nb1), fmaf((float)(h2 & 255u), na2, nb2));
+                        __nv_bfloat162 q1 = __floats2bfloat162_rn(fmaf((float)(h2 >> 8), na0, nb0), fmaf((float)(h4 & 255u), na1, nb1));
+                        __nv_bfloat162 q2 = __floats2bfloat162_rn(fmaf((float)(h4 >> 8), na2, nb2), t == 127 ? 0.f : fmaf((float)b6, na0, nb0));
+                        w0 = *reinterpret_cast<uint32_t*>(&q0); w1 = *reinterpret_cast<uint32_t*>(&q1); w2 = *reinterpret_cast<uint32_t*>(&q2);
+                        if (t == 0) { __nv_bfloat162 qe = __floats2bfloat162_rn(0.f, fmaf((float)r8[0], na0, nb0)); we = *reinterpret_cast<uint32_t*>(&qe); }
                     }
+                    uint32_t* d = sw + row * (S2_STG_LD / 2);
+                    d[0] = w0; d[1] = w1; d[2] = w2;
+                    if (t == 0) d[-1] = we;                                  // staged values 8 (zero pad), 9 (byte 0)
                 }
+                if (prof) { const long long tb1 = clock64(); cp_async_wait<S2_D - 2>(); const long long tb2 = clock64(); pc[2] += tb1 - tb0; pc[3] += tb2 - tb1; }
+                else
+                cp_async_wait<S2_D - 2>();                 // the NEXT pair's chunk of this thread has landed; the barrier below publishes it
             } else if (kind == 0) {
-                // uint8 tiles whose base is not 4-byte aligned: byte loads, same table, same staged values
+                // uint8 tiles whose base is not 16-byte aligned: byte loads, the 3 x 256 table of the reference formula, same staged values
                 const uint8_t* src = reinterpret_cast<const uint8_t*>(in) + (size_t)cur.img * H * (W * 3);
                 for (int i = t; i < 2 * 3 * W; i += 128) {
                     const int row = i / (3 * W), e = i - row * (3 * W), iy = 2 * j - 1 + row;
@@ -539,49 +605,55 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem_tc_kernel(const void* __re
                     stg[row * S2_STG_LD + 9 + x * 3 + c] = __float2bfloat16_rn(v);
                 }
             }
-            named_bar_sync(2 + g, 128);
             const int slot = cur.seq % S2_R;
-            mbar_wait(&pair_free[slot], ((cur.seq / S2_R) & 1) ^ 1);
-            {
-                uint8_t* arow = sA + slot * S2_PAIR_BYTES + t * 128;
-                const uint32_t* s32 = reinterpret_cast<const uint32_t*>(stg);
+            const uint32_t* s32 = reinterpret_cast<const uint32_t*>(stg) + 3 * t;             // pixel t: values 6t .. 6t+23 of a staged row
+            if (prof) { const long long w0 = clock64(); named_bar_sync(2 + g, 128); pc[0] += clock64() - w0; }
+            else named_bar_sync(2 + g, 128);
+            uint32_t r0[16], r1[16];
 #pragma unroll
-                for (int row = 0; row < 2; ++row)
+            for (int u = 0; u < 12; ++u) { r0[u] = s32[u]; r1[u] = s32[S2_STG_LD / 2 + u]; }
 #pragma unroll
-                    for (int part = 0; part < 3; ++part) {
-                        const int w0 = (row * S2_STG_LD + 6 * t + 8 * part) >> 1;                 // 32-bit word index (6t + 8 part is even)
-                        const uint4 val = make_uint4(s32[w0], s32[w0 + 1], s32[w0 + 2], s32[w0 + 3]);
-                        *reinterpret_cast<uint4*>(arow + (((row * 4 + part) ^ (t & 7)) << 4)) = val;
-                    }
-            }
-            fence_proxy_async_smem();
-            mbar_arrive(&pair_full[slot]);
-            cur = nx;
-#pragma unroll
-            for (int u = 0; u < 3; ++u) w[u] = wn[u];
+            for (int u = 12; u < 16; ++u) { r0[u] = 0u; r1[u] = 0u; }
+            r0[12] = 0x3f803f80u;                          // columns 24, 25 = 1.0: they meet shift hi / lo in the r6 weight block, zeros elsewhere
+            if (prof) { const long long w1 = clock64(); mbar_wait(&pair_free[slot], ((cur.seq / S2_R) & 1) ^ 1); pc[1] += clock64() - w1; }
+            else mbar_wait(&pair_free[slot], ((cur.seq / S2_R) & 1) ^ 1);
+            tc_fence_after();
+            const long long tb3 = prof ? clock64() : 0;
+            const uint32_t ta = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + 128 + slot * 32;
+            tmem_st16(ta, r0);
+            tmem_st16(ta + 16, r1);
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&pair_full[slot]);
+            advance2(cur);
             ++itn;
+            if (prof) { const long long tb4 = clock64(); pc[4] += tb4 - tb3; pc[5] += tb4 - tb0; }
         }
     } else {
         // ================================================================ MMA issuer
         const uint32_t idesc = make_idesc_bf16(64, 0, 0, 128);
-        const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+        const uint32_t b0 = smem_u32(sB);
         int n = 0, seq0 = 0, next_wait = 0;
         for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
             const S2Item it = s2_item(item);
             for (int c = 0; c < it.nrows; ++c, ++n) {
                 const int ab = n & 1;
+                const long long w0 = prof ? clock64() : 0;
                 mbar_wait(&tmem_empty[ab], ((n >> 1) & 1) ^ 1);
+                const long long w1 = prof ? clock64() : 0;
                 while (next_wait <= seq0 + c + 3) { mbar_wait(&pair_full[next_wait % S2_R], (next_wait / S2_R) & 1); ++next_wait; }
+                if (prof) { pc[0] += w1 - w0; pc[1] += clock64() - w1; }
                 tc_fence_after();
                 if (elect_one()) {
 #pragma unroll
                     for (int b = 0; b < 4; ++b) {
-                        const uint32_t abase = a0 + ((seq0 + c + b) % S2_R) * S2_PAIR_BYTES;
+                        const int slot = (seq0 + c + b) % S2_R;
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             if (b == 3 && k >= 2) break;
-                            umma_bf16(tmem_base + ab * 64, make_smem_desc(abase + k * 32, 1024, 0), make_smem_desc(b0 + b * 8192 + k * 32, 1024, 0),
-                                      idesc, (b | k) ? 1u : 0u);
+                            umma_bf16_ts(tmem_base + ab * 64, tmem_base + 128 + slot * 32 + k * 8, make_smem_desc(b0 + b * 8192 + k * 32, 1024, 0), idesc,
+                                         (b | k) ? 1u : 0u);
                         }
                     }
                     umma_commit(&tmem_full[ab]);
@@ -594,11 +666,18 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem_tc_kernel(const void* __re
             seq0 += it.nrows + 3;
         }
     }
+    if (prof && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 8 || warp == 12 || warp == 16))
+        printf("stem_tc prof block 0 warp %2d (%s): total %lld cycles; waits: %s %lld, %s %lld\n", warp, warp == 0 ? "epilogue" : (warp == 16 ? "mma" : "builder"),
+               clock64() - pt0, warp == 0 ? "accumulator" : (warp == 16 ? "tmem_empty" : "stage barrier"), pc[0],
+               warp == 0 ? "pool barrier" : (warp == 16 ? "pair_full" : "pair_free"), pc[1]);
+    if (prof && blockIdx.x == 0 && lane == 0 && (warp == 8 || warp == 12))
+        printf("stem_tc prof builder warp %d: issue+convert %lld, cp.async wait %lld, tcgen05.st+arrive+advance %lld, loop total %lld\n", warp, pc[2], pc[3], pc[4], pc[5]);
     tc_fence_before();
     __syncthreads();
-    if (warp == 16) tmem_dealloc(tmem_base, 128);
+    if (warp == 16) tmem_dealloc(tmem_base, S2_TMEM_COLS);
 }
 
+// SQ_STEM_TC=0 keeps the mma.sync fused stem for 256 x 256 tiles too (A/B runs)
 static int stem_tc_enabled() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("SQ_STEM_TC"); v = (e && e[0] == '0') ? 0 : 1; }
@@ -606,10 +685,7 @@ static int stem_tc_enabled() {
 }
 
 // 256 x 256 tiles (uint8 NHWC or normalised fp32 NCHW); other sizes keep stem_fused_kernel
-static bool stem_tc_supported(const void* input, int kind, int H, int W) {
-    (void)input;
-    return H == 256 && W == 256 && (kind == 0 || kind == 1);
-}
+static bool stem_tc_supported(int kind, int H, int W) { return H == 256 && W == 256 && (kind == 0 || kind == 1); }
 
 static int launch_stem_tc(const void* input, int kind, int batch, const bf16* wpk, const float* shift, bf16* out, cudaStream_t st) {
     static bool attr_set = false;
@@ -621,8 +697,9 @@ static int launch_stem_tc(const void* input, int kind, int batch, const bf16* wp
     }
     const int nitems = batch * (64 / S2_P);
     int grid = num_sms(); if (grid > nitems) grid = nitems;
-    if (kind == 0 && (reinterpret_cast<uintptr_t>(input) & 3) == 0) kind = 2;      // word loads: every row is 768 B
-    stem_tc_kernel<<<grid, S2_THREADS, S2_SMEM, st>>>(input, kind, batch, wpk, shift, out);
+    if (kind == 0 && (reinterpret_cast<uintptr_t>(input) & 15) == 0) kind = 2;      // 16-byte cp.async chunks: every row is 768 B
+    static const int prof = getenv("SQ_STEM_PROF") ? atoi(getenv("SQ_STEM_PROF")) : 0;
+    stem_tc_kernel<<<grid, S2_THREADS, S2_SMEM, st>>>(input, kind, batch, wpk, shift, out, prof);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) { set_error("stem_tc: %s", cudaGetErrorString(err)); return -1; }
     return 0;
@@ -827,7 +904,7 @@ int sq_resnet50_extract(const void* input, int input_kind, int batch, int H, int
     int h = conv_out(Ho, 3, 2, 1), w = conv_out(Wo, 3, 2, 1);
     bf16* im2col = (bf16*)(ws + L.im2col);
     const size_t im2col_bytes = L.total - L.im2col;
-    if (stem_fused_enabled() && stem_tc_enabled() && stem_tc_supported(input, input_kind, H, W)) {
+    if (stem_fused_enabled() && stem_tc_enabled() && stem_tc_supported(input_kind, H, W)) {
         if (launch_stem_tc(input, input_kind, batch, wp + p.conv[0].w_off, shifts + p.conv[0].s_off, big[0], st)) return -1;
     } else if (stem_fused_enabled()) {
         if (launch_stem_fused(input, input_kind, batch, H, W, wp + p.conv[0].w_off, shifts + p.conv[0].s_off, big[0], st)) return -1;
