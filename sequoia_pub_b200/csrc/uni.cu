@@ -243,6 +243,203 @@ __global__ void __launch_bounds__(AT_WARPS * 32, 2) uni_attention_kernel(const b
     }
 }
 
+// ---------------------------------------------------------------- softmax attention on tcgen05 / TMEM (default)
+// One work item = (image, head): S = Q K^T and O = P V on the 5th-generation tensor cores, the softmax between them in registers.
+//   warp 8     TMA producer: the head's q / k / v slices of the qkv matrix, one 64 x 208-row box each (rows past the image belong to
+//              the next image or are zero-filled past the end: finite, and masked below), double-buffered across items
+//   warp 9     MMA issuer: per 128-query tile S[128 x 208] = Q K^T (4 k-steps, both operands K-major in shared memory), later
+//              O[128 x 64] = P V (13 k-steps): P is read from TENSOR MEMORY (A operand in TMEM), V is the MN-major B operand
+//   warps 0-7  softmax: a thread owns one query row (= one TMEM lane); pass 1 row maximum, pass 2 exp2 / row sum / bf16 pack, and
+//              P overwrites the S columns it came from (32 fp32 columns -> 16 packed columns, always behind the read cursor);
+//              after the second MMA the same thread scales its O row by 1 / sum and stores 128 contiguous bytes
+// TMEM: two 256-column regions (one per query tile): S in [0, 208), P in [0, 104), O in [128, 192).
+constexpr int ATC_THREADS = 10 * 32;
+constexpr int ATC_KP = 208;                                   // keys padded to 13 k-steps of 16
+constexpr int ATC_Q_BYTES = 256 * 128, ATC_KV_BYTES = ATC_KP * 128;
+constexpr int ATC_BUF_BYTES = ATC_Q_BYTES + 2 * ATC_KV_BYTES;
+constexpr int ATC_SMEM = 2 * ATC_BUF_BYTES + 256;
+
+__global__ void __launch_bounds__(ATC_THREADS, 1) uni_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* __restrict__ out, int batch) {
+    extern __shared__ __align__(1024) uint8_t atc_smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(atc_smem + 2 * ATC_BUF_BYTES);
+    uint64_t* kv_full = bars;          // [2] TMA bytes
+    uint64_t* kv_empty = bars + 2;     // [2] tcgen05.commit after the item's last MMA
+    uint64_t* s_full = bars + 4;       // [tile] scores ready
+    uint64_t* p_full = bars + 6;       // [tile] probabilities written (4 warps)
+    uint64_t* o_full = bars + 8;       // [tile] output accumulator ready
+    uint64_t* o_free = bars + 10;      // [tile] output read: the region may take the next item's scores (4 warps)
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nitems = batch * U_HEADS;
+    if (threadIdx.x == 0) {
+        if (smem_u32(atc_smem) & 1023u) { printf("sequoia_b200: dynamic shared memory is not 1024-byte aligned\n"); __trap(); }
+        tma_prefetch_desc(&map_qkv);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4);
+            mbar_init(&o_full[i], 1); mbar_init(&o_free[i], 4);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 9) tmem_alloc(tmem_ptr, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 8) {
+        if (elect_one()) {
+            int n = 0;
+            for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++n) {
+                const int buf = n & 1, b = item / U_HEADS, hd = item - b * U_HEADS;
+                mbar_wait(&kv_empty[buf], ((n >> 1) & 1) ^ 1);
+                uint8_t* sq = atc_smem + buf * ATC_BUF_BYTES;
+                mbar_expect_tx(&kv_full[buf], 3 * ATC_KV_BYTES);
+                tma_load_2d(&map_qkv, &kv_full[buf], sq, hd * U_HD, b * U_TOK);
+                tma_load_2d(&map_qkv, &kv_full[buf], sq + ATC_Q_BYTES, U_DIM + hd * U_HD, b * U_TOK);
+                tma_load_2d(&map_qkv, &kv_full[buf], sq + ATC_Q_BYTES + ATC_KV_BYTES, 2 * U_DIM + hd * U_HD, b * U_TOK);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 9) {
+        const uint32_t idesc_s = make_idesc_bf16(ATC_KP, 0, 0, 128), idesc_o = make_idesc_bf16(U_HD, 0, 1, 128);
+        int n = 0;
+        for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++n) {
+            const int buf = n & 1;
+            const uint32_t sq = smem_u32(atc_smem + buf * ATC_BUF_BYTES), sk = sq + ATC_Q_BYTES, sv = sk + ATC_KV_BYTES;
+            mbar_wait(&kv_full[buf], (n >> 1) & 1);
+            for (int t = 0; t < 2; ++t) {
+                mbar_wait(&o_free[t], (n & 1) ^ 1);
+                tc_fence_after();
+                if (elect_one()) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16(tmem_base + t * 256, make_smem_desc(sq + t * 16384 + k * 32, 1024, 0), make_smem_desc(sk + k * 32, 1024, 0), idesc_s, k ? 1u : 0u);
+                    umma_commit(&s_full[t]);
+                }
+                __syncwarp();
+            }
+            for (int t = 0; t < 2; ++t) {
+                mbar_wait(&p_full[t], n & 1);
+                tc_fence_after();
+                if (elect_one()) {
+#pragma unroll
+                    for (int k = 0; k < ATC_KP / 16; ++k)
+                        umma_bf16_ts(tmem_base + t * 256 + 128, tmem_base + t * 256 + k * 8, make_smem_desc(sv + k * 2048, 1024, 8192), idesc_o, k ? 1u : 0u);
+                    umma_commit(&o_full[t]);
+                    if (t == 1) umma_commit(&kv_empty[buf]);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        const int t = warp >> 2, q = warp & 3, row = t * 128 + q * 32 + lane;
+        const bool active = t * 128 + q * 32 < U_TOK;                 // warp-uniform: rows 224.. of the second tile are padding
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + t * 256;
+        const float sl2 = 0.125f * 1.44269504088896340736f;           // softmax scale 64^-0.5 folded with log2(e)
+        int n = 0;
+        for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++n) {
+            const int b = item / U_HEADS, hd = item - b * U_HEADS;
+            float l = 0.f;
+            mbar_wait(&s_full[t], n & 1);
+            tc_fence_after();
+            if (active) {
+                float v[32];
+                float mx = -INFINITY;
+#pragma unroll 1
+                for (int c = 0; c < 6; ++c) {
+                    tmem_ld32(taddr + 32 * c, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, v[i]);
+                }
+                tmem_ld16(taddr + 192, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < U_TOK - 192; ++i) mx = fmaxf(mx, v[i]);
+                const float msl = mx * sl2;
+#pragma unroll 1
+                for (int c = 0; c < 6; ++c) {
+                    tmem_ld32(taddr + 32 * c, v);
+                    tmem_ld_wait();
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float e0 = ex2_approx(fmaf(v[2 * i], sl2, -msl)), e1 = ex2_approx(fmaf(v[2 * i + 1], sl2, -msl));
+                        l += e0 + e1;
+                        __nv_bfloat162 h2 = __floats2bfloat162_rn(e0, e1);
+                        pk[i] = *reinterpret_cast<uint32_t*>(&h2);
+                    }
+                    tmem_st16(taddr + 16 * c, pk);
+                }
+                tmem_ld16(taddr + 192, v);
+                tmem_ld_wait();
+                uint32_t pk[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float e0 = 2 * i < U_TOK - 192 ? ex2_approx(fmaf(v[2 * i], sl2, -msl)) : 0.f;
+                    const float e1 = 2 * i + 1 < U_TOK - 192 ? ex2_approx(fmaf(v[2 * i + 1], sl2, -msl)) : 0.f;
+                    l += e0 + e1;
+                    __nv_bfloat162 h2 = __floats2bfloat162_rn(e0, e1);
+                    pk[i] = *reinterpret_cast<uint32_t*>(&h2);
+                }
+                tmem_st8(taddr + 96, pk);
+                tmem_st_wait();
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_full[t]);
+            mbar_wait(&o_full[t], n & 1);
+            tc_fence_after();
+            if (active) {
+                float o[64];
+                tmem_ld32(taddr + 128, o);
+                tmem_ld32(taddr + 160, o + 32);
+                tmem_ld_wait();
+                if (row < U_TOK) {
+                    const float inv = 1.0f / l;
+                    uint4* dst = reinterpret_cast<uint4*>(out + ((long long)b * U_TOK + row) * U_DIM + hd * U_HD);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        uint4 w; __nv_bfloat162 h2;
+                        h2 = __floats2bfloat162_rn(o[8 * k] * inv, o[8 * k + 1] * inv); w.x = *reinterpret_cast<uint32_t*>(&h2);
+                        h2 = __floats2bfloat162_rn(o[8 * k + 2] * inv, o[8 * k + 3] * inv); w.y = *reinterpret_cast<uint32_t*>(&h2);
+                        h2 = __floats2bfloat162_rn(o[8 * k + 4] * inv, o[8 * k + 5] * inv); w.z = *reinterpret_cast<uint32_t*>(&h2);
+                        h2 = __floats2bfloat162_rn(o[8 * k + 6] * inv, o[8 * k + 7] * inv); w.w = *reinterpret_cast<uint32_t*>(&h2);
+                        dst[k] = w;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&o_free[t]);
+        }
+    }
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) tmem_dealloc(tmem_base, 512);
+}
+
+static int uni_attention_tc(const bf16* qkv, bf16* attn, int batch, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) {
+        if (cudaFuncSetAttribute(uni_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM) != cudaSuccess) {
+            set_error("uni_attention: cannot raise the dynamic shared memory limit"); (void)cudaGetLastError(); return -1;
+        }
+        attr = true;
+    }
+    CUtensorMap map;
+    cuuint64_t dims[2] = {(cuuint64_t)3 * U_DIM, (cuuint64_t)batch * U_TOK}, strides[1] = {(cuuint64_t)3 * U_DIM * 2};
+    cuuint32_t box[2] = {(cuuint32_t)U_HD, (cuuint32_t)ATC_KP}, estr[2] = {1, 1};
+    if (encode_map(&map, qkv, 2, dims, strides, box, estr)) return -1;
+    const int nitems = batch * U_HEADS;
+    const int grid = nitems < num_sms() ? nitems : num_sms();
+    uni_attention_tc_kernel<<<grid, ATC_THREADS, ATC_SMEM, st>>>(map, attn, batch);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) { set_error("uni_attention: %s", cudaGetErrorString(err)); return -1; }
+    return 0;
+}
+
 struct UniWs { size_t col, patch, x, h, qkv, attn, u, total; };
 static void uni_ws_layout(int batch, UniWs* w) {
     size_t off = 0;
@@ -326,6 +523,7 @@ int sq_vitl16_extract(const void* input, int input_kind, int batch, int depth, c
     bf16* col = (bf16*)(ws + L.col); float* patch = (float*)(ws + L.patch); float* x = (float*)(ws + L.x);
     bf16* h = (bf16*)(ws + L.h); bf16* qkv = (bf16*)(ws + L.qkv); bf16* attn = (bf16*)(ws + L.attn); bf16* u = (bf16*)(ws + L.u);
     const int M = batch * U_TOK, P = batch * 196;
+    static const int attn_tc = getenv("SQ_UNI_ATTN_TC") ? atoi(getenv("SQ_UNI_ATTN_TC")) : 1;      // 0: the mma.sync kernel (A/B runs)
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(uni_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM); attr = true; }
     uni_patchify_kernel<<<1184, 256, 0, st>>>(input, input_kind, batch, col);
@@ -335,7 +533,8 @@ int sq_vitl16_extract(const void* input, int input_kind, int batch, int depth, c
         const long long* vb = V.blk[i];
         uni_ln_kernel<<<(M + 7) / 8, 256, 0, st>>>(x, U_DIM, packed_v + vb[0], packed_v + vb[1], M, h, nullptr);
         if (uni_gemm(M, 3 * U_DIM, U_DIM, h, pw + W.blk[i][0], packed_v + vb[2], nullptr, nullptr, qkv, ACT_NONE, st)) return -1;
-        uni_attention_kernel<<<batch * U_HEADS, AT_WARPS * 32, AT_SMEM, st>>>(qkv, attn);
+        if (attn_tc) { if (uni_attention_tc(qkv, attn, batch, st)) return -1; }
+        else uni_attention_kernel<<<batch * U_HEADS, AT_WARPS * 32, AT_SMEM, st>>>(qkv, attn);
         if (uni_gemm(M, U_DIM, U_DIM, attn, pw + W.blk[i][1], packed_v + vb[3], x, x, nullptr, ACT_NONE, st)) return -1;
         uni_ln_kernel<<<(M + 7) / 8, 256, 0, st>>>(x, U_DIM, packed_v + vb[4], packed_v + vb[5], M, h, nullptr);
         if (uni_gemm(M, U_MLP, U_DIM, h, pw + W.blk[i][2], packed_v + vb[6], nullptr, nullptr, u, ACT_GELU, st)) return -1;
