@@ -186,33 +186,51 @@ convgemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     } else if (warp == 1) {
         if (rank == 0) {
             // ===================== MMA issuer (leader CTA) =====================
+            // A 64- or 128-wide MMA is 32 / 64 cycles of tensor-pipe time: the issuing thread must not spend more than that per
+            // instruction, so descriptors are not rebuilt per k-step - only their low word (address >> 4) moves, by additions
+            // from a running stage / tap offset, and the cycle counters are read only when profiling is on.
             const uint32_t idesc = make_idesc_bf16(BN, 0, 0, GEMM_BM * CG);
-            int stage = 0; uint32_t phase = 0;
+            constexpr uint32_t DESC_HI = (1u << 14) | (2u << 29);                              // descriptor version, SWIZZLE_128B
+            constexpr uint32_t HI_K = DESC_HI | (1024u >> 4);                                  // K-major tile: 8-row groups 1024 B apart
+            [[maybe_unused]] constexpr uint32_t HI_HALO = DESC_HI | ((HALO_PITCH * 128u) >> 4);    // halo view: 8-pixel groups one halo row apart
+            const uint32_t smem_lo = smem_u32(smem) >> 4;
+            [[maybe_unused]] const uint32_t halo_lo = smem_u32(halo) >> 4;
+            auto desc = [](uint32_t lo, uint32_t hi) { return (static_cast<uint64_t>(hi) << 32) | lo; };
+            const bool prof_on = p.prof != nullptr;
+            int stage = 0; uint32_t phase = 0; uint32_t stage_lo = smem_lo;
             [[maybe_unused]] int hslot = 0; [[maybe_unused]] uint32_t hphase = 0;
-            long long mw_full = 0, mw_tmem = 0; const long long mt0 = clock64();
+            long long mw_full = 0, mw_tmem = 0; const long long mt0 = prof_on ? clock64() : 0;
             for (int ti = 0; ti < my_tiles; ++ti) {
                 const int as = ti & 1; const uint32_t aphase = (ti >> 1) & 1;
-                { const long long w1 = clock64(); mbar_wait(&tmem_empty[as], aphase ^ 1); mw_tmem += clock64() - w1; }
+                if (prof_on) { const long long w1 = clock64(); mbar_wait(&tmem_empty[as], aphase ^ 1); mw_tmem += clock64() - w1; }
+                else mbar_wait(&tmem_empty[as], aphase ^ 1);
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + as * BN;
                 if constexpr (HALO) {
                     for (int cbh = 0; cbh < p.cblocks; ++cbh) {
-                        { const long long w2 = clock64(); mbar_wait(&full_h[hslot], hphase); mw_full += clock64() - w2; }
-                        const uint32_t h_base = smem_u32(halo + hslot * HALO_BYTES);
-                        for (int tap = 0; tap < 9; ++tap) {
-                            { const long long w2 = clock64(); mbar_wait(&full[stage], phase); mw_full += clock64() - w2; }
+                        if (prof_on) { const long long w2 = clock64(); mbar_wait(&full_h[hslot], hphase); mw_full += clock64() - w2; }
+                        else mbar_wait(&full_h[hslot], hphase);
+                        uint32_t a_lo = halo_lo + hslot * (HALO_BYTES >> 4);               // tap (r, s): + (r * HALO_PITCH + s) * 128 bytes
+                        for (int tap = 0, ts = 0; tap < 9; ++tap) {
+                            if (prof_on) { const long long w2 = clock64(); mbar_wait(&full[stage], phase); mw_full += clock64() - w2; }
+                            else mbar_wait(&full[stage], phase);
                             tc_fence_after();
                             if (elect_one()) {
-                                const int tr = tap / 3, ts = tap - tr * 3;
-                                const uint32_t a_base = h_base + (uint32_t)(tr * HALO_PITCH + ts) * 128u;
-                                const uint32_t b_base = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-                                const uint32_t bo = p.halo_bo ? ((a_base >> 7) & 7u) : 0u;
+                                if (p.halo_bo) {
+                                    const uint32_t a_base = a_lo << 4, b_base = stage_lo << 4, bo = (a_base >> 7) & 7u;
 #pragma unroll
-                                for (int k = 0; k < GEMM_BK / 16; ++k) {
-                                    const uint64_t da = make_smem_desc(a_base + k * 32, HALO_PITCH * 128, 0, bo);
-                                    const uint64_t db = make_smem_desc(b_base + k * 32, 1024, 0);
-                                    const uint32_t acc = (cbh > 0 || tap > 0 || k > 0) ? 1u : 0u;
-                                    if constexpr (CG == 2) umma_bf16_pair(tacc, da, db, idesc, acc); else umma_bf16(tacc, da, db, idesc, acc);
+                                    for (int k = 0; k < GEMM_BK / 16; ++k) {
+                                        const uint32_t acc = (cbh > 0 || tap > 0 || k > 0) ? 1u : 0u;
+                                        const uint64_t da = make_smem_desc(a_base + k * 32, HALO_PITCH * 128, 0, bo), db = make_smem_desc(b_base + k * 32, 1024, 0);
+                                        if constexpr (CG == 2) umma_bf16_pair(tacc, da, db, idesc, acc); else umma_bf16(tacc, da, db, idesc, acc);
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int k = 0; k < GEMM_BK / 16; ++k) {
+                                        const uint32_t acc = (cbh > 0 || tap > 0 || k > 0) ? 1u : 0u;
+                                        if constexpr (CG == 2) umma_bf16_pair(tacc, desc(a_lo + 2 * k, HI_HALO), desc(stage_lo + 2 * k, HI_K), idesc, acc);
+                                        else umma_bf16(tacc, desc(a_lo + 2 * k, HI_HALO), desc(stage_lo + 2 * k, HI_K), idesc, acc);
+                                    }
                                 }
                                 const bool last = cbh == p.cblocks - 1 && tap == 8;
                                 if constexpr (CG == 2) {
@@ -226,33 +244,34 @@ convgemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                                 }
                             }
                             __syncwarp();
-                            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                            a_lo += 8; if (++ts == 3) { ts = 0; a_lo += (HALO_PITCH - 3) * 8; }
+                            stage_lo += Cfg::STAGE_BYTES >> 4;
+                            if (++stage == STAGES) { stage = 0; phase ^= 1; stage_lo = smem_lo; }
                         }
                         if (++hslot == Cfg::HS) { hslot = 0; hphase ^= 1; }
                     }
                 } else {
                 for (int kb = 0; kb < p.nk; ++kb) {
-                    { const long long w2 = clock64(); mbar_wait(&full[stage], phase); mw_full += clock64() - w2; }
+                    if (prof_on) { const long long w2 = clock64(); mbar_wait(&full[stage], phase); mw_full += clock64() - w2; }
+                    else mbar_wait(&full[stage], phase);
                     tc_fence_after();
                     if (elect_one()) {
-                        const uint32_t a_base = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-                        const uint32_t b_base = a_base + Cfg::A_BYTES;
+                        const uint32_t b_lo = stage_lo + (Cfg::A_BYTES >> 4);
 #pragma unroll
                         for (int k = 0; k < GEMM_BK / 16; ++k) {
-                            const uint64_t da = make_smem_desc(a_base + k * 32, 1024, 0);
-                            const uint64_t db = make_smem_desc(b_base + k * 32, 1024, 0);
-                            if constexpr (CG == 2) umma_bf16_pair(tacc, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-                            else umma_bf16(tacc, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                            if constexpr (CG == 2) umma_bf16_pair(tacc, desc(stage_lo + 2 * k, HI_K), desc(b_lo + 2 * k, HI_K), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                            else umma_bf16(tacc, desc(stage_lo + 2 * k, HI_K), desc(b_lo + 2 * k, HI_K), idesc, (kb > 0 || k > 0) ? 1u : 0u);
                         }
                         if constexpr (CG == 2) { umma_commit_pair(&empty[stage]); if (kb == p.nk - 1) umma_commit_pair(&tmem_full[as]); }
                         else { umma_commit(&empty[stage]); if (kb == p.nk - 1) umma_commit(&tmem_full[as]); }
                     }
                     __syncwarp();
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    stage_lo += Cfg::STAGE_BYTES >> 4;
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; stage_lo = smem_lo; }
                 }
                 }
             }
-            if (p.prof && lane == 0) { p.prof[blockIdx.x * 16 + 2] = mw_full; p.prof[blockIdx.x * 16 + 3] = mw_tmem; p.prof[blockIdx.x * 16 + 4] = clock64() - mt0; }
+            if (prof_on && lane == 0) { p.prof[blockIdx.x * 16 + 2] = mw_full; p.prof[blockIdx.x * 16 + 3] = mw_tmem; p.prof[blockIdx.x * 16 + 4] = clock64() - mt0; }
         }
     } else if (warp >= 4 && warp - 4 < Cfg::NWORK) {
         // ===================== epilogue: TMEM -> (+ shift, + residual, ReLU) in the warp's ring -> TMA store =====================

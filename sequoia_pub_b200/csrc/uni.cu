@@ -245,48 +245,55 @@ __global__ void __launch_bounds__(AT_WARPS * 32, 2) uni_attention_kernel(const b
 
 // ---------------------------------------------------------------- softmax attention on tcgen05 / TMEM (default)
 // One work item = (image, head): S = Q K^T and O = P V on the 5th-generation tensor cores, the softmax between them in registers.
-//   warp 8     TMA producer: the head's q / k / v slices of the qkv matrix, one 64 x 208-row box each (rows past the image belong to
-//              the next image or are zero-filled past the end: finite, and masked below), double-buffered across items
-//   warp 9     MMA issuer: per 128-query tile S[128 x 208] = Q K^T (4 k-steps, both operands K-major in shared memory), later
-//              O[128 x 64] = P V (13 k-steps): P is read from TENSOR MEMORY (A operand in TMEM), V is the MN-major B operand
-//   warps 0-7  softmax: a thread owns one query row (= one TMEM lane); pass 1 row maximum, pass 2 exp2 / row sum / bf16 pack, and
-//              P overwrites the S columns it came from (32 fp32 columns -> 16 packed columns, always behind the read cursor);
-//              after the second MMA the same thread scales its O row by 1 / sum and stores 128 contiguous bytes
+//   warp 16     TMA producer: the head's q / k / v slices of the qkv matrix, one 64 x 208-row box each (rows past the image belong
+//               to the next image or are zero-filled past the end: finite, and masked below), double-buffered across items
+//   warp 17     MMA issuer: per 128-query tile S[128 x 208] = Q K^T (4 k-steps, both operands K-major in shared memory), later
+//               O[128 x 64] = P V (13 k-steps): P is read from TENSOR MEMORY (A operand in TMEM), V is the MN-major B operand
+//   warps 0-15  softmax, 8 warps per query tile: a TMEM lane is a query row; the two warps of a lane quadrant split the row's key
+//               columns (0..103 / 104..207) - four warps per scheduler hide the tcgen05.ld round trips.  Pass 1: partial row
+//               maxima, exchanged through shared memory; pass 2: exp2, partial sums, bf16 pack into registers; once every warp
+//               of the tile has read its scores, P overwrites the S columns (packed, 104 columns) and the second MMA starts;
+//               afterwards each warp scales its 32 output columns by 1 / sum and stores 64 contiguous bytes per row
 // TMEM: two 256-column regions (one per query tile): S in [0, 208), P in [0, 104), O in [128, 192).
-constexpr int ATC_THREADS = 10 * 32;
+constexpr int ATC_THREADS = 18 * 32;
 constexpr int ATC_KP = 208;                                   // keys padded to 13 k-steps of 16
 constexpr int ATC_Q_BYTES = 256 * 128, ATC_KV_BYTES = ATC_KP * 128;
 constexpr int ATC_BUF_BYTES = ATC_Q_BYTES + 2 * ATC_KV_BYTES;
-constexpr int ATC_SMEM = 2 * ATC_BUF_BYTES + 256;
+constexpr int ATC_SMEM = 2 * ATC_BUF_BYTES + 2 * 2 * 2 * 128 * 4 + 256;
 
 __global__ void __launch_bounds__(ATC_THREADS, 1) uni_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, bf16* __restrict__ out, int batch) {
     extern __shared__ __align__(1024) uint8_t atc_smem[];
-    uint64_t* bars = reinterpret_cast<uint64_t*>(atc_smem + 2 * ATC_BUF_BYTES);
+    float* s_max = reinterpret_cast<float*>(atc_smem + 2 * ATC_BUF_BYTES);      // [tile][half][row]
+    float* s_sum = s_max + 2 * 2 * 128;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_sum + 2 * 2 * 128);
     uint64_t* kv_full = bars;          // [2] TMA bytes
     uint64_t* kv_empty = bars + 2;     // [2] tcgen05.commit after the item's last MMA
     uint64_t* s_full = bars + 4;       // [tile] scores ready
-    uint64_t* p_full = bars + 6;       // [tile] probabilities written (4 warps)
+    uint64_t* p_full = bars + 6;       // [tile] probabilities written (the tile's active warps)
     uint64_t* o_full = bars + 8;       // [tile] output accumulator ready
-    uint64_t* o_free = bars + 10;      // [tile] output read: the region may take the next item's scores (4 warps)
+    uint64_t* o_free = bars + 10;      // [tile] output read: the region may take the next item's scores
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nitems = batch * U_HEADS;
+    // rows 197..255 of the second query tile are padding: its last lane quadrant (rows 224..255) has no work at all
+    constexpr int ACTIVE_Q1 = (U_TOK - 128 + 31) / 32;                // 3 active quadrants in tile 1
     if (threadIdx.x == 0) {
         if (smem_u32(atc_smem) & 1023u) { printf("sequoia_b200: dynamic shared memory is not 1024-byte aligned\n"); __trap(); }
         tma_prefetch_desc(&map_qkv);
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4);
-            mbar_init(&o_full[i], 1); mbar_init(&o_free[i], 4);
+            const uint32_t nw = i == 0 ? 8 : 2 * ACTIVE_Q1;
+            mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); mbar_init(&s_full[i], 1); mbar_init(&p_full[i], nw);
+            mbar_init(&o_full[i], 1); mbar_init(&o_free[i], nw);
         }
         mbar_fence_init();
     }
-    if (warp == 9) tmem_alloc(tmem_ptr, 512);
+    if (warp == 17) tmem_alloc(tmem_ptr, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
-    if (warp == 8) {
+    if (warp == 16) {
         if (elect_one()) {
             int n = 0;
             for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++n) {
@@ -300,7 +307,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) uni_attention_tc_kernel(const 
             }
         }
         __syncwarp();
-    } else if (warp == 9) {
+    } else if (warp == 17) {
         const uint32_t idesc_s = make_idesc_bf16(ATC_KP, 0, 0, 128), idesc_o = make_idesc_bf16(U_HD, 0, 1, 128);
         int n = 0;
         for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++n) {
@@ -331,82 +338,96 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) uni_attention_tc_kernel(const 
                 __syncwarp();
             }
         }
-    } else {
-        const int t = warp >> 2, q = warp & 3, row = t * 128 + q * 32 + lane;
-        const bool active = t * 128 + q * 32 < U_TOK;                 // warp-uniform: rows 224.. of the second tile are padding
+    } else if ((warp >> 3) == 0 || (warp & 3) < ACTIVE_Q1) {
+        const int t = warp >> 3, h = (warp >> 2) & 1, q = warp & 3, r = q * 32 + lane, row = t * 128 + r;
+        const int bar_threads = (t == 0 ? 8 : 2 * ACTIVE_Q1) * 32;
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + t * 256;
+        const uint32_t sbase = taddr + h * 104;                        // this warp's score columns
         const float sl2 = 0.125f * 1.44269504088896340736f;           // softmax scale 64^-0.5 folded with log2(e)
+        float* my_max = s_max + (t * 2 + h) * 128 + r; const float* other_max = s_max + (t * 2 + (h ^ 1)) * 128 + r;
+        float* my_sum = s_sum + (t * 2 + h) * 128 + r; const float* other_sum = s_sum + (t * 2 + (h ^ 1)) * 128 + r;
+        constexpr int LASTV = U_TOK - 104 - 64;                       // valid columns in the last 32-column piece of the second half (29)
         int n = 0;
         for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++n) {
             const int b = item / U_HEADS, hd = item - b * U_HEADS;
-            float l = 0.f;
             mbar_wait(&s_full[t], n & 1);
             tc_fence_after();
-            if (active) {
-                float v[32];
-                float mx = -INFINITY;
-#pragma unroll 1
-                for (int c = 0; c < 6; ++c) {
-                    tmem_ld32(taddr + 32 * c, v);
-                    tmem_ld_wait();
+            float v[32];
+            // ---- pass 1: maximum of this warp's half of the row
+            float mx = -INFINITY;
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, v[i]);
-                }
-                tmem_ld16(taddr + 192, v);
+            for (int c = 0; c < 3; ++c) {
+                tmem_ld32(sbase + 32 * c, v);
                 tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < U_TOK - 192; ++i) mx = fmaxf(mx, v[i]);
-                const float msl = mx * sl2;
-#pragma unroll 1
-                for (int c = 0; c < 6; ++c) {
-                    tmem_ld32(taddr + 32 * c, v);
-                    tmem_ld_wait();
-                    uint32_t pk[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const float e0 = ex2_approx(fmaf(v[2 * i], sl2, -msl)), e1 = ex2_approx(fmaf(v[2 * i + 1], sl2, -msl));
-                        l += e0 + e1;
-                        __nv_bfloat162 h2 = __floats2bfloat162_rn(e0, e1);
-                        pk[i] = *reinterpret_cast<uint32_t*>(&h2);
-                    }
-                    tmem_st16(taddr + 16 * c, pk);
-                }
-                tmem_ld16(taddr + 192, v);
+                for (int i = 0; i < 32; ++i) if (!(h == 1 && c == 2 && i >= LASTV)) mx = fmaxf(mx, v[i]);
+            }
+            if (h == 0) {
+                tmem_ld8(sbase + 96, v);
                 tmem_ld_wait();
-                uint32_t pk[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float e0 = 2 * i < U_TOK - 192 ? ex2_approx(fmaf(v[2 * i], sl2, -msl)) : 0.f;
-                    const float e1 = 2 * i + 1 < U_TOK - 192 ? ex2_approx(fmaf(v[2 * i + 1], sl2, -msl)) : 0.f;
+                for (int i = 0; i < 8; ++i) mx = fmaxf(mx, v[i]);
+            }
+            *my_max = mx;
+            named_bar_sync(1 + t, bar_threads);
+            const float msl = fmaxf(mx, *other_max) * sl2;
+            // ---- pass 2: exp2, partial row sum, bf16 pack (kept in registers until every warp of the tile has read its scores)
+            uint32_t pk[52];
+            float l = 0.f;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                tmem_ld32(sbase + 32 * c, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const bool m0 = h == 1 && c == 2 && 2 * i >= LASTV, m1 = h == 1 && c == 2 && 2 * i + 1 >= LASTV;
+                    const float e0 = m0 ? 0.f : ex2_approx(fmaf(v[2 * i], sl2, -msl)), e1 = m1 ? 0.f : ex2_approx(fmaf(v[2 * i + 1], sl2, -msl));
                     l += e0 + e1;
                     __nv_bfloat162 h2 = __floats2bfloat162_rn(e0, e1);
-                    pk[i] = *reinterpret_cast<uint32_t*>(&h2);
+                    pk[16 * c + i] = *reinterpret_cast<uint32_t*>(&h2);
                 }
-                tmem_st8(taddr + 96, pk);
-                tmem_st_wait();
             }
+            if (h == 0) {
+                tmem_ld8(sbase + 96, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float e0 = ex2_approx(fmaf(v[2 * i], sl2, -msl)), e1 = ex2_approx(fmaf(v[2 * i + 1], sl2, -msl));
+                    l += e0 + e1;
+                    __nv_bfloat162 h2 = __floats2bfloat162_rn(e0, e1);
+                    pk[48 + i] = *reinterpret_cast<uint32_t*>(&h2);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) pk[48 + i] = 0u;               // keys 200..207: padding
+            }
+            *my_sum = l;
+            tc_fence_before();
+            named_bar_sync(1 + t, bar_threads);                            // all scores of the tile are in registers: P may overwrite S
+            tc_fence_after();
+            const uint32_t pbase = taddr + h * 52;
+            tmem_st32(pbase, pk);
+            tmem_st16(pbase + 32, pk + 32);
+            tmem_st4(pbase + 48, pk + 48);
+            tmem_st_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_full[t]);
+            const float inv = 1.0f / (l + *other_sum);
             mbar_wait(&o_full[t], n & 1);
             tc_fence_after();
-            if (active) {
-                float o[64];
-                tmem_ld32(taddr + 128, o);
-                tmem_ld32(taddr + 160, o + 32);
-                tmem_ld_wait();
-                if (row < U_TOK) {
-                    const float inv = 1.0f / l;
-                    uint4* dst = reinterpret_cast<uint4*>(out + ((long long)b * U_TOK + row) * U_DIM + hd * U_HD);
+            tmem_ld32(taddr + 128 + 32 * h, v);
+            tmem_ld_wait();
+            if (row < U_TOK) {
+                uint4* dst = reinterpret_cast<uint4*>(out + ((long long)b * U_TOK + row) * U_DIM + hd * U_HD + 32 * h);
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        uint4 w; __nv_bfloat162 h2;
-                        h2 = __floats2bfloat162_rn(o[8 * k] * inv, o[8 * k + 1] * inv); w.x = *reinterpret_cast<uint32_t*>(&h2);
-                        h2 = __floats2bfloat162_rn(o[8 * k + 2] * inv, o[8 * k + 3] * inv); w.y = *reinterpret_cast<uint32_t*>(&h2);
-                        h2 = __floats2bfloat162_rn(o[8 * k + 4] * inv, o[8 * k + 5] * inv); w.z = *reinterpret_cast<uint32_t*>(&h2);
-                        h2 = __floats2bfloat162_rn(o[8 * k + 6] * inv, o[8 * k + 7] * inv); w.w = *reinterpret_cast<uint32_t*>(&h2);
-                        dst[k] = w;
-                    }
+                for (int k = 0; k < 4; ++k) {
+                    uint4 w; __nv_bfloat162 h2;
+                    h2 = __floats2bfloat162_rn(v[8 * k] * inv, v[8 * k + 1] * inv); w.x = *reinterpret_cast<uint32_t*>(&h2);
+                    h2 = __floats2bfloat162_rn(v[8 * k + 2] * inv, v[8 * k + 3] * inv); w.y = *reinterpret_cast<uint32_t*>(&h2);
+                    h2 = __floats2bfloat162_rn(v[8 * k + 4] * inv, v[8 * k + 5] * inv); w.z = *reinterpret_cast<uint32_t*>(&h2);
+                    h2 = __floats2bfloat162_rn(v[8 * k + 6] * inv, v[8 * k + 7] * inv); w.w = *reinterpret_cast<uint32_t*>(&h2);
+                    dst[k] = w;
                 }
             }
             tc_fence_before();
@@ -417,7 +438,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) uni_attention_tc_kernel(const 
     __syncwarp();
     tc_fence_before();
     __syncthreads();
-    if (warp == 9) tmem_dealloc(tmem_base, 512);
+    if (warp == 17) tmem_dealloc(tmem_base, 512);
 }
 
 static int uni_attention_tc(const bf16* qkv, bf16* attn, int batch, cudaStream_t st) {
