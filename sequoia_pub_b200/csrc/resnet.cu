@@ -347,12 +347,14 @@ static int launch_stem_fused(const void* input, int kind, int batch, int H, int 
 //   warps 0-7   epilogue: tcgen05.ld (32 lanes x 32 channels each), ReLU + bf16 pack; the VERTICAL 3-max of the pool lives in
 //               registers (a TMEM lane is a pixel column, the same thread sees it in every conv row); every second conv row the
 //               vertical maxima go to shared memory and the horizontal stride-2 3-max writes the pooled row (8 KB, contiguous)
-//   warps 8-15  two builder groups (alternate pairs): uint8 rows -> cp.async into a 4-deep ring (three pairs ahead) -> staged
+//   warps 8-15  two builder groups (pairs dealt round-robin): uint8 rows -> cp.async into a 4-deep ring (three pairs ahead) -> staged
 //               normalised bf16 rows -> registers -> tcgen05.st -> mbarrier
 //   warp 16     one elected thread issues 14 tcgen05.mma (M 128, N 64, K 16) per conv row into a double-buffered TMEM accumulator;
 //               tcgen05.commit releases the oldest pair and publishes the accumulator
 // A CTA walks bands of 4 pooled rows (9 conv rows, 12 pairs) of one image.
-constexpr int S2_THREADS = 17 * 32;
+constexpr int S2_NG = 2;                          // builder groups of 128 threads, pairs dealt round-robin (3 groups measured: no gain, 80 registers + spills)
+constexpr int S2_MMA_WARP = 8 + 4 * S2_NG;
+constexpr int S2_THREADS = (S2_MMA_WARP + 1) * 32;
 constexpr int S2_P = 4;                          // pooled rows per band
 constexpr int S2_R = 8;                          // pair ring slots (32 TMEM columns each)
 constexpr int S2_D = 4;                          // raw-row ring depth per builder group (pairs in flight from global memory)
@@ -362,7 +364,7 @@ constexpr int S2_V_LD = 144;                     // vertical-max row: 128 pixels
 constexpr int S2_V_BYTES = 128 * S2_V_LD;
 constexpr int S2_RAW_BYTES = 2 * 768;            // the two uint8 rows of a pair
 constexpr uint32_t S2_TMEM_COLS = 512;           // 2 x 64 accumulator columns + 8 pairs x 32 columns = 384 -> 512
-constexpr size_t S2_SMEM = (size_t)S2_B_BYTES + 2 * S2_V_BYTES + 2 * 2 * 2 * S2_STG_LD * 2 + 2 * S2_D * S2_RAW_BYTES + 3 * 256 * 2 + 256;
+constexpr size_t S2_SMEM = (size_t)S2_B_BYTES + 2 * S2_V_BYTES + S2_NG * 2 * 2 * S2_STG_LD * 2 + S2_NG * S2_D * S2_RAW_BYTES + 3 * 256 * 2 + 256;
 
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
@@ -396,8 +398,8 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem_tc_kernel(const void* __re
     uint8_t* sB = s2_smem;                                              // [4][64][128 B], 128B swizzle
     uint8_t* sV = sB + S2_B_BYTES;                                      // [2][128][144 B]
     bf16* sStg = reinterpret_cast<bf16*>(sV + 2 * S2_V_BYTES);          // [group][buffer][row][S2_STG_LD]
-    uint8_t* sRaw = reinterpret_cast<uint8_t*>(sStg + 2 * 2 * 2 * S2_STG_LD);   // [group][S2_D][2 x 768 B]
-    bf16* sLut = reinterpret_cast<bf16*>(sRaw + 2 * S2_D * S2_RAW_BYTES);       // [3][256] (byte-wise path only)
+    uint8_t* sRaw = reinterpret_cast<uint8_t*>(sStg + S2_NG * 2 * 2 * S2_STG_LD);   // [group][S2_D][2 x 768 B]
+    bf16* sLut = reinterpret_cast<bf16*>(sRaw + S2_NG * S2_D * S2_RAW_BYTES);       // [3][256] (byte-wise path only)
     uint64_t* bars = reinterpret_cast<uint64_t*>(sLut + 3 * 256);
     uint64_t* pair_full = bars;                                         // [R] 4 builder warps
     uint64_t* pair_free = bars + S2_R;                                  // [R] tcgen05.commit
@@ -427,13 +429,13 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem_tc_kernel(const void* __re
         *reinterpret_cast<uint4*>(sB + b * 8192 + n * 128 + ((ch ^ (n & 7)) << 4)) = v;
     }
     // the zero pixels left / right of a staged row are written here once and never again
-    for (int i = tid; i < 2 * 2 * 2 * S2_STG_LD; i += S2_THREADS) sStg[i] = __float2bfloat16_rn(0.f);
+    for (int i = tid; i < S2_NG * 2 * 2 * S2_STG_LD; i += S2_THREADS) sStg[i] = __float2bfloat16_rn(0.f);
     if (tid == 0) {
         for (int i = 0; i < S2_R; ++i) { mbar_init(&pair_full[i], 4); mbar_init(&pair_free[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 8); }
         mbar_fence_init();
     }
-    if (warp == 16) tmem_alloc(tmem_ptr, S2_TMEM_COLS);
+    if (warp == S2_MMA_WARP) tmem_alloc(tmem_ptr, S2_TMEM_COLS);
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -497,8 +499,8 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem_tc_kernel(const void* __re
                 }
             }
         }
-    } else if (warp < 16) {
-        // ================================================================ pair builders (two groups of 128 threads, alternate pairs)
+    } else if (warp < S2_MMA_WARP) {
+        // ================================================================ pair builders (S2_NG groups of 128 threads, pairs dealt round-robin)
         const int g = (warp - 8) >> 2, t = tid - 256 - g * 128;                  // t: pixel column of this thread = TMEM lane, 0..127
         bf16* stg_base = sStg + g * (2 * 2 * S2_STG_LD);
         uint8_t* raw_base = sRaw + g * (S2_D * S2_RAW_BYTES);
@@ -508,7 +510,7 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem_tc_kernel(const void* __re
             ++c.seq;
             if (++c.i == c.np) { c.item += gridDim.x; c.i = 0; if (c.item < nitems) decode(c); }
         };
-        auto advance2 = [&](Cur& c) { advance(c); if (c.item < nitems) advance(c); };
+        auto advance_ng = [&](Cur& c) { for (int a = 0; a < S2_NG && c.item < nitems; ++a) advance(c); };    // this group's next pair
         // cp.async: thread t < 96 copies 16-byte chunk t of the pair's 2 x 768 raw bytes
         const int my_row = t >= 48 ? 1 : 0, my_chunk = t - my_row * 48;
         auto issue_copy = [&](const Cur& c, int rslot) {
@@ -524,12 +526,12 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem_tc_kernel(const void* __re
         const float na2 = __uint_as_float(0x3c8ec798u), nb2 = __uint_as_float(0xbfe6f7ddu);
         Cur cur; cur.item = blockIdx.x; cur.i = 0; cur.seq = 0; cur.np = 0; cur.j0 = 0; cur.img = 0;
         if (cur.item < nitems) decode(cur);
-        if (g == 1 && cur.item < nitems) advance(cur);
+        for (int a = 0; a < g && cur.item < nitems; ++a) advance(cur);
         Cur pf = cur;
         if (kind == 2) {
 #pragma unroll
             for (int d = 0; d < S2_D - 1; ++d) {
-                if (pf.item < nitems) { issue_copy(pf, d); advance2(pf); }
+                if (pf.item < nitems) { issue_copy(pf, d); advance_ng(pf); }
                 cp_async_commit();
             }
             cp_async_wait<S2_D - 2>();                     // this thread's chunk of the first pair has landed ...
@@ -541,7 +543,7 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem_tc_kernel(const void* __re
             const int j = cur.j0 + cur.i;
             const long long tb0 = prof ? clock64() : 0;
             if (kind == 2) {
-                if (pf.item < nitems) { issue_copy(pf, (itn + S2_D - 1) % S2_D); advance2(pf); }
+                if (pf.item < nitems) { issue_copy(pf, (itn + S2_D - 1) % S2_D); advance_ng(pf); }
                 cp_async_commit();
                 // thread t converts bytes 6t+1 .. 6t+6 of both rows: three aligned bf16 pairs per row (staged index = byte + 9), channels
                 // (1,2) (0,1) (2,0) whatever t is; consecutive threads write words 3 apart (conflict-free)
@@ -605,7 +607,7 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem_tc_kernel(const void* __re
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&pair_full[slot]);
-            advance2(cur);
+            advance_ng(cur);
             ++itn;
             if (prof) { const long long tb4 = clock64(); pc[4] += tb4 - tb3; pc[5] += tb4 - tb0; }
         }
@@ -645,15 +647,15 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem_tc_kernel(const void* __re
             seq0 += it.nrows + 3;
         }
     }
-    if (prof && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 8 || warp == 12 || warp == 16))
-        printf("stem_tc prof block 0 warp %2d (%s): total %lld cycles; waits: %s %lld, %s %lld\n", warp, warp == 0 ? "epilogue" : (warp == 16 ? "mma" : "builder"),
-               clock64() - pt0, warp == 0 ? "accumulator" : (warp == 16 ? "tmem_empty" : "stage barrier"), pc[0],
-               warp == 0 ? "pool barrier" : (warp == 16 ? "pair_full" : "pair_free"), pc[1]);
+    if (prof && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 8 || warp == 12 || warp == S2_MMA_WARP))
+        printf("stem_tc prof block 0 warp %2d (%s): total %lld cycles; waits: %s %lld, %s %lld\n", warp, warp == 0 ? "epilogue" : (warp == S2_MMA_WARP ? "mma" : "builder"),
+               clock64() - pt0, warp == 0 ? "accumulator" : (warp == S2_MMA_WARP ? "tmem_empty" : "stage barrier"), pc[0],
+               warp == 0 ? "pool barrier" : (warp == S2_MMA_WARP ? "pair_full" : "pair_free"), pc[1]);
     if (prof && blockIdx.x == 0 && lane == 0 && (warp == 8 || warp == 12))
         printf("stem_tc prof builder warp %d: issue+convert %lld, cp.async wait %lld, tcgen05.st+arrive+advance %lld, loop total %lld\n", warp, pc[2], pc[3], pc[4], pc[5]);
     tc_fence_before();
     __syncthreads();
-    if (warp == 16) tmem_dealloc(tmem_base, S2_TMEM_COLS);
+    if (warp == S2_MMA_WARP) tmem_dealloc(tmem_base, S2_TMEM_COLS);
 }
 
 // SQ_STEM_TC=0 keeps the mma.sync fused stem for 256 x 256 tiles too (A/B runs)
