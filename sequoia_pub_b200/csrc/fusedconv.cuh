@@ -1,0 +1,334 @@
+// Layer-1 bottleneck tail in ONE kernel: conv2 (3x3, 64 -> 64, stride 1, + shift, ReLU) feeding conv3 (1x1, 64 -> 256, + shift,
+// + residual, ReLU) of src/resnet.py:73-93 without the 64-channel intermediate ever leaving the SM.
+//
+// Why: an SS-mode tcgen05.mma fetches its shared-memory operands at ~64 B/clk, so the two N = 64 launches are bound by operand
+// fetch and the 1x1 expansion by HBM; unfused they cost 40 + 49 us per block (floor of the pair: 46 us of HBM traffic).  Fused, the
+// expansion's A operand (128 pixels x 64 channels, bf16) is written by the first epilogue straight into TENSOR MEMORY - an epilogue
+// thread owns one pixel = one TMEM lane, so the tile is 32 packed columns stored with tcgen05.st - and the second MMA reads it from
+// there (A in TMEM) against the 256 x 64 weight tile that stays resident in shared memory: 33.5 MB less written and read per block,
+// one launch less, and no shared-memory fetch for A in the expansion.
+//
+//   warp 0      TMA producer: the nine 64 x 64 conv2 tap tiles and the 256 x 64 conv3 tile ONCE per CTA (104 KB, resident), then one
+//               18 x 10 halo box (64 channels) per 16 x 8 output patch into a ring of three slots
+//   warp 1      MMA issuer: A(i) = 36 tcgen05.mma (nine taps from shifted views of the halo, N = 64) into a double-buffered
+//               accumulator; B(i-1) = 4 tcgen05.mma (A from TMEM, N = 256) issued after A(i), so the tensor pipe never waits for
+//               the first epilogue
+//   warp 2      TMEM allocation (512 columns: 2 x 64 conv2 accumulators, 2 x 32 packed intermediates, 256 conv3 accumulator)
+//   warps 4-7   epilogue A: tcgen05.ld, + shift, ReLU, bf16 pack (cvt.rn.relu), tcgen05.st of the intermediate
+//   warps 8-11  epilogue B: the TMA epilogue of convgemm.cuh (residual sub-tiles prefetched by TMA into a per-warp ring, shift +
+//               residual + ReLU in place, cp.async.bulk.tensor stores), four 64-channel items per tile and warp
+// Results are bit-identical to the two separate launches: the intermediate is rounded to bf16 exactly as when it was stored.
+#pragma once
+#include "convgemm.cuh"
+
+namespace sq {
+
+constexpr int FB_W2_BYTES = 9 * 8192;                 // nine [64 n][64 k] tap tiles
+constexpr int FB_W3_BYTES = 256 * 128;                // [256 n][64 k]
+constexpr int FB_HS = 3;                              // halo slots
+constexpr int FB_D = 3;                               // ring depth of an epilogue-B warp
+constexpr int FB_SUB_BYTES = 32 * 128;
+constexpr int FB_RING_BYTES = 4 * FB_D * FB_SUB_BYTES;
+constexpr int FB_TAB_BYTES = (64 + 256) * 4;
+constexpr int FB_SMEM = FB_W2_BYTES + FB_W3_BYTES + FB_HS * HALO_BYTES + FB_RING_BYTES + FB_TAB_BYTES + 256;
+static_assert(FB_SMEM <= 232448, "shared memory budget");
+
+struct FbParams {
+    int batch, tiles_x, tiles_per_img, total_tiles;
+    const float* shift2;   // [64]  folded BN shift of conv2
+    const float* shift3;   // [256] folded BN shift of conv3
+};
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+bneck_l1_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW2, const __grid_constant__ CUtensorMap mapW3,
+                const __grid_constant__ CUtensorMap mapR, const __grid_constant__ CUtensorMap mapO, const FbParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* sW2 = smem;
+    uint8_t* sW3 = sW2 + FB_W2_BYTES;
+    uint8_t* halo = sW3 + FB_W3_BYTES;
+    uint8_t* ring = halo + FB_HS * HALO_BYTES;
+    float* tab = reinterpret_cast<float*>(ring + FB_RING_BYTES);          // shift2[64], shift3[256]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + FB_RING_BYTES + FB_TAB_BYTES);
+    uint64_t* w_full = bars;                 // weights resident
+    uint64_t* full_h = bars + 1;             // [HS]
+    uint64_t* empty_h = full_h + FB_HS;      // [HS]
+    uint64_t* acca_full = empty_h + FB_HS;   // [2] conv2 accumulator ready
+    uint64_t* acca_free = acca_full + 2;     // [2] read by the four epilogue-A warps
+    uint64_t* t_full = acca_free + 2;        // [2] intermediate written (four warps)
+    uint64_t* t_free = t_full + 2;           // [2] intermediate consumed (tcgen05.commit)
+    uint64_t* accb_full = t_free + 2;        // conv3 accumulator ready
+    uint64_t* accb_free = accb_full + 1;     // read by the four epilogue-B warps
+    uint64_t* res_full = accb_free + 1;      // [4][D]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_full + 4 * FB_D);
+    static_assert((1 + 2 * FB_HS + 8 + 2 + 4 * FB_D) * 8 + 4 <= 256, "barrier area");
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    asm volatile("griddepcontrol.launch_dependents;");
+    if (warp == 0 && lane == 0) {
+        if (smem_u32(smem) & 1023u) { printf("sequoia_b200: dynamic shared memory is not 1024-byte aligned\n"); __trap(); }
+        tma_prefetch_desc(&mapA); tma_prefetch_desc(&mapW2); tma_prefetch_desc(&mapW3); tma_prefetch_desc(&mapR); tma_prefetch_desc(&mapO);
+    }
+    if (warp == 1 && lane == 0) {
+        mbar_init(w_full, 1);
+        for (int i = 0; i < FB_HS; ++i) { mbar_init(&full_h[i], 1); mbar_init(&empty_h[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acca_full[i], 1); mbar_init(&acca_free[i], 4); mbar_init(&t_full[i], 4); mbar_init(&t_free[i], 1); }
+        mbar_init(accb_full, 1); mbar_init(accb_free, 4);
+        for (int i = 0; i < 4 * FB_D; ++i) mbar_init(&res_full[i], 1);
+        mbar_fence_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_ptr, 512);
+    for (int i = threadIdx.x; i < 64 + 256; i += GEMM_THREADS) tab[i] = i < 64 ? p.shift2[i] : p.shift3[i - 64];     // weights-side data: not produced by the previous kernel
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+
+    const int my_tiles = (int)blockIdx.x < p.total_tiles ? (p.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    constexpr uint32_t TM_ACCA = 0, TM_T = 128, TM_ACCB = 256;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            // ===================== TMA producer =====================
+            mbar_expect_tx(w_full, FB_W2_BYTES + FB_W3_BYTES);
+            for (int tap = 0; tap < 9; ++tap) tma_load_2d(&mapW2, w_full, sW2 + tap * 8192, tap * 64, 0);
+            tma_load_2d(&mapW3, w_full, sW3, 0, 0);
+            int hslot = 0; uint32_t hphase = 0;
+            for (int ti = 0; ti < my_tiles; ++ti) {
+                const int t = blockIdx.x + ti * gridDim.x;
+                const int img = t / p.tiles_per_img, rem = t - img * p.tiles_per_img;
+                const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+                mbar_wait(&empty_h[hslot], hphase ^ 1);
+                mbar_expect_tx(&full_h[hslot], HALO_BYTES_RAW);
+                tma_load_4d(&mapA, &full_h[hslot], halo + hslot * HALO_BYTES, 0, tx * HALO_TW - 1, ty * HALO_TH - 1, img);
+                if (++hslot == FB_HS) { hslot = 0; hphase ^= 1; }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        const uint32_t idesc_a = make_idesc_bf16(64, 0, 0, GEMM_BM), idesc_b = make_idesc_bf16(256, 0, 0, GEMM_BM);
+        constexpr uint32_t DESC_HI = (1u << 14) | (2u << 29);
+        constexpr uint32_t HI_K = DESC_HI | (1024u >> 4), HI_HALO = DESC_HI | ((HALO_PITCH * 128u) >> 4);
+        const uint32_t w2_lo = smem_u32(sW2) >> 4, w3_lo = smem_u32(sW3) >> 4, halo_lo = smem_u32(halo) >> 4;
+        auto desc = [](uint32_t lo, uint32_t hi) { return (static_cast<uint64_t>(hi) << 32) | lo; };
+        auto issue_b = [&](int j) {          // conv3 of tile j: A = intermediate in TMEM, B = resident weight tile
+            const int ts = j & 1;
+            mbar_wait(&t_full[ts], (j >> 1) & 1);
+            mbar_wait(accb_free, (j & 1) ^ 1);
+            tc_fence_after();
+            if (elect_one()) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_bf16_ts(tmem_base + TM_ACCB, tmem_base + TM_T + ts * 32 + k * 8, desc(w3_lo + 2 * k, HI_K), idesc_b, k ? 1u : 0u);
+                umma_commit(accb_full);
+                umma_commit(&t_free[ts]);
+            }
+            __syncwarp();
+        };
+        mbar_wait(w_full, 0);
+        int hslot = 0; uint32_t hphase = 0;
+        for (int ti = 0; ti < my_tiles; ++ti) {
+            const int as = ti & 1;
+            mbar_wait(&acca_free[as], ((ti >> 1) & 1) ^ 1);
+            mbar_wait(&full_h[hslot], hphase);
+            tc_fence_after();
+            if (elect_one()) {
+                uint32_t a_lo = halo_lo + hslot * (HALO_BYTES >> 4);
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16(tmem_base + TM_ACCA + as * 64, desc(a_lo + 2 * k, HI_HALO), desc(w2_lo + tap * 512 + 2 * k, HI_K), idesc_a, (tap | k) ? 1u : 0u);
+                    a_lo += (tap % 3 == 2) ? (HALO_PITCH - 2) * 8 : 8;
+                }
+                umma_commit(&empty_h[hslot]);
+                umma_commit(&acca_full[as]);
+            }
+            __syncwarp();
+            if (++hslot == FB_HS) { hslot = 0; hphase ^= 1; }
+            if (ti >= 1) issue_b(ti - 1);
+        }
+        if (my_tiles > 0) issue_b(my_tiles - 1);
+    } else if (warp >= 4 && warp < 8) {
+        // ===================== epilogue A: conv2 accumulator -> (+ shift, ReLU, bf16) -> intermediate in TMEM =====================
+        const int q = warp & 3;
+        const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        const float4* sh4 = reinterpret_cast<const float4*>(tab);
+        for (int ti = 0; ti < my_tiles; ++ti) {
+            const int as = ti & 1;
+            mbar_wait(&acca_full[as], (ti >> 1) & 1);
+            tc_fence_after();
+            float v[64];
+            tmem_ld32(lane_base + TM_ACCA + as * 64, v);
+            tmem_ld32(lane_base + TM_ACCA + as * 64 + 32, v + 32);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acca_free[as]);
+            uint32_t pk[32];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const float4 s4 = sh4[k];
+                asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(pk[2 * k]) : "f"(v[4 * k + 1] + s4.y), "f"(v[4 * k] + s4.x));
+                asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(pk[2 * k + 1]) : "f"(v[4 * k + 3] + s4.w), "f"(v[4 * k + 2] + s4.z));
+            }
+            mbar_wait(&t_free[as], ((ti >> 1) & 1) ^ 1);
+            tc_fence_after();
+            tmem_st32(lane_base + TM_T + as * 32, pk);
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&t_full[as]);
+        }
+    } else if (warp >= 8) {
+        // ===================== epilogue B: conv3 accumulator -> (+ shift, + residual, ReLU) in the warp's ring -> TMA store =====================
+        const int q = warp & 3;
+        uint8_t* myring = ring + q * FB_D * FB_SUB_BYTES;
+        uint64_t* myfull = res_full + q * FB_D;
+        const float4* bias4 = reinterpret_cast<const float4*>(tab + 64);
+        const int n_items = my_tiles * 4;
+        const uint32_t rowoff = (uint32_t)lane * 128u, swz = (uint32_t)(lane & 7);
+        const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + TM_ACCB;
+        auto coords = [&](int ti, int& img, int& ox0, int& row0) {
+            const int t = blockIdx.x + ti * gridDim.x;
+            img = t / p.tiles_per_img; const int rem = t - img * p.tiles_per_img;
+            const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+            ox0 = tx * HALO_TW; row0 = ty * HALO_TH + q * 4;
+        };
+        // residual prefetch cursor (lane 0)
+        int pf_j = 0, pf_cc = 0, pf_slot = 0, pf_ti = 0;
+        auto request_next = [&]() {
+            int img, ox0, row0; coords(pf_ti, img, ox0, row0);
+            mbar_expect_tx(&myfull[pf_slot], FB_SUB_BYTES);
+            tma_load_4d(&mapR, &myfull[pf_slot], myring + pf_slot * FB_SUB_BYTES, pf_cc * 64, ox0, row0, img);
+            ++pf_j; if (++pf_slot == FB_D) pf_slot = 0;
+            if (++pf_cc == 4) { pf_cc = 0; ++pf_ti; }
+        };
+        if (lane == 0)
+            for (int i = 0; i < FB_D - 1 && i < n_items; ++i) request_next();
+        int j = 0, slot = 0; uint32_t sphase = 0;
+        for (int ti = 0; ti < my_tiles; ++ti) {
+            int img, ox0, row0; coords(ti, img, ox0, row0);
+            mbar_wait(accb_full, ti & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int cc = 0; cc < 4; ++cc, ++j) {
+                uint8_t* sl = myring + slot * FB_SUB_BYTES;
+                uint8_t* rowp = sl + rowoff;
+                float v[64];
+                tmem_ld32(tacc + cc * 64, v);
+                tmem_ld32(tacc + cc * 64 + 32, v + 32);
+                uint4 r[8];
+                mbar_wait(&myfull[slot], sphase);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) r[k] = *reinterpret_cast<const uint4*>(rowp + ((k ^ swz) << 4));     // 128B swizzle: chunk ^ (row % 8)
+                tmem_ld_wait();
+                if (cc == 3) {                      // the accumulator is in registers: conv3 of the next tile may overwrite it
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(accb_free);
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    float* f = v + 8 * k;
+                    const float4 b0 = bias4[cc * 16 + 2 * k], b1 = bias4[cc * 16 + 2 * k + 1];
+                    f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w; f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+                    const uint32_t w[4] = {r[k].x, r[k].y, r[k].z, r[k].w};
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        f[2 * u] += __uint_as_float(w[u] << 16);
+                        f[2 * u + 1] += __uint_as_float(w[u] & 0xffff0000u);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) f[u] = fmaxf(f[u], 0.0f);
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float* f = v + 8 * k;
+                    __nv_bfloat162 h2;
+                    h2 = __floats2bfloat162_rn(f[0], f[1]); r[k].x = *reinterpret_cast<uint32_t*>(&h2);
+                    h2 = __floats2bfloat162_rn(f[2], f[3]); r[k].y = *reinterpret_cast<uint32_t*>(&h2);
+                    h2 = __floats2bfloat162_rn(f[4], f[5]); r[k].z = *reinterpret_cast<uint32_t*>(&h2);
+                    h2 = __floats2bfloat162_rn(f[6], f[7]); r[k].w = *reinterpret_cast<uint32_t*>(&h2);
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) *reinterpret_cast<uint4*>(rowp + ((k ^ swz) << 4)) = r[k];
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_4d(&mapO, sl, cc * 64, ox0, row0, img);      // 64 channels x 8 pixels x 4 output rows
+                    bulk_commit_group();
+                    if (pf_j < n_items) {
+                        if (j >= 1) bulk_wait_group_read<1>();              // the store of item j-1 has read the slot being refilled
+                        request_next();
+                    }
+                }
+                __syncwarp();
+                if (++slot == FB_D) { slot = 0; sphase ^= 1; }
+            }
+        }
+        if (lane == 0) bulk_wait_group_read<0>();
+    }
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// in: [batch, H, W, 64] (conv1's output), res / out: [batch, H, W, 256]; w2: [64][3][3][64], w3: [256][64] (BN scale folded)
+inline bool bneck_l1_supported(int H, int W) { return H % HALO_TH == 0 && W % HALO_TW == 0; }
+
+inline int bneck_l1_launch(const bf16* in, const bf16* w2, const float* shift2, const bf16* w3, const float* shift3, const bf16* res, bf16* out,
+                           int batch, int H, int W, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t err = cudaFuncSetAttribute(bneck_l1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM);
+        if (err != cudaSuccess) { set_error("bneck_l1: cudaFuncSetAttribute: %s", cudaGetErrorString(err)); return -1; }
+        configured = true;
+    }
+    FbParams kp;
+    kp.batch = batch; kp.tiles_x = W / HALO_TW; kp.tiles_per_img = (H / HALO_TH) * kp.tiles_x; kp.total_tiles = batch * kp.tiles_per_img;
+    kp.shift2 = shift2; kp.shift3 = shift3;
+    CUtensorMap maps[5];
+    {
+        cuuint64_t dims[4] = {64, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)batch};
+        cuuint64_t strides[3] = {64 * 2, (cuuint64_t)W * 64 * 2, (cuuint64_t)H * W * 64 * 2};
+        cuuint32_t box[4] = {64, HALO_PITCH, HALO_TH + 2, 1}, estr[4] = {1, 1, 1, 1};
+        if (encode_map(&maps[0], in, 4, dims, strides, box, estr)) return -1;
+    }
+    {
+        cuuint64_t dims[2] = {576, 64}, strides[1] = {576 * 2};
+        cuuint32_t box[2] = {64, 64}, estr[2] = {1, 1};
+        if (encode_map(&maps[1], w2, 2, dims, strides, box, estr)) return -1;
+    }
+    {
+        cuuint64_t dims[2] = {64, 256}, strides[1] = {64 * 2};
+        cuuint32_t box[2] = {64, 256}, estr[2] = {1, 1};
+        if (encode_map(&maps[2], w3, 2, dims, strides, box, estr)) return -1;
+    }
+    {
+        cuuint64_t dims[4] = {256, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)batch};
+        cuuint64_t strides[3] = {256 * 2, (cuuint64_t)W * 256 * 2, (cuuint64_t)H * W * 256 * 2};
+        cuuint32_t box[4] = {64, HALO_TW, 4, 1}, estr[4] = {1, 1, 1, 1};
+        if (encode_map(&maps[3], res, 4, dims, strides, box, estr)) return -1;
+        if (encode_map(&maps[4], out, 4, dims, strides, box, estr)) return -1;
+    }
+    const int grid = kp.total_tiles < num_sms() ? kp.total_tiles : num_sms();
+    static const int pdl = getenv("SQ_PDL") ? atoi(getenv("SQ_PDL")) : 1;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = FB_SMEM; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    const double M = (double)batch * H * W;
+    gemm_timing_begin(st, 2.0 * M * 64 * 576 + 2.0 * M * 256 * 64);
+    cudaError_t err = cudaLaunchKernelEx(&cfg, bneck_l1_kernel, maps[0], maps[1], maps[2], maps[3], maps[4], kp);
+    if (err == cudaSuccess) err = cudaGetLastError();
+    gemm_timing_end(st);
+    if (err != cudaSuccess) { set_error("bneck_l1 launch: %s", cudaGetErrorString(err)); return -1; }
+    return 0;
+}
+
+}  // namespace sq

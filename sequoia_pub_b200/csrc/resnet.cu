@@ -7,6 +7,7 @@
 // buffer (K = 147 padded to 192) so it also runs on the tensor cores; uint8 -> /255 -> normalise is fused
 // into that im2col kernel (R4), max-pool and the 7x7 top-left average pool (fact 4) are small bandwidth kernels.
 #include "convgemm.cuh"
+#include "fusedconv.cuh"
 #include "../../include/sequoia_b200.h"
 #include <stdlib.h>
 
@@ -759,6 +760,12 @@ static int pool_fused_enabled() {
     return v;
 }
 
+static int bneck_fuse_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SQ_BNECK_FUSE"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v;
+}
+
 static int convgemm_enabled() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("SQ_CONVGEMM"); v = (e && e[0] == '0') ? 0 : 1; }
@@ -915,7 +922,10 @@ int sq_resnet50_extract(const void* input, int input_kind, int batch, int H, int
             const ConvSpec& c1 = p.conv[ci]; const ConvSpec& c2 = p.conv[ci + 1]; const ConvSpec& c3 = p.conv[ci + 2];
             int h1, w1, h2, w2, h3, w3, hd, wd;
             if (run_conv(c1, wp, shifts, big[x], batch, h, w, small_[0], nullptr, nullptr, true, st, &h1, &w1)) return -1;
-            if (run_conv(c2, wp, shifts, small_[0], batch, h1, w1, small_[1], nullptr, nullptr, true, st, &h2, &w2, nullptr, im2col, im2col_bytes)) return -1;
+            // layer 1: conv2 + conv3 as one kernel (the 64-channel intermediate stays in tensor memory); SQ_BNECK_FUSE=0 keeps the two launches
+            const bool fuse_tail = stg == 0 && bneck_fuse_enabled() && convgemm_enabled() && !last && bneck_l1_supported(h1, w1);
+            if (fuse_tail) { h2 = h1; w2 = w1; }
+            else if (run_conv(c2, wp, shifts, small_[0], batch, h1, w1, small_[1], nullptr, nullptr, true, st, &h2, &w2, nullptr, im2col, im2col_bytes)) return -1;
             const bf16* res = big[x];
             const int y = (x + 1) % 3, d = (x + 2) % 3;
             if (down) {
@@ -924,6 +934,10 @@ int sq_resnet50_extract(const void* input, int input_kind, int batch, int H, int
             }
             // the last convolution of an 8x8 final map feeds the fused average pool (no fp32 map, no pooling kernel)
             const bool fuse_pool = last && h2 == 8 && w2 == 8 && convgemm_enabled() && pool_fused_enabled();
+            if (fuse_tail) {
+                if (bneck_l1_launch(small_[0], wp + c2.w_off, shifts + c2.s_off, wp + c3.w_off, shifts + c3.s_off, res, big[y], batch, h1, w1, st)) return -1;
+                h3 = h2; w3 = w2;
+            } else
             if (fuse_pool) {
                 cudaMemsetAsync(features, 0, (size_t)batch * 2048 * sizeof(float), st);
                 if (run_conv(c3, wp, shifts, small_[1], batch, h2, w2, nullptr, nullptr, res, true, st, &h3, &w3, features)) return -1;

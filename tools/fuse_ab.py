@@ -1,0 +1,32 @@
+"""A/B of the fused layer-1 bottleneck tail (SQ_BNECK_FUSE=1, default) against the two separate launches (SQ_BNECK_FUSE=0):
+features must be bit-identical; batch time with 1 and 2 extractor lanes.  Each setting runs in its own process (the switch is read once)."""
+import hashlib, os, subprocess, sys
+
+if len(sys.argv) > 1 and sys.argv[1] == "child":
+    import torch
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from oracle import resnet50_oracle as O
+    from sequoia_pub_b200.resnet import resnet50
+    m = resnet50().eval(); m.load_state_dict(O.make_state_dict(0)); m = m.cuda()
+    x = torch.randint(0, 256, (1024, 256, 256, 3), dtype=torch.uint8, device="cuda", generator=torch.Generator(device="cuda").manual_seed(3))
+    ref = torch.cat([m.extract_uint8(x[b:b + 64]) for b in range(0, 1024, 64)])
+    small = m.extract_uint8(x[:5])
+    torch.cuda.synchronize()
+    assert torch.equal(small, ref[:5])
+    print("sha", hashlib.sha256(ref.cpu().numpy().tobytes()).hexdigest()[:16], "finite", bool(torch.isfinite(ref).all()))
+    for lanes in (1, 2):
+        out = m.extract_many(x, lanes=lanes); torch.cuda.synchronize()
+        assert torch.equal(out, ref), lanes
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(3): m.extract_many(x, out=out, lanes=lanes)
+        e.record(); torch.cuda.synchronize()
+        ms = s.elapsed_time(e) / 3
+        print(f"lanes={lanes}: {ms / 16:.3f} ms/batch -> {1024 / ms * 1e3:.0f} patches/s")
+else:
+    for rep in range(2):
+        for v in ("0", "1"):
+            env = dict(os.environ, SQ_BNECK_FUSE=v)
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "child"], env=env, capture_output=True, text=True, timeout=150)
+            print(f"== SQ_BNECK_FUSE={v} rc={r.returncode}")
+            print((r.stdout + r.stderr[-1500:]).strip())
