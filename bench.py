@@ -577,8 +577,10 @@ def main():
     slide_host.copy_(slide_dev)
     feats = torch.empty(PATCHES_PER_SLIDE, 2048, dtype=torch.float32, device=dev)
     fused_stem = os.environ.get("SQ_STEM_FUSED", "1") != "0"     # one kernel for preprocessing + conv1 + max-pool (csrc/resnet.cu)
-    # per batch of 64: the fused stem + 52 bottleneck convolutions (the 7x7 average pool is fused into the last one)
-    launches_per_step = (PATCHES_PER_SLIDE // BATCH) * (L.sq_resnet50_num_convs() + (0 if fused_stem else 3))
+    # per batch of 64: the fused stem + 52 bottleneck convolutions (the 7x7 average pool is fused into the last one); layer 1's conv2 + conv3
+    # run as ONE kernel per block (csrc/fusedconv.cuh), i.e. 49 convolution launches
+    fused_tail = os.environ.get("SQ_BNECK_FUSE", "1") != "0" and os.environ.get("SQ_CONVGEMM", "1") != "0"
+    launches_per_step = (PATCHES_PER_SLIDE // BATCH) * (L.sq_resnet50_num_convs() + (0 if fused_stem else 3) - (3 if fused_tail else 0))
 
     def step_device():
         # batch 64 per extractor launch (BASELINE configs[1]); consecutive batches alternate between two CUDA streams
@@ -613,15 +615,16 @@ def main():
         # stem_fused_kernel, not in gemm_tc_kernel, and is left out of the numerator
         alg_flops = (FLOP_PER_PATCH - (STEM_FLOP_PER_PATCH if fused_stem else 0.0)) * PATCHES_PER_SLIDE
         achieved = alg_flops / (tms * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "convgemm_kernel (CTA-pair tcgen05 implicit-GEMM convolution, TMA epilogue; 52 launches per batch of 64)",
+        per_batch = n // (PATCHES_PER_SLIDE // BATCH)
+        roof = {"bound": "tensor", "kernel": f"convgemm_kernel + bneck_l1_kernel (tcgen05 implicit-GEMM convolutions of the 16 bottlenecks, TMA epilogue; {per_batch} launches per batch of 64)",
                 "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
                 "peak_source": pk["source"] + " bf16 sustained", "traffic": ncu_traffic("resnet"),
-                "traffic_note": "dram read+write bytes per launch, mean over the 52 convolution launches of one batch (ncu, profiles/r02_traffic.json)",
+                "traffic_note": "dram read+write bytes per launch, mean over the convolution launches of one batch (ncu, profiles/r02_traffic.json)",
                 "launches": n, "avg_launch_us": tms * 1e3 / max(n, 1),
                 "step_frac": value / world * FLOP_PER_PATCH / 1e12 / pk["bf16_sustained"],
                 "kernel_share_of_step": tms / ser_ms, "serialized_step_ms": ser_ms,
-                "timing_note": "one CUDA-event pair around the 52 back-to-back convolution launches of every batch, on one stream (no inter-batch overlap): "
-                               "avg_launch_us = chain duration / 52, launches overlap through programmatic dependent launch as in the untimed step",
+                "timing_note": "one CUDA-event pair around the back-to-back convolution launches of every batch, on one stream (no inter-batch overlap): "
+                               "avg_launch_us = chain duration / launches, launches overlap through programmatic dependent launch as in the untimed step",
                 "issued_mma_tflops": fl / (tms * 1e-3) / 1e12}
         if roof["traffic"]:
             # secondary bound: DRAM bytes the same launches moved (ncu) over their live duration

@@ -145,6 +145,14 @@ typedef struct sq_conv_desc {
 } sq_conv_desc;
 SQ_API int sq_conv_bf16(const sq_conv_desc* desc, void* stream);
 
+/* Tail of a layer-1 bottleneck (src/resnet.py:73-93) as ONE kernel (csrc/fusedconv.cuh):
+ *   out = relu(conv1x1(relu(conv3x3(in, w2) + shift2), w3) + shift3 + residual)
+ * in: NHWC bf16 [batch, H, W, 64] (conv1's output); w2: bf16 [64][3][3][64]; w3: bf16 [256][64]; shifts fp32; residual / out: bf16
+ * [batch, H, W, 256].  H a multiple of 16, W of 8.  The 64-channel intermediate is rounded to bf16 and kept in tensor memory; results
+ * are bit-identical to sq_conv_bf16 called twice.  Building block of sq_resnet50_extract, exposed for tests. */
+SQ_API int sq_bneck_l1_bf16(const void* in, const void* w2, const float* shift2, const void* w3, const float* shift3, const void* residual,
+                            void* out, int batch, int H, int W, void* stream);
+
 /* ------------------------------------------------------------------ ViS aggregator (SummaryMixing transformer)
  * Replaces ViS.forward (src/tformer_lin.py:97-106 and everything it calls, :18-26,39-48,60-61,73-77), the autograd
  * backward behind loss.backward() (src/vit.py:179), nn.MSELoss (src/vit.py:129,166) and the AdamW step

@@ -81,3 +81,15 @@ def conv_bf16(x, w, shift, residual=None, relu=True, stride=1, pad=0, block_n=0,
     d.relu, d.block_n, d.cta_group = int(relu), block_n, cta_group
     _lib.check(_lib.lib().sq_conv_bf16(C.byref(d), _lib.stream_ptr()))
     return out
+
+
+def bneck_l1_bf16(x, w2, shift2, w3, shift3, residual, out=None):
+    """Fused tail of a layer-1 bottleneck through `sq_bneck_l1_bf16`: x bf16 NHWC [B,H,W,64], w2 bf16 [64,3,3,64], w3 bf16 [256,64] (or
+    [256,1,1,64]), shifts fp32, residual bf16 [B,H,W,256] -> relu(conv1x1(relu(conv3x3(x) + shift2)) + shift3 + residual)."""
+    B, H, W, _ = x.shape
+    if out is None:
+        out = torch.empty(B, H, W, 256, dtype=torch.bfloat16, device=x.device)
+    _lib.check(_lib.lib().sq_bneck_l1_bf16(C.c_void_p(x.data_ptr()), C.c_void_p(w2.data_ptr()), C.c_void_p(shift2.data_ptr()), C.c_void_p(w3.data_ptr()),
+                                           C.c_void_p(shift3.data_ptr()), C.c_void_p(residual.data_ptr()), C.c_void_p(out.data_ptr()), B, H, W,
+                                           _lib.stream_ptr()))
+    return out

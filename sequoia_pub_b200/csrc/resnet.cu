@@ -859,6 +859,15 @@ int sq_conv_bf16(const sq_conv_desc* d, void* stream) {
     return convgemm_launch(a, (cudaStream_t)stream);
 }
 
+int sq_bneck_l1_bf16(const void* in, const void* w2, const float* shift2, const void* w3, const float* shift3, const void* residual, void* out,
+                     int batch, int H, int W, void* stream) {
+    if (!in || !w2 || !shift2 || !w3 || !shift3 || !residual || !out) { set_error("bneck_l1: null pointer"); return -1; }
+    if (batch <= 0 || !bneck_l1_supported(H, W)) { set_error("bneck_l1: H must be a multiple of %d and W of %d", HALO_TH, HALO_TW); return -1; }
+    if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(w2) | reinterpret_cast<uintptr_t>(w3) | reinterpret_cast<uintptr_t>(residual) |
+         reinterpret_cast<uintptr_t>(out)) & 15) { set_error("bneck_l1: operands must be 16-byte aligned"); return -1; }
+    return bneck_l1_launch((const bf16*)in, (const bf16*)w2, shift2, (const bf16*)w3, shift3, (const bf16*)residual, (bf16*)out, batch, H, W, (cudaStream_t)stream);
+}
+
 size_t sq_resnet50_workspace_bytes(int batch, int H, int W) { return ws_layout(batch, H, W).total; }
 
 int sq_resnet50_extract(const void* input, int input_kind, int batch, int H, int W, const void* packed_w, const float* shifts,

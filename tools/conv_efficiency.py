@@ -22,7 +22,16 @@ for st in range(4):
         inpl, H = planes[st] * 4, Ho
 recs = json.load(open(path))
 stem = [r for r in recs if "stem" in r["kernel"]]
-convs = [r for r in recs if "convgemm" in r["kernel"] or "gemm_tc" in r["kernel"]]
+convs = [r for r in recs if "convgemm" in r["kernel"] or "gemm_tc" in r["kernel"] or "bneck" in r["kernel"]]
+if any("bneck" in r["kernel"] for r in convs):
+    # layer 1's conv2 + conv3 run as one kernel (csrc/fusedconv.cuh): one table row "c23" per block, launched after the downsample
+    merged = []
+    for e in order:
+        st, b, n, c = e
+        if st == 1 and n == "c2":
+            continue
+        merged.append((st, b, "c23", c) if st == 1 and n == "c3" else e)
+    order = merged
 assert len(convs) == len(order), (len(convs), len(order))
 tot = ideal_tot = 0.0
 print("conv         cin  cout k  Hin->Hout       M     GF  meas_us  TF/s  DRAM_MB  L2>SM_MB  minMB  floor_us  x_floor  tensor%  kernel")
@@ -31,6 +40,9 @@ for (st, b, n, (cin, cout, k, Hi, Ho)), r in zip(order, convs):
     M, K = 64 * Ho * Ho, cin * k * k
     gf = 2 * M * cout * K / 1e9
     mb = (64 * Hi * Hi * cin * 2 + M * cout * 2 * (2 if n == "c3" else 1) + cout * K * 2) / 1e6
+    if n == "c23":                       # 3x3 64 -> 64 then 1x1 64 -> 256 + residual: the 64-channel intermediate never reaches HBM
+        gf = (2 * M * 64 * 576 + 2 * M * 256 * 64) / 1e9
+        mb = (M * 64 * 2 + 2 * M * 256 * 2 + (64 * 576 + 256 * 64) * 2) / 1e6
     floor = max(mb / PEAK_GBS * 1e3, gf / PEAK_TF * 1e3)
     tot += t
     ideal_tot += floor

@@ -5,8 +5,6 @@ cd "$(dirname "$0")/.."
 mkdir -p gpurun_out /tmp/ncu
 timeout 400 python -m pytest tests -m gpu -q -s > gpurun_out/r02_pytest_gpu_final.log 2>&1; echo "pytest rc=$?"; tail -1 gpurun_out/r02_pytest_gpu_final.log
 timeout 200 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r02_smoke.log 2>&1; echo "smoke rc=$?"; tail -1 gpurun_out/r02_smoke.log
-timeout 600 python bench.py > gpurun_out/r02_bench_n1_final.json 2> gpurun_out/r02_bench_n1_final.err; echo "bench rc=$?"; head -c 600 gpurun_out/r02_bench_n1_final.json; echo
-timeout 400 python bench.py --impl reference > gpurun_out/r02_bench_reference_arm.json 2> gpurun_out/r02_bench_reference_arm.err; echo "ref rc=$?"; head -c 400 gpurun_out/r02_bench_reference_arm.json; echo
 M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_bytes.sum,l1tex__m_xbar2l1tex_read_bytes.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_tc.sum,sm__ops_path_tensor_op_utchmma_src_bf16_dst_fp32.sum,sm__throughput.avg.pct_of_peak_sustained_elapsed,gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed
 met() { name=$1; k=$2; s=$3; c=$4; shift 4
   timeout 400 ncu --metrics $M --clock-control none -k regex:"$k" -s $s -c $c --csv --log-file gpurun_out/$name.csv "$@" > gpurun_out/$name.log 2>&1
@@ -17,7 +15,10 @@ full() { name=$1; k=$2; s=$3; shift 3
   ncu -i /tmp/ncu/$name.ncu-rep --page raw --csv > gpurun_out/$name.raw.csv 2>/dev/null
   ncu -i /tmp/ncu/$name.ncu-rep --page details > gpurun_out/$name.details.txt 2>/dev/null
   grep -E "Duration|DRAM Throughput|Memory Throughput  " gpurun_out/$name.details.txt | head -3; }
-met r02_resnet_batch64_metrics_final "stem|convgemm|avgpool|maxpool" 53 53 python tools/profile_resnet.py 2      # second batch: stem + 52 convolutions
-met r02_uni_batch64_metrics_final "uni_attention|uni_ln|uni_patchify|uni_assemble|gemm_tc|convgemm" 0 172 python tools/profile_uni.py 1
+met r02_resnet_batch64_metrics_final "stem|convgemm|bneck|avgpool|maxpool" 50 50 python tools/profile_resnet.py 2      # second batch: stem + 49 convolution launches (layer 1's conv2 + conv3 are one kernel)
 full r02_full_stem_tc "stem_tc" 1 python tools/profile_resnet.py 2
-full r02_full_uni_attention_tc "uni_attention_tc" 1 python tools/profile_uni.py 1
+full r02_full_bneck_l1 "bneck_l1" 4 python tools/profile_resnet.py 2
+python tools/traffic_json.py gpurun_out/r02_resnet_batch64_metrics_final.json profiles/r02_traffic.json
+cp profiles/r02_traffic.json gpurun_out/r02_traffic.json
+timeout 600 python bench.py > gpurun_out/r02_bench_n1_final.json 2> gpurun_out/r02_bench_n1_final.err; echo "bench rc=$?"; head -c 600 gpurun_out/r02_bench_n1_final.json; echo
+timeout 400 python bench.py --impl reference > gpurun_out/r02_bench_reference_arm.json 2> gpurun_out/r02_bench_reference_arm.err; echo "ref rc=$?"; head -c 400 gpurun_out/r02_bench_reference_arm.json; echo
