@@ -8,35 +8,41 @@
 // there (A in TMEM) against the 256 x 64 weight tile that stays resident in shared memory: 33.5 MB less written and read per block,
 // one launch less, and no shared-memory fetch for A in the expansion.
 //
-//   warp 0      TMA producer: the nine 64 x 64 conv2 tap tiles and the 256 x 64 conv3 tile ONCE per CTA (104 KB, resident), then one
-//               18 x 10 halo box (64 channels) per 16 x 8 output patch into a ring of three slots
+//   warp 0      TMA producer: the 256 x 64 conv3 tile ONCE per CTA (resident); per 16 x 8 output patch one 18 x 10 halo box (64
+//               channels, two slots) and the nine 64 x 64 conv2 tap tiles through a 4-stage ring
 //   warp 1      MMA issuer: A(i) = 36 tcgen05.mma (nine taps from shifted views of the halo, N = 64) into a double-buffered
 //               accumulator; B(i-1) = 4 tcgen05.mma (A from TMEM, N = 256) issued after A(i), so the tensor pipe never waits for
 //               the first epilogue
 //   warp 2      TMEM allocation (512 columns: 2 x 64 conv2 accumulators, 2 x 32 packed intermediates, 256 conv3 accumulator)
-//   warps 4-7   epilogue A: tcgen05.ld, + shift, ReLU, bf16 pack (cvt.rn.relu), tcgen05.st of the intermediate
-//   warps 8-11  epilogue B: the TMA epilogue of convgemm.cuh (residual sub-tiles prefetched by TMA into a per-warp ring, shift +
-//               residual + ReLU in place, cp.async.bulk.tensor stores), four 64-channel items per tile and warp
+//   warps 4-7   epilogue A: tcgen05.ld, + shift, ReLU, bf16 pack (cvt.rn.relu), tcgen05.st of the intermediate - and, because that is
+//               300 cycles of a 5000-cycle tile, channel chunks 2 and 3 of epilogue B of the previous tile
+//   warps 8-11  epilogue B, channel chunks 0 and 1: the TMA epilogue of convgemm.cuh (residual sub-tiles prefetched by TMA into a
+//               per-warp ring, shift + residual + ReLU in place, cp.async.bulk.tensor stores)
+// Measured steps (per-role cycle counters, SQ_BNECK_PROF=1): with epilogue B on four warps the kernel took 67 us and the MMA warp
+// waited 30 % of the time for the conv3 accumulator to drain (1800 cycles per 32 x 64 item); staging the halo as three shifted
+// copies (every tap a plain K-major tile of whole swizzle atoms) changed nothing, so the shifted views stay.
 // Results are bit-identical to the two separate launches: the intermediate is rounded to bf16 exactly as when it was stored.
 #pragma once
 #include "convgemm.cuh"
 
 namespace sq {
 
-constexpr int FB_W2_BYTES = 9 * 8192;                 // nine [64 n][64 k] tap tiles
+constexpr int FB_WS = 4;                              // conv2 tap-tile ring: [64 n][64 k] per stage
+constexpr int FB_W2_BYTES = FB_WS * 8192;
 constexpr int FB_W3_BYTES = 256 * 128;                // [256 n][64 k]
-constexpr int FB_HS = 3;                              // halo slots
+constexpr int FB_HS = 2;                              // halo slots (HALO_BYTES each: 18 x 10 pixels x 64 channels)
 constexpr int FB_D = 3;                               // ring depth of an epilogue-B warp
 constexpr int FB_SUB_BYTES = 32 * 128;
-constexpr int FB_RING_BYTES = 4 * FB_D * FB_SUB_BYTES;
+constexpr int FB_RING_BYTES = 8 * FB_D * FB_SUB_BYTES;
 constexpr int FB_TAB_BYTES = (64 + 256) * 4;
-constexpr int FB_SMEM = FB_W2_BYTES + FB_W3_BYTES + FB_HS * HALO_BYTES + FB_RING_BYTES + FB_TAB_BYTES + 256;
+constexpr int FB_SMEM = FB_W2_BYTES + FB_W3_BYTES + FB_HS * HALO_BYTES + FB_RING_BYTES + FB_TAB_BYTES + 512;
 static_assert(FB_SMEM <= 232448, "shared memory budget");
 
 struct FbParams {
     int batch, tiles_x, tiles_per_img, total_tiles;
     const float* shift2;   // [64]  folded BN shift of conv2
     const float* shift3;   // [256] folded BN shift of conv3
+    int prof;              // SQ_BNECK_PROF=1: block 0 prints the cycles each role spends waiting
 };
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -49,18 +55,20 @@ bneck_l1_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     uint8_t* ring = halo + FB_HS * HALO_BYTES;
     float* tab = reinterpret_cast<float*>(ring + FB_RING_BYTES);          // shift2[64], shift3[256]
     uint64_t* bars = reinterpret_cast<uint64_t*>(ring + FB_RING_BYTES + FB_TAB_BYTES);
-    uint64_t* w_full = bars;                 // weights resident
-    uint64_t* full_h = bars + 1;             // [HS]
+    uint64_t* w_full = bars;                 // conv3 weights resident
+    uint64_t* full_w = bars + 1;             // [WS] conv2 tap tile landed
+    uint64_t* empty_w = full_w + FB_WS;      // [WS]
+    uint64_t* full_h = empty_w + FB_WS;      // [HS]
     uint64_t* empty_h = full_h + FB_HS;      // [HS]
     uint64_t* acca_full = empty_h + FB_HS;   // [2] conv2 accumulator ready
     uint64_t* acca_free = acca_full + 2;     // [2] read by the four epilogue-A warps
     uint64_t* t_full = acca_free + 2;        // [2] intermediate written (four warps)
     uint64_t* t_free = t_full + 2;           // [2] intermediate consumed (tcgen05.commit)
     uint64_t* accb_full = t_free + 2;        // conv3 accumulator ready
-    uint64_t* accb_free = accb_full + 1;     // read by the four epilogue-B warps
-    uint64_t* res_full = accb_free + 1;      // [4][D]
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_full + 4 * FB_D);
-    static_assert((1 + 2 * FB_HS + 8 + 2 + 4 * FB_D) * 8 + 4 <= 256, "barrier area");
+    uint64_t* accb_free = accb_full + 1;     // read by the eight warps that run epilogue B
+    uint64_t* res_full = accb_free + 1;      // [8][D]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_full + 8 * FB_D);
+    static_assert((1 + 2 * FB_WS + 2 * FB_HS + 8 + 2 + 8 * FB_D) * 8 + 4 <= 512, "barrier area");
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     asm volatile("griddepcontrol.launch_dependents;");
@@ -70,10 +78,11 @@ bneck_l1_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     }
     if (warp == 1 && lane == 0) {
         mbar_init(w_full, 1);
+        for (int i = 0; i < FB_WS; ++i) { mbar_init(&full_w[i], 1); mbar_init(&empty_w[i], 1); }
         for (int i = 0; i < FB_HS; ++i) { mbar_init(&full_h[i], 1); mbar_init(&empty_h[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&acca_full[i], 1); mbar_init(&acca_free[i], 4); mbar_init(&t_full[i], 4); mbar_init(&t_free[i], 1); }
-        mbar_init(accb_full, 1); mbar_init(accb_free, 4);
-        for (int i = 0; i < 4 * FB_D; ++i) mbar_init(&res_full[i], 1);
+        mbar_init(accb_full, 1); mbar_init(accb_free, 8);
+        for (int i = 0; i < 8 * FB_D; ++i) mbar_init(&res_full[i], 1);
         mbar_fence_init();
     }
     if (warp == 2) tmem_alloc(tmem_ptr, 512);
@@ -85,16 +94,20 @@ bneck_l1_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     const uint32_t tmem_base = *tmem_ptr;
     asm volatile("griddepcontrol.wait;" ::: "memory");
 
+    long long pc[6] = {0, 0, 0, 0, 0, 0}; const long long pt0 = clock64();
+    const bool prof = p.prof != 0;
+    auto twait = [&](uint64_t* bar, uint32_t parity, int slot) {
+        if (prof) { const long long w0 = clock64(); mbar_wait(bar, parity); pc[slot] += clock64() - w0; } else mbar_wait(bar, parity);
+    };
     const int my_tiles = (int)blockIdx.x < p.total_tiles ? (p.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     constexpr uint32_t TM_ACCA = 0, TM_T = 128, TM_ACCB = 256;
 
     if (warp == 0) {
         if (elect_one()) {
             // ===================== TMA producer =====================
-            mbar_expect_tx(w_full, FB_W2_BYTES + FB_W3_BYTES);
-            for (int tap = 0; tap < 9; ++tap) tma_load_2d(&mapW2, w_full, sW2 + tap * 8192, tap * 64, 0);
+            mbar_expect_tx(w_full, FB_W3_BYTES);
             tma_load_2d(&mapW3, w_full, sW3, 0, 0);
-            int hslot = 0; uint32_t hphase = 0;
+            int hslot = 0; uint32_t hphase = 0; int ws = 0; uint32_t wphase = 0;
             for (int ti = 0; ti < my_tiles; ++ti) {
                 const int t = blockIdx.x + ti * gridDim.x;
                 const int img = t / p.tiles_per_img, rem = t - img * p.tiles_per_img;
@@ -103,6 +116,12 @@ bneck_l1_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 mbar_expect_tx(&full_h[hslot], HALO_BYTES_RAW);
                 tma_load_4d(&mapA, &full_h[hslot], halo + hslot * HALO_BYTES, 0, tx * HALO_TW - 1, ty * HALO_TH - 1, img);
                 if (++hslot == FB_HS) { hslot = 0; hphase ^= 1; }
+                for (int tap = 0; tap < 9; ++tap) {
+                    mbar_wait(&empty_w[ws], wphase ^ 1);
+                    mbar_expect_tx(&full_w[ws], 8192);
+                    tma_load_2d(&mapW2, &full_w[ws], sW2 + ws * 8192, tap * 64, 0);
+                    if (++ws == FB_WS) { ws = 0; wphase ^= 1; }
+                }
             }
         }
         __syncwarp();
@@ -115,8 +134,8 @@ bneck_l1_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         auto desc = [](uint32_t lo, uint32_t hi) { return (static_cast<uint64_t>(hi) << 32) | lo; };
         auto issue_b = [&](int j) {          // conv3 of tile j: A = intermediate in TMEM, B = resident weight tile
             const int ts = j & 1;
-            mbar_wait(&t_full[ts], (j >> 1) & 1);
-            mbar_wait(accb_free, (j & 1) ^ 1);
+            twait(&t_full[ts], (j >> 1) & 1, 3);
+            twait(accb_free, (j & 1) ^ 1, 4);
             tc_fence_after();
             if (elect_one()) {
 #pragma unroll
@@ -127,104 +146,77 @@ bneck_l1_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             __syncwarp();
         };
         mbar_wait(w_full, 0);
-        int hslot = 0; uint32_t hphase = 0;
+        int hslot = 0; uint32_t hphase = 0; int ws = 0; uint32_t wphase = 0;
         for (int ti = 0; ti < my_tiles; ++ti) {
             const int as = ti & 1;
-            mbar_wait(&acca_free[as], ((ti >> 1) & 1) ^ 1);
-            mbar_wait(&full_h[hslot], hphase);
-            tc_fence_after();
-            if (elect_one()) {
-                uint32_t a_lo = halo_lo + hslot * (HALO_BYTES >> 4);
-#pragma unroll
-                for (int tap = 0; tap < 9; ++tap) {
+            twait(&acca_free[as], ((ti >> 1) & 1) ^ 1, 0);
+            twait(&full_h[hslot], hphase, 1);
+            const uint32_t h_lo = halo_lo + hslot * (HALO_BYTES >> 4);
+#pragma unroll 1
+            for (int tap = 0, tr = 0, ts = 0; tap < 9; ++tap) {
+                twait(&full_w[ws], wphase, 2);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t a_lo = h_lo + (tr * HALO_PITCH + ts) * 8, b_lo = w2_lo + ws * 512;     // tap (r, s): the halo view shifted by (r, s) pixels
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        umma_bf16(tmem_base + TM_ACCA + as * 64, desc(a_lo + 2 * k, HI_HALO), desc(w2_lo + tap * 512 + 2 * k, HI_K), idesc_a, (tap | k) ? 1u : 0u);
-                    a_lo += (tap % 3 == 2) ? (HALO_PITCH - 2) * 8 : 8;
+                        umma_bf16(tmem_base + TM_ACCA + as * 64, desc(a_lo + 2 * k, HI_HALO), desc(b_lo + 2 * k, HI_K), idesc_a, (tap | k) ? 1u : 0u);
+                    umma_commit(&empty_w[ws]);
+                    if (tap == 8) { umma_commit(&empty_h[hslot]); umma_commit(&acca_full[as]); }
                 }
-                umma_commit(&empty_h[hslot]);
-                umma_commit(&acca_full[as]);
+                __syncwarp();
+                if (++ws == FB_WS) { ws = 0; wphase ^= 1; }
+                if (++ts == 3) { ts = 0; ++tr; }
             }
-            __syncwarp();
             if (++hslot == FB_HS) { hslot = 0; hphase ^= 1; }
             if (ti >= 1) issue_b(ti - 1);
         }
         if (my_tiles > 0) issue_b(my_tiles - 1);
-    } else if (warp >= 4 && warp < 8) {
-        // ===================== epilogue A: conv2 accumulator -> (+ shift, ReLU, bf16) -> intermediate in TMEM =====================
-        const int q = warp & 3;
+    } else if (warp >= 4) {
+        // ===================== epilogues (warps 4-11) =====================
+        const int q = warp & 3, grp = warp >= 8 ? 0 : 1, cc0 = grp * 2;          // epilogue-B channel chunks cc0, cc0 + 1 of every tile
         const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-        const float4* sh4 = reinterpret_cast<const float4*>(tab);
-        for (int ti = 0; ti < my_tiles; ++ti) {
-            const int as = ti & 1;
-            mbar_wait(&acca_full[as], (ti >> 1) & 1);
-            tc_fence_after();
-            float v[64];
-            tmem_ld32(lane_base + TM_ACCA + as * 64, v);
-            tmem_ld32(lane_base + TM_ACCA + as * 64 + 32, v + 32);
-            tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&acca_free[as]);
-            uint32_t pk[32];
-#pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                const float4 s4 = sh4[k];
-                asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(pk[2 * k]) : "f"(v[4 * k + 1] + s4.y), "f"(v[4 * k] + s4.x));
-                asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(pk[2 * k + 1]) : "f"(v[4 * k + 3] + s4.w), "f"(v[4 * k + 2] + s4.z));
-            }
-            mbar_wait(&t_free[as], ((ti >> 1) & 1) ^ 1);
-            tc_fence_after();
-            tmem_st32(lane_base + TM_T + as * 32, pk);
-            tmem_st_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&t_full[as]);
-        }
-    } else if (warp >= 8) {
-        // ===================== epilogue B: conv3 accumulator -> (+ shift, + residual, ReLU) in the warp's ring -> TMA store =====================
-        const int q = warp & 3;
-        uint8_t* myring = ring + q * FB_D * FB_SUB_BYTES;
-        uint64_t* myfull = res_full + q * FB_D;
+        // ---- epilogue B state: the TMA epilogue of convgemm.cuh, two 64-channel items per tile and warp
+        uint8_t* myring = ring + (grp * 4 + q) * FB_D * FB_SUB_BYTES;
+        uint64_t* myfull = res_full + (grp * 4 + q) * FB_D;
         const float4* bias4 = reinterpret_cast<const float4*>(tab + 64);
-        const int n_items = my_tiles * 4;
+        const int n_items = my_tiles * 2;
         const uint32_t rowoff = (uint32_t)lane * 128u, swz = (uint32_t)(lane & 7);
-        const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + TM_ACCB;
         auto coords = [&](int ti, int& img, int& ox0, int& row0) {
             const int t = blockIdx.x + ti * gridDim.x;
             img = t / p.tiles_per_img; const int rem = t - img * p.tiles_per_img;
             const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
             ox0 = tx * HALO_TW; row0 = ty * HALO_TH + q * 4;
         };
-        // residual prefetch cursor (lane 0)
-        int pf_j = 0, pf_cc = 0, pf_slot = 0, pf_ti = 0;
+        int pf_j = 0, pf_c = 0, pf_slot = 0, pf_ti = 0;                           // residual prefetch cursor (lane 0)
         auto request_next = [&]() {
             int img, ox0, row0; coords(pf_ti, img, ox0, row0);
             mbar_expect_tx(&myfull[pf_slot], FB_SUB_BYTES);
-            tma_load_4d(&mapR, &myfull[pf_slot], myring + pf_slot * FB_SUB_BYTES, pf_cc * 64, ox0, row0, img);
+            tma_load_4d(&mapR, &myfull[pf_slot], myring + pf_slot * FB_SUB_BYTES, (cc0 + pf_c) * 64, ox0, row0, img);
             ++pf_j; if (++pf_slot == FB_D) pf_slot = 0;
-            if (++pf_cc == 4) { pf_cc = 0; ++pf_ti; }
+            if (++pf_c == 2) { pf_c = 0; ++pf_ti; }
         };
         if (lane == 0)
             for (int i = 0; i < FB_D - 1 && i < n_items; ++i) request_next();
         int j = 0, slot = 0; uint32_t sphase = 0;
-        for (int ti = 0; ti < my_tiles; ++ti) {
+        auto epilogue_b = [&](int ti) {
             int img, ox0, row0; coords(ti, img, ox0, row0);
-            mbar_wait(accb_full, ti & 1);
+            twait(accb_full, ti & 1, 2);
             tc_fence_after();
 #pragma unroll 1
-            for (int cc = 0; cc < 4; ++cc, ++j) {
+            for (int c = 0; c < 2; ++c, ++j) {
+                const int cc = cc0 + c;
                 uint8_t* sl = myring + slot * FB_SUB_BYTES;
                 uint8_t* rowp = sl + rowoff;
                 float v[64];
-                tmem_ld32(tacc + cc * 64, v);
-                tmem_ld32(tacc + cc * 64 + 32, v + 32);
+                tmem_ld32(lane_base + TM_ACCB + cc * 64, v);
+                tmem_ld32(lane_base + TM_ACCB + cc * 64 + 32, v + 32);
                 uint4 r[8];
-                mbar_wait(&myfull[slot], sphase);
+                twait(&myfull[slot], sphase, 3);
 #pragma unroll
                 for (int k = 0; k < 8; ++k) r[k] = *reinterpret_cast<const uint4*>(rowp + ((k ^ swz) << 4));     // 128B swizzle: chunk ^ (row % 8)
                 tmem_ld_wait();
-                if (cc == 3) {                      // the accumulator is in registers: conv3 of the next tile may overwrite it
+                if (c == 1) {                       // this warp's share of the accumulator is in registers
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(accb_free);
@@ -267,8 +259,49 @@ bneck_l1_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 __syncwarp();
                 if (++slot == FB_D) { slot = 0; sphase ^= 1; }
             }
+        };
+        if (grp == 0) {
+            for (int ti = 0; ti < my_tiles; ++ti) epilogue_b(ti);
+        } else {
+            // ---- epilogue A: conv2 accumulator -> (+ shift, ReLU, bf16) -> intermediate in TMEM; then chunks 2, 3 of the previous tile
+            const float4* sh4 = reinterpret_cast<const float4*>(tab);
+            for (int ti = 0; ti < my_tiles; ++ti) {
+                const int as = ti & 1;
+                twait(&acca_full[as], (ti >> 1) & 1, 0);
+                tc_fence_after();
+                {
+                    float v[64];
+                    tmem_ld32(lane_base + TM_ACCA + as * 64, v);
+                    tmem_ld32(lane_base + TM_ACCA + as * 64 + 32, v + 32);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acca_free[as]);
+                    uint32_t pk[32];
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) {
+                        const float4 s4 = sh4[k];
+                        asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(pk[2 * k]) : "f"(v[4 * k + 1] + s4.y), "f"(v[4 * k] + s4.x));
+                        asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(pk[2 * k + 1]) : "f"(v[4 * k + 3] + s4.w), "f"(v[4 * k + 2] + s4.z));
+                    }
+                    twait(&t_free[as], ((ti >> 1) & 1) ^ 1, 1);
+                    tc_fence_after();
+                    tmem_st32(lane_base + TM_T + as * 32, pk);
+                    tmem_st_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&t_full[as]);
+                }
+                if (ti >= 1) epilogue_b(ti - 1);
+            }
+            if (my_tiles > 0) epilogue_b(my_tiles - 1);
         }
         if (lane == 0) bulk_wait_group_read<0>();
+    }
+    if (prof && blockIdx.x == 0 && lane == 0) {
+        if (warp == 1) printf("bneck prof mma: total %lld; waits acca_free %lld full_h %lld full_w %lld t_full %lld accb_free %lld\n", clock64() - pt0, pc[0], pc[1], pc[2], pc[3], pc[4]);
+        if (warp == 4) printf("bneck prof epiA+B(2,3): total %lld; waits acca_full %lld t_free %lld accb_full %lld residual %lld\n", clock64() - pt0, pc[0], pc[1], pc[2], pc[3]);
+        if (warp == 8) printf("bneck prof epiB(0,1): total %lld; waits accb_full %lld residual %lld (tiles %d)\n", clock64() - pt0, pc[2], pc[3], my_tiles);
     }
     __syncwarp();
     tc_fence_before();
@@ -290,6 +323,8 @@ inline int bneck_l1_launch(const bf16* in, const bf16* w2, const float* shift2, 
     FbParams kp;
     kp.batch = batch; kp.tiles_x = W / HALO_TW; kp.tiles_per_img = (H / HALO_TH) * kp.tiles_x; kp.total_tiles = batch * kp.tiles_per_img;
     kp.shift2 = shift2; kp.shift3 = shift3;
+    static const int prof_env = getenv("SQ_BNECK_PROF") ? atoi(getenv("SQ_BNECK_PROF")) : 0;
+    kp.prof = prof_env;
     CUtensorMap maps[5];
     {
         cuuint64_t dims[4] = {64, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)batch};
