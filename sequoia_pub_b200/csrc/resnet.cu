@@ -2,10 +2,12 @@
 // caller pre_processing/compute_features_hdf5.py:49-51,116-123).
 //
 // Data layout in HBM: activations NHWC bf16, weights [Cout][R][S][Cin] bf16 with the eval-mode BatchNorm scale
-// folded in, one fp32 shift per output channel.  Every convolution is one launch of the tcgen05 implicit-GEMM
-// kernel (gemm.cuh) whose epilogue applies shift + residual + ReLU.  The 7x7/2 stem goes through an im2col
-// buffer (K = 147 padded to 192) so it also runs on the tensor cores; uint8 -> /255 -> normalise is fused
-// into that im2col kernel (R4), max-pool and the 7x7 top-left average pool (fact 4) are small bandwidth kernels.
+// folded in, one fp32 shift per output channel.  Per batch (256-px tiles): `stem_tc_kernel` (this file: uint8 -> /255 -> normalise,
+// conv1 7x7/2, shift, ReLU, 3x3/2 max-pool on tcgen05; `stem_fused_kernel` for other tile sizes), then the 16 bottlenecks as
+// launches of `convgemm_kernel` (convgemm.cuh: CTA-pair tcgen05 implicit GEMM, epilogue = shift + residual + ReLU by TMA) with
+// layer 1's conv2 + conv3 as one `bneck_l1_kernel` (fusedconv.cuh); the top-left 7x7 average pool (fact 4) is fused into the last
+// convolution's epilogue.  The round-1 chain (im2col stem + gemm.cuh kernels, SQ_STEM_FUSED=0 / SQ_CONVGEMM=0) is kept for A/B runs;
+// the split-precision mode at the end of the file carries every tensor as bf16 hi / lo planes.
 #include "convgemm.cuh"
 #include "fusedconv.cuh"
 #include "../../include/sequoia_b200.h"
