@@ -549,25 +549,35 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem_tc_kernel(const void* __re
                 if (pf.item < nitems) { issue_copy(pf, (itn + S2_D - 1) % S2_D); advance_ng(pf); }
                 cp_async_commit();
                 // thread t converts bytes 6t+1 .. 6t+6 of both rows: three aligned bf16 pairs per row (staged index = byte + 9), channels
-                // (1,2) (0,1) (2,0) whatever t is; consecutive threads write words 3 apart (conflict-free)
+                // (1,2) (0,1) (2,0) whatever t is; consecutive threads write words 3 apart (conflict-free).  byte -> float through the
+                // 2^23 trick (one PRMT + one FADD on the FMA pipe instead of I2F on the quarter-rate conversion unit; same exact value),
+                // loads unconditional and both rows interleaved (rows outside the image are zeroed by a select)
                 const uint8_t* rp = raw_base + (itn % S2_D) * S2_RAW_BYTES + 6 * t;
                 uint32_t* sw = reinterpret_cast<uint32_t*>(stg) + 5 + 3 * t;
+                uint32_t b1[2], h2[2], h4[2], b6[2], b0[2];
+#pragma unroll
+                for (int row = 0; row < 2; ++row) {
+                    const uint8_t* r8 = rp + row * 768;
+                    b1[row] = r8[1]; h2[row] = *reinterpret_cast<const uint16_t*>(r8 + 2); h4[row] = *reinterpret_cast<const uint16_t*>(r8 + 4); b6[row] = r8[6];
+                    b0[row] = t == 0 ? r8[0] : 0u;
+                }
+                auto b2f = [](uint32_t x, uint32_t sel) { return __uint_as_float(__byte_perm(x, 0x4B000000u, sel)) - 8388608.0f; };   // 2^23 + byte, exact
 #pragma unroll
                 for (int row = 0; row < 2; ++row) {
                     const int iy = 2 * j - 1 + row;
-                    uint32_t w0 = 0u, w1 = 0u, w2 = 0u, we = 0u;
-                    if (iy >= 0 && iy < H) {
-                        const uint8_t* r8 = rp + row * 768;
-                        const uint32_t b1 = r8[1], h2 = *reinterpret_cast<const uint16_t*>(r8 + 2), h4 = *reinterpret_cast<const uint16_t*>(r8 + 4), b6 = r8[6];
-                        __nv_bfloat162 q0 = __floats2bfloat162_rn(fmaf((float)b1, na1, nb1), fmaf((float)(h2 & 255u), na2, nb2));
-                        __nv_bfloat162 q1 = __floats2bfloat162_rn(fmaf((float)(h2 >> 8), na0, nb0), fmaf((float)(h4 & 255u), na1, nb1));
-                        __nv_bfloat162 q2 = __floats2bfloat162_rn(fmaf((float)(h4 >> 8), na2, nb2), t == 127 ? 0.f : fmaf((float)b6, na0, nb0));
-                        w0 = *reinterpret_cast<uint32_t*>(&q0); w1 = *reinterpret_cast<uint32_t*>(&q1); w2 = *reinterpret_cast<uint32_t*>(&q2);
-                        if (t == 0) { __nv_bfloat162 qe = __floats2bfloat162_rn(0.f, fmaf((float)r8[0], na0, nb0)); we = *reinterpret_cast<uint32_t*>(&qe); }
-                    }
+                    const bool valid = iy >= 0 && iy < H;
+                    const float v1 = fmaf(b2f(b1[row], 0x7540u), na1, nb1), v2 = fmaf(b2f(h2[row], 0x7540u), na2, nb2), v3 = fmaf(b2f(h2[row], 0x7541u), na0, nb0);
+                    const float v4 = fmaf(b2f(h4[row], 0x7540u), na1, nb1), v5 = fmaf(b2f(h4[row], 0x7541u), na2, nb2);
+                    const float v6 = t == 127 ? 0.f : fmaf(b2f(b6[row], 0x7540u), na0, nb0);
+                    __nv_bfloat162 q0 = __floats2bfloat162_rn(v1, v2), q1 = __floats2bfloat162_rn(v3, v4), q2 = __floats2bfloat162_rn(v5, v6);
                     uint32_t* d = sw + row * (S2_STG_LD / 2);
-                    d[0] = w0; d[1] = w1; d[2] = w2;
-                    if (t == 0) d[-1] = we;                                  // staged values 8 (zero pad), 9 (byte 0)
+                    d[0] = valid ? *reinterpret_cast<uint32_t*>(&q0) : 0u;
+                    d[1] = valid ? *reinterpret_cast<uint32_t*>(&q1) : 0u;
+                    d[2] = valid ? *reinterpret_cast<uint32_t*>(&q2) : 0u;
+                    if (t == 0) {                                            // staged values 8 (zero pad), 9 (byte 0)
+                        __nv_bfloat162 qe = __floats2bfloat162_rn(0.f, fmaf(b2f(b0[row], 0x7540u), na0, nb0));
+                        d[-1] = valid ? *reinterpret_cast<uint32_t*>(&qe) : 0u;
+                    }
                 }
                 if (prof) { const long long tb1 = clock64(); cp_async_wait<S2_D - 2>(); const long long tb2 = clock64(); pc[2] += tb1 - tb0; pc[3] += tb2 - tb1; }
                 else
