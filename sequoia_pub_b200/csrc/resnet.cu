@@ -778,6 +778,12 @@ static int bneck_fuse_enabled() {
     return v;
 }
 
+static int bneck_ds_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SQ_BNECK_DS"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v;
+}
+
 static int convgemm_enabled() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("SQ_CONVGEMM"); v = (e && e[0] == '0') ? 0 : 1; }
@@ -949,14 +955,19 @@ int sq_resnet50_extract(const void* input, int input_kind, int batch, int H, int
             else if (run_conv(c2, wp, shifts, small_[0], batch, h1, w1, small_[1], nullptr, nullptr, true, st, &h2, &w2, nullptr, im2col, im2col_bytes)) return -1;
             const bf16* res = big[x];
             const int y = (x + 1) % 3, d = (x + 2) % 3;
-            if (down) {
+            // first block of layer 1: the downsample branch is computed inside the fused tail (no residual tensor at all); SQ_BNECK_DS=0 keeps its launch
+            const bool fuse_ds = fuse_tail && down && bneck_ds_enabled();
+            if (down && !fuse_ds) {
                 if (run_conv(p.conv[ci + 3], wp, shifts, big[x], batch, h, w, big[d], nullptr, nullptr, false, st, &hd, &wd, nullptr, im2col, im2col_bytes)) return -1;
                 res = big[d];
             }
             // the last convolution of an 8x8 final map feeds the fused average pool (no fp32 map, no pooling kernel)
             const bool fuse_pool = last && h2 == 8 && w2 == 8 && convgemm_enabled() && pool_fused_enabled();
             if (fuse_tail) {
-                if (bneck_l1_launch(small_[0], wp + c2.w_off, shifts + c2.s_off, wp + c3.w_off, shifts + c3.s_off, res, big[y], batch, h1, w1, st)) return -1;
+                const ConvSpec& cd = p.conv[ci + 3];
+                if (fuse_ds ? bneck_l1_ds_launch(small_[0], wp + c2.w_off, shifts + c2.s_off, wp + c3.w_off, shifts + c3.s_off, big[x], wp + cd.w_off, shifts + cd.s_off,
+                                                 big[y], batch, h1, w1, st)
+                            : bneck_l1_launch(small_[0], wp + c2.w_off, shifts + c2.s_off, wp + c3.w_off, shifts + c3.s_off, res, big[y], batch, h1, w1, st)) return -1;
                 h3 = h2; w3 = w2;
             } else
             if (fuse_pool) {

@@ -1,5 +1,5 @@
 """A/B of the fused layer-1 bottleneck tail (SQ_BNECK_FUSE=1, default) against the two separate launches (SQ_BNECK_FUSE=0):
-features must be bit-identical; batch time with 1 and 2 extractor lanes.  Each setting runs in its own process (the switch is read once)."""
+features must be bit-identical without the in-kernel downsample (SQ_BNECK_DS=0); batch time with 1 and 2 extractor lanes.  Each setting runs in its own process (the switch is read once)."""
 import hashlib, os, subprocess, sys
 
 if len(sys.argv) > 1 and sys.argv[1] == "child":
@@ -24,9 +24,11 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
         ms = s.elapsed_time(e) / 3
         print(f"lanes={lanes}: {ms / 16:.3f} ms/batch -> {1024 / ms * 1e3:.0f} patches/s")
 else:
-    for rep in range(2):
-        for v in ("0", "1"):
-            env = dict(os.environ, SQ_BNECK_FUSE=v)
+    # FUSE=1 DS=0 must reproduce FUSE=0 bit for bit; DS=1 (downsample inside the first block's tail) rounds the residual sum once
+    # instead of twice, so its features differ in the last bits (parity against the reference: tests/test_resnet_gpu.py)
+    for rep in range(int(os.environ.get("FUSE_AB_REPS", "2"))):
+        for fuse, ds in (("0", "0"), ("1", "0"), ("1", "1")):
+            env = dict(os.environ, SQ_BNECK_FUSE=fuse, SQ_BNECK_DS=ds)
             r = subprocess.run([sys.executable, os.path.abspath(__file__), "child"], env=env, capture_output=True, text=True, timeout=150)
-            print(f"== SQ_BNECK_FUSE={v} rc={r.returncode}")
+            print(f"== SQ_BNECK_FUSE={fuse} SQ_BNECK_DS={ds} rc={r.returncode}")
             print((r.stdout + r.stderr[-1500:]).strip())
