@@ -583,7 +583,7 @@ def main():
     feats = torch.empty(PATCHES_PER_SLIDE, 2048, dtype=torch.float32, device=dev)
     fused_stem = os.environ.get("SQ_STEM_FUSED", "1") != "0"     # one kernel for preprocessing + conv1 + max-pool (csrc/resnet.cu)
     # per batch of 64: the fused stem + 52 bottleneck convolutions (the 7x7 average pool is fused into the last one); layer 1's conv2 + conv3
-    # run as ONE kernel per block (csrc/fusedconv.cuh), i.e. 49 convolution launches
+    # run as ONE kernel per block (csrc/fusedconv.cuh), the first block's downsample inside it: 48 convolution launches
     fused_tail = os.environ.get("SQ_BNECK_FUSE", "1") != "0" and os.environ.get("SQ_CONVGEMM", "1") != "0"
     fused_ds = fused_tail and os.environ.get("SQ_BNECK_DS", "1") != "0"     # the first block's downsample runs inside its fused tail
     launches_per_step = (PATCHES_PER_SLIDE // BATCH) * (L.sq_resnet50_num_convs() + (0 if fused_stem else 3) - (3 if fused_tail else 0) - (1 if fused_ds else 0))

@@ -152,6 +152,11 @@ SQ_API int sq_conv_bf16(const sq_conv_desc* desc, void* stream);
  * are bit-identical to sq_conv_bf16 called twice.  Building block of sq_resnet50_extract, exposed for tests. */
 SQ_API int sq_bneck_l1_bf16(const void* in, const void* w2, const float* shift2, const void* w3, const float* shift3, const void* residual,
                             void* out, int batch, int H, int W, void* stream);
+/* The same tail for the FIRST block of the layer: the downsample branch is computed inside the kernel,
+ *   out = relu(conv1x1(relu(conv3x3(in, w2) + shift2), w3) + shift3 + conv1x1(x, wds) + shiftds)
+ * x: NHWC bf16 [batch, H, W, 64] (the block input), wds: bf16 [256][64].  The residual sum is formed in fp32 and rounded once. */
+SQ_API int sq_bneck_l1_ds_bf16(const void* in, const void* w2, const float* shift2, const void* w3, const float* shift3, const void* x,
+                               const void* wds, const float* shiftds, void* out, int batch, int H, int W, void* stream);
 
 /* ------------------------------------------------------------------ ViS aggregator (SummaryMixing transformer)
  * Replaces ViS.forward (src/tformer_lin.py:97-106 and everything it calls, :18-26,39-48,60-61,73-77), the autograd

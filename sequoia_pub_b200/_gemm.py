@@ -93,3 +93,15 @@ def bneck_l1_bf16(x, w2, shift2, w3, shift3, residual, out=None):
                                            C.c_void_p(shift3.data_ptr()), C.c_void_p(residual.data_ptr()), C.c_void_p(out.data_ptr()), B, H, W,
                                            _lib.stream_ptr()))
     return out
+
+
+def bneck_l1_ds_bf16(x1, w2, shift2, w3, shift3, x, wds, shiftds, out=None):
+    """First-block variant through `sq_bneck_l1_ds_bf16`: x1 = conv1's output [B,H,W,64], x = the block input [B,H,W,64], wds bf16 [256,64]
+    -> relu(conv1x1(relu(conv3x3(x1) + shift2)) + shift3 + conv1x1(x, wds) + shiftds), the downsample computed inside the kernel."""
+    B, H, W, _ = x1.shape
+    if out is None:
+        out = torch.empty(B, H, W, 256, dtype=torch.bfloat16, device=x1.device)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    _lib.check(_lib.lib().sq_bneck_l1_ds_bf16(p(x1), p(w2), p(shift2), p(w3), p(shift3), p(x), p(wds), p(shiftds), p(out), B, H, W, _lib.stream_ptr()))
+    return out
+

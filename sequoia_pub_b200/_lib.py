@@ -72,6 +72,7 @@ SIGNATURES = {
     "sq_gemm_bf16": (c_int, [C.POINTER(GemmDesc), c_void_p]),
     "sq_conv_bf16": (c_int, [C.POINTER(ConvDesc), c_void_p]),
     "sq_bneck_l1_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "sq_bneck_l1_ds_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "sq_resnet50_num_convs": (c_int, []),
     "sq_resnet50_conv_info": (c_int, [c_int] + [C.POINTER(c_int)] * 5),
     "sq_resnet50_packed_weight_elems": (c_ll, []),

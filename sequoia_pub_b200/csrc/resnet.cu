@@ -886,6 +886,16 @@ int sq_bneck_l1_bf16(const void* in, const void* w2, const float* shift2, const 
     return bneck_l1_launch((const bf16*)in, (const bf16*)w2, shift2, (const bf16*)w3, shift3, (const bf16*)residual, (bf16*)out, batch, H, W, (cudaStream_t)stream);
 }
 
+int sq_bneck_l1_ds_bf16(const void* in, const void* w2, const float* shift2, const void* w3, const float* shift3, const void* x, const void* wds,
+                        const float* shiftds, void* out, int batch, int H, int W, void* stream) {
+    if (!in || !w2 || !shift2 || !w3 || !shift3 || !x || !wds || !shiftds || !out) { set_error("bneck_l1_ds: null pointer"); return -1; }
+    if (batch <= 0 || !bneck_l1_supported(H, W)) { set_error("bneck_l1_ds: H must be a multiple of %d and W of %d", HALO_TH, HALO_TW); return -1; }
+    if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(w2) | reinterpret_cast<uintptr_t>(w3) | reinterpret_cast<uintptr_t>(x) |
+         reinterpret_cast<uintptr_t>(wds) | reinterpret_cast<uintptr_t>(out)) & 15) { set_error("bneck_l1_ds: operands must be 16-byte aligned"); return -1; }
+    return bneck_l1_ds_launch((const bf16*)in, (const bf16*)w2, shift2, (const bf16*)w3, shift3, (const bf16*)x, (const bf16*)wds, shiftds, (bf16*)out, batch, H, W,
+                              (cudaStream_t)stream);
+}
+
 size_t sq_resnet50_workspace_bytes(int batch, int H, int W) { return ws_layout(batch, H, W).total; }
 
 int sq_resnet50_extract(const void* input, int input_kind, int batch, int H, int W, const void* packed_w, const float* shifts,

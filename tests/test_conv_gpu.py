@@ -132,3 +132,32 @@ def test_fused_layer1_tail_rejects_untiled_maps():
     with pytest.raises(RuntimeError):
         gm.bneck_l1_bf16(x, w2, s2, w3, s3, r)
 
+
+@pytest.mark.parametrize("B,H,W", [(2, 64, 64), (1, 16, 8), (3, 32, 24)])
+def test_fused_layer1_first_block_with_downsample_matches_reference(B, H, W):
+    """`sq_bneck_l1_ds_bf16`: the downsample branch (1x1, 64 -> 256 on the block input) is computed inside the fused tail, so the residual sum
+    is formed in fp32 and rounded once.  Reference: torch fp64 on the bf16-rounded operands with the bf16 intermediate (src/resnet.py:73-93,
+    downsample = conv1x1 + bn without ReLU); it must also agree with the two-launch path up to the extra rounding of the residual."""
+    gm = _gm()
+    g = torch.Generator(device="cuda").manual_seed(7000 + B * 100 + H + W)
+    x = torch.randn(B, H, W, 64, device="cuda", generator=g).relu().to(torch.bfloat16)            # block input
+    x1 = torch.randn(B, H, W, 64, device="cuda", generator=g).relu().to(torch.bfloat16)           # conv1's output
+    w2 = (torch.randn(64, 3, 3, 64, device="cuda", generator=g) * (1.0 / 576 ** 0.5)).to(torch.bfloat16)
+    w3 = (torch.randn(256, 1, 1, 64, device="cuda", generator=g) * (1.0 / 8.0)).to(torch.bfloat16)
+    wds = (torch.randn(256, 1, 1, 64, device="cuda", generator=g) * (1.0 / 8.0)).to(torch.bfloat16)
+    s2 = torch.randn(64, device="cuda", generator=g) * 0.5
+    s3 = torch.randn(256, device="cuda", generator=g) * 0.5
+    sds = torch.randn(256, device="cuda", generator=g) * 0.5
+    out = torch.full((B, H, W, 256), float("nan"), device="cuda", dtype=torch.bfloat16)
+    gm.bneck_l1_ds_bf16(x1, w2, s2, w3, s3, x, wds, sds, out=out)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all()
+    mid = (F.conv2d(x1.double().permute(0, 3, 1, 2), w2.double().permute(0, 3, 1, 2), padding=1).permute(0, 2, 3, 1) + s2.double()).clamp_min(0)
+    mid = mid.to(torch.bfloat16).double()
+    ref = (mid @ w3.double().reshape(256, 64).t() + s3.double() + x.double() @ wds.double().reshape(256, 64).t() + sds.double()).clamp_min(0)
+    scale = ref.abs().max().item()
+    assert (out.double() - ref).abs().max().item() / scale < 6e-3
+    res = gm.conv_bf16(x, wds, sds, None, False, 1, 0)                                            # two-launch path: residual rounded to bf16 first
+    two = gm.bneck_l1_bf16(x1, w2, s2, w3, s3, res)
+    assert (out.double() - two.double()).abs().max().item() / scale < 1.2e-2
+

@@ -24,13 +24,15 @@ recs = json.load(open(path))
 stem = [r for r in recs if "stem" in r["kernel"]]
 convs = [r for r in recs if "convgemm" in r["kernel"] or "gemm_tc" in r["kernel"] or "bneck" in r["kernel"]]
 if any("bneck" in r["kernel"] for r in convs):
-    # layer 1's conv2 + conv3 run as one kernel (csrc/fusedconv.cuh): one table row "c23" per block, launched after the downsample
+    # layer 1's conv2 + conv3 run as one kernel (csrc/fusedconv.cuh): one table row "c23" per block; in the first block the downsample
+    # runs inside it as well ("c23d", no residual tensor) when the list has one launch less
+    with_ds = len(convs) == len(order) - 4
     merged = []
     for e in order:
         st, b, n, c = e
-        if st == 1 and n == "c2":
+        if st == 1 and (n == "c2" or (with_ds and n == "ds")):
             continue
-        merged.append((st, b, "c23", c) if st == 1 and n == "c3" else e)
+        merged.append((st, b, "c23d" if with_ds and b == 0 else "c23", c) if st == 1 and n == "c3" else e)
     order = merged
 assert len(convs) == len(order), (len(convs), len(order))
 tot = ideal_tot = 0.0
@@ -43,10 +45,13 @@ for (st, b, n, (cin, cout, k, Hi, Ho)), r in zip(order, convs):
     if n == "c23":                       # 3x3 64 -> 64 then 1x1 64 -> 256 + residual: the 64-channel intermediate never reaches HBM
         gf = (2 * M * 64 * 576 + 2 * M * 256 * 64) / 1e9
         mb = (M * 64 * 2 + 2 * M * 256 * 2 + (64 * 576 + 256 * 64) * 2) / 1e6
+    if n == "c23d":                      # first block: + downsample(x) inside the kernel, no residual read
+        gf = (2 * M * 64 * 576 + 2 * 2 * M * 256 * 64) / 1e9
+        mb = (2 * M * 64 * 2 + M * 256 * 2 + (64 * 576 + 2 * 256 * 64) * 2) / 1e6
     floor = max(mb / PEAK_GBS * 1e3, gf / PEAK_TF * 1e3)
     tot += t
     ideal_tot += floor
-    print(f"L{st}.b{b}.{n:3s} {cin:5d} {cout:5d} {k}  {Hi:3d}->{Ho:3d} {M:8d} {gf:6.1f} {t:8.1f} {gf / t * 1e3:5.0f} {r['dram_rd_MB'] + r['dram_wr_MB']:8.1f} "
+    print(f"L{st}.b{b}.{n:4s}{cin:5d} {cout:5d} {k}  {Hi:3d}->{Ho:3d} {M:8d} {gf:6.1f} {t:8.1f} {gf / t * 1e3:5.0f} {r['dram_rd_MB'] + r['dram_wr_MB']:8.1f} "
           f"{r['l2_to_sm_MB']:9.1f} {mb:6.1f} {floor:9.1f} {t / floor:8.1f} {r['tensor_pct']:8.1f}  {r['kernel'].replace('void ', '')}")
 print(f"sum of measured {tot:.0f} us, sum of floors {ideal_tot:.0f} us, ratio {tot / ideal_tot:.2f} (ncu durations are cold-cache and serialised: "
       f"the un-profiled chain overlaps through programmatic dependent launch)")

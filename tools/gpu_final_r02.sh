@@ -15,9 +15,9 @@ full() { name=$1; k=$2; s=$3; shift 3
   ncu -i /tmp/ncu/$name.ncu-rep --page raw --csv > gpurun_out/$name.raw.csv 2>/dev/null
   ncu -i /tmp/ncu/$name.ncu-rep --page details > gpurun_out/$name.details.txt 2>/dev/null
   grep -E "Duration|DRAM Throughput|Memory Throughput  " gpurun_out/$name.details.txt | head -3; }
-met r02_resnet_batch64_metrics_final "stem|convgemm|bneck|avgpool|maxpool" 50 50 python tools/profile_resnet.py 2      # second batch: stem + 49 convolution launches (layer 1's conv2 + conv3 are one kernel)
-full r02_full_stem_tc "stem_tc" 1 python tools/profile_resnet.py 2
+met r02_resnet_batch64_metrics_final "stem|convgemm|bneck|avgpool|maxpool" 49 49 python tools/profile_resnet.py 2      # second batch: stem + 48 convolution launches (layer 1: conv2 + conv3 [+ downsample] are one kernel)
 full r02_full_bneck_l1 "bneck_l1" 4 python tools/profile_resnet.py 2
+full r02_full_bneck_l1_ds "bneck_l1" 3 python tools/profile_resnet.py 2
 python tools/traffic_json.py gpurun_out/r02_resnet_batch64_metrics_final.json profiles/r02_traffic.json
 cp profiles/r02_traffic.json gpurun_out/r02_traffic.json
 timeout 600 python bench.py > gpurun_out/r02_bench_n1_final.json 2> gpurun_out/r02_bench_n1_final.err; echo "bench rc=$?"; head -c 600 gpurun_out/r02_bench_n1_final.json; echo
